@@ -1,0 +1,168 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden
+
+Every fixture stores the seed, the call arguments and the reference's outputs.  The
+tests replay the same seeded call sequence through ``oracle/matriseq_port.py`` (which
+must reproduce the outputs bit for bit) and through the CUDA path (supplied-noise
+mode, noise recorded from the seeded port run).  Environment the fixtures were made
+with: python 3.12.3, numpy 2.3.5 (legacy RandomState streams are frozen by NEP 19).
+"""
+import os
+import random
+import sys
+
+import numpy as np
+
+from oracle import reference_harness as rh
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def seed_all(ms, seed):
+    ms.init(outputDir=None, seed=seed, verbose=False)
+
+
+def csr_triplets(gc):
+    r, c = np.nonzero(gc)
+    return r.astype(np.int32), c.astype(np.int32), gc[r, c]
+
+
+def case_networks(ms):
+    out = {}
+    seed_all(ms, 11)
+    gc, tf = ms.generateGeneCorrelationMatrix(60, "SimulatedPowerLaw", powerLawExponent=2.5)
+    out["pl_gc"], out["pl_tf"] = gc, tf
+    seed_all(ms, 12)
+    gc, tf = ms.generateGeneCorrelationMatrix(50, "Random", networkSparsity=0.9, normalizeWRows=True)
+    out["rnd_gc"], out["rnd_tf"] = gc, tf
+    seed_all(ms, 13)
+    gc, tf = ms.generateGeneCorrelationMatrix(5, "TRRUST", maxAlphaBeta=6)
+    r, c, v = csr_triplets(gc)
+    out["tr_n"] = np.int64(gc.shape[0])
+    out["tr_rows"], out["tr_cols"], out["tr_vals"], out["tr_tf"] = r, c, v, tf
+    np.savez_compressed(os.path.join(OUT, "networks.npz"), **out)
+
+
+def case_step(ms):
+    """developCell (MS:503-537) one step, non-trivial proj/const/mu; noise recorded."""
+    seed_all(ms, 21)
+    n = 48
+    gc, tf = ms.generateGeneCorrelationMatrix(n, "Random", networkSparsity=0.7)
+    gc = gc / 0.5
+    x0 = 2 * np.random.rand(n) - 1 + 0.3
+    proj = (np.random.rand(n) > 0.2).astype(float)
+    const = np.where(proj == 0, np.sign(np.random.rand(n) - 0.5), 0.0)
+    st = np.random.get_state()
+    noise = np.random.normal(loc=0, scale=0.05, size=n)       # what developCell will draw next
+    np.random.set_state(st)
+    x1 = ms.developCell(n, gc, 0.01, x0, proj, const, 0.05, 0.3)
+    np.savez_compressed(os.path.join(OUT, "step.npz"), gc=gc, x0=x0, proj=proj, const=const,
+                        noise=noise, x1=x1, dt=0.01, sigma=0.05, mu=0.3)
+
+
+def case_cellsteps(ms):
+    """findCellNextState (MS:683-736): 40 steps of one cell at gain 50 (alpha 0.02)."""
+    seed_all(ms, 31)
+    n = 96
+    gc, tf = ms.generateGeneCorrelationMatrix(n, "SimulatedPowerLaw")
+    gc = gc / 0.02
+    x0 = 2 * np.random.rand(n) - 1
+    proj = np.ones(n); const = np.zeros(n)
+    proj[tf[:5]] = 0; const[tf[:5]] = [1, -1, 1, 1, -1]
+    steps = 40
+    st = np.random.get_state()
+    np.random.uniform()                                       # MS:707
+    noise = np.stack([np.random.normal(loc=0, scale=0.05, size=n) for _ in range(steps)])
+    np.random.set_state(st)
+    xT = ms.findCellNextState(gc, n, 0.01, 0, proj, const, x0, steps, 0.05, 0, False)
+    np.savez_compressed(os.path.join(OUT, "cellsteps.npz"), gc=gc, x0=x0, proj=proj, const=const,
+                        noise=noise, xT=xT, steps=steps, dt=0.01, sigma=0.05)
+
+
+def case_probe(ms):
+    """findOptimalIterations (MS:616-680) with small limits."""
+    seed_all(ms, 41)
+    n, cells = 64, 12
+    gc, tf = ms.generateGeneCorrelationMatrix(n, "SimulatedPowerLaw")
+    gc = gc / 0.3
+    states = 2 * np.random.rand(n, cells) - 1
+    proj = np.ones(n); const = np.zeros(n)
+    members = list(range(1, cells))
+    T = ms.findOptimalIterations(n, gc, 0.01, members, proj, const, 0, 0.35, 0.05, states, 120, 8, 6)
+    np.savez_compressed(os.path.join(OUT, "probe.npz"), gc=gc, states=states, proj=proj, const=const,
+                        members=np.array(members), T=T, seed=41, thresh=0.35, maxIter=120, avgNum=8,
+                        numToSample=6)
+
+
+def case_pipeline(ms):
+    """The example.py call sequence (EX:7-85) at small size: 3 types, 56+50+60 cells."""
+    seed_all(ms, 1337)
+    n, cells = 40, 166
+    gc, tf = ms.generateGeneCorrelationMatrix(n, "SimulatedPowerLaw", powerLawExponent=2.3)
+    tree, projM, constM = ms.formCellTypeTree(n, cells, [-1, 0, 0], [56, 50, 60], [0.1, 0.15, 0.2],
+                                              tf, [0, 0, 0])
+    init = ms.generateInitialStates(n, cells)
+    alpha_log_states = init.copy()
+    alpha = ms.findOptimalAlpha(n, gc, tree, init, numToSample=10, maxNumIterations=120,
+                                convDistAvgNum=10, convergenceThreshold=0.3)
+    gc_unscaled = gc.copy()
+    gc = gc / alpha
+    states = init
+    types = np.zeros(cells, dtype="int64")
+    iters = np.zeros(cells, dtype="int64")
+    ms.findAllNextStates(gc, tree.head(), tree, states, types, iters)
+    final_states = states.copy()
+    counts, size = ms.transformData(n, cells, states)
+    members = {str(t): np.array(tree[t].cellTypeMembers) for t in range(3)}
+    np.savez_compressed(os.path.join(OUT, "pipeline.npz"), gc_unscaled=gc_unscaled, tf=tf, projM=projM,
+                        constM=constM, init=alpha_log_states, alpha=alpha, final_states=final_states,
+                        types=types, iters=iters, counts=counts, size=size,
+                        members0=members["0"], members1=members["1"], members2=members["2"],
+                        head_children=np.array(tree.head().children),
+                        child_members0=np.array(tree[0].childCellTypeMembers))
+
+
+def case_transform_alt(ms):
+    """transformData (MS:816-891), gammaDistMean=False branch and expScale != 1."""
+    seed_all(ms, 51)
+    n, cells = 20, 15
+    S = np.tanh(np.random.normal(size=(n, cells)))
+    c1, s1 = ms.transformData(n, cells, S.copy(), expScale=4.0, cellRadiusDisp=0.3)
+    c2, s2 = ms.transformData(n, cells, S.copy(), gammaDistMean=False, geneScale=1.5, expLambda=0.7)
+    np.savez_compressed(os.path.join(OUT, "transform_alt.npz"), S=S, c1=c1, s1=s1, c2=c2, s2=s2)
+
+
+def case_poisson_mode(ms):
+    """findAllNextStates with cellDevelopmentMode=False at the head's only child (quirk R1:
+    kwargs reach only the node the user passes)."""
+    seed_all(ms, 61)
+    n, cells = 24, 52
+    gc, tf = ms.generateGeneCorrelationMatrix(n, "Random", networkSparsity=0.8)
+    gc = gc / 1.5
+    tree, projM, constM = ms.formCellTypeTree(n, cells, [-1], [52], [0.0], tf, [0])
+    states = ms.generateInitialStates(n, cells, sameInitialCell=False)
+    init = states.copy()
+    types = np.zeros(cells, dtype="int64"); iters = np.zeros(cells, dtype="int64")
+    ms.findAllNextStates(gc, tree[0], tree, states, types, iters, cellDevelopmentMode=False,
+                         maxNumIterations=90, convDistAvgNum=6, cellsToSample=7,
+                         convergenceThreshold=0.4, noiseDisp=0.02, timeStep=0.05)
+    np.savez_compressed(os.path.join(OUT, "poisson_mode.npz"), gc=gc, init=init, final=states,
+                        types=types, iters=iters)
+
+
+def main():
+    if not rh.available():
+        sys.exit("reference not available; fixtures can only be regenerated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    ms = rh.load_reference()
+    for fn in (case_networks, case_step, case_cellsteps, case_probe, case_pipeline,
+               case_transform_alt, case_poisson_mode):
+        fn(ms)
+        print("wrote", fn.__name__)
+
+
+if __name__ == "__main__":
+    main()
