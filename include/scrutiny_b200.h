@@ -1,0 +1,136 @@
+/* scrutiny_b200 -- C ABI of the B200-native MatriSeq simulation hot path.
+ *
+ * The reference (steffen12/scRutiNy) is pure Python/numpy and has no FFI; its boundary for this
+ * path is the module-level function surface of RNAscrutiny/RNAscrutiny/MatriSeq.py (cited "MS").
+ * Each entry point below names the reference function it replaces.  The Python mirror of that
+ * surface lives in scrutiny_b200/MatriSeq.py and binds these symbols with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success or a negative SCR_E_*
+ *     code and never throws; scr_last_error(ctx) gives the message for the last failure.
+ *   - one context per GPU; a context is NOT thread-safe; calls are synchronous on return unless
+ *     stated otherwise (the work is enqueued on the context's own CUDA stream).
+ *   - host matrices use the reference's layout: float64, (genes, cells) C-order, `ld` = row
+ *     stride in elements (MS:340-365 builds them that way).  Device state is cell-major, in the
+ *     context's precision (float32 throughput path or float64 parity path), gene order permuted
+ *     internally (DESIGN.md "Data layout").
+ *   - cells are addressed by LOCAL slot 0..C-1; the global id (cell_offset + slot) keys the
+ *     counter-based RNG so results do not depend on how cells are sharded over GPUs.
+ *   - there is no CPU fallback: without a CUDA device scr_create fails with SCR_E_CUDA.
+ */
+#ifndef SCRUTINY_B200_H
+#define SCRUTINY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scr_ctx scr_ctx;
+
+enum {
+  SCR_OK = 0,
+  SCR_E_ARG = -1,      /* bad argument                                           */
+  SCR_E_CUDA = -2,     /* CUDA runtime error (message in scr_last_error)          */
+  SCR_E_STATE = -3,    /* call order: network / cells not set yet                 */
+  SCR_E_RESOURCE = -4, /* problem does not fit the kernel's on-chip budget        */
+  SCR_E_DRAWS = -5     /* supplied uniforms exhausted in scr_counts               */
+};
+
+enum { SCR_F32 = 0, SCR_F64 = 1 };
+
+/* RNG stream ids (mixed into the Philox key) */
+enum { SCR_STREAM_STEP = 0, SCR_STREAM_PROBE = 1, SCR_STREAM_COUNTS = 2, SCR_STREAM_ALPHA = 16 };
+
+int scr_abi_version(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+int scr_create(scr_ctx** out, int device_ordinal, int precision /* SCR_F32 | SCR_F64 */);
+void scr_destroy(scr_ctx* ctx);
+const char* scr_last_error(const scr_ctx* ctx); /* ctx may be NULL: last create error */
+int scr_sync(scr_ctx* ctx);
+
+/* ---- regulatory network: the `gc` argument of developCell (MS:503-504), already divided by
+ * alpha (EX:49).  CSR over rows = regulated gene.  Builds the on-chip operator (gene
+ * permutation, sliced-ELL tiles, long-row chunks).  Any density is accepted. */
+int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* rowptr,
+                        const int32_t* col, const double* val);
+/* same from a dense row-major (n, n) float64 matrix (what the reference passes around) */
+int scr_set_network_dense(scr_ctx* ctx, int32_t n, const double* gc_rowmajor);
+
+/* Test hook, host only (no GPU work): y = W x computed by walking the SAME packed operator the
+ * kernels read (internal order, tiles, chunks), so packing bugs show up in the CPU test-suite. */
+int scr_debug_host_matvec(const scr_ctx* ctx, const double* x, double* y);
+/* Layout facts for DESIGN.md / tests: out[0]=n_pad, [1]=ping-pong genes, [2]=tile slots,
+ * [3]=long-row chunks, [4]=chunk length, [5]=row cap, [6]=warps per cell group,
+ * [7]=cell groups per CTA, [8]=dynamic smem bytes, [9]=operator resident in smem (0/1),
+ * [10]=cells per group, [11]=CTAs per SM. */
+int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count);
+
+/* ---- cell states: `currentStates` of findAllNextStates (MS:540-554) --------------------------- */
+int scr_alloc_cells(scr_ctx* ctx, int64_t cells, int64_t global_cell_offset);
+int scr_set_states(scr_ctx* ctx, int64_t cell0, int64_t count, const double* S_genes_by_cells,
+                   int64_t ld);
+/* every cell <- x0 (generateInitialStates(sameInitialCell=True), MS:360-361) */
+int scr_set_states_broadcast(scr_ctx* ctx, const double* x0 /* n */);
+int scr_get_states(scr_ctx* ctx, int64_t cell0, int64_t count, double* S_genes_by_cells,
+                   int64_t ld);
+
+/* ---- stepping: replaces the two per-cell loops of findAllNextStates (MS:587-605), i.e.
+ * findCellNextState (MS:683-736) x developCell (MS:503-537), for one lineage node.
+ *   cell_ids[m]  local slots (each at most once);  steps[m]  iterations for that cell (ragged);
+ *   step_base[m] iterations the cell has already done (totalCellIterations, keys the noise);
+ *   proj, cnst   the node's vectors (n);  dt, sigma, mu = timeStep, noiseDisp, geneMeanLevels.
+ *   noise        NULL -> free-running Philox noise keyed (seed, global cell, step, gene);
+ *                else float64 (m, noise_steps, n): noise[i][s][g] is ADDED inside tanh at local
+ *                step s of cell_ids[i] (already scaled by sigma) -- the parity mode. */
+int scr_run_phase(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t* steps,
+                  const int64_t* step_base, const double* proj, const double* cnst, double dt,
+                  double sigma, double mu, uint64_t seed, const double* noise, int64_t noise_steps);
+
+/* ---- convergence probe: the sampled-cell loop of findOptimalIterations (MS:650-669) and of
+ * findOptimalAlpha (MS:456-482).  Steps COPIES of the k sampled cells until the mean of the last
+ * avg_num values of mean|dx|/dt is <= thresh or max_iter is reached; states are not modified.
+ *   w_div[k] or NULL: per-sample divisor of the network (the alpha ladder, MS:461);
+ *   iters_out[k]: iterations executed;  normdiff_out (k, max_iter) float64 or NULL: trace. */
+int scr_probe(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_div,
+              const double* proj, const double* cnst, double dt, double sigma, double mu,
+              double thresh, int32_t max_iter, int32_t avg_num, uint64_t seed, uint32_t stream,
+              const double* noise /* (k, max_iter, n) or NULL */, int32_t* iters_out,
+              double* normdiff_out);
+
+/* ---- read-out: transformData (MS:816-891) --------------------------------------------------- */
+/* per-gene SUM over this context's cells (MS:851 needs the mean over ALL cells: all-reduce
+ * these n doubles across ranks, divide by the global cell count). */
+int scr_gene_sums(scr_ctx* ctx, double* sums_out /* n */);
+/* counts[c][g] = Poisson(max(exp(exp_scale*(x[c][g]+shift[g])) * size[c], 0))   (MS:873-885)
+ *   uniforms NULL -> Philox uniforms keyed (seed, global cell, gene, draw);
+ *            else float64 (cells, n, draws_per_entry) consumed in order per entry.
+ *   counts_out: int32 (cells, n) row-major, host or device memory (out_on_device);
+ *   lambda_out: float64 (cells, n) HOST buffer or NULL (parity aid). */
+int scr_counts(scr_ctx* ctx, const double* shift /* n */, double exp_scale,
+               const double* size_factors /* cells */, uint64_t seed, const double* uniforms,
+               int32_t draws_per_entry, int32_t* counts_out, int out_on_device, double* lambda_out);
+
+/* ---- debugging / parity aids ------------------------------------------------------------------ */
+/* raw Philox4x32-10 words for counters (c0..c3)[count] under key (k0,k1): device generator check */
+int scr_debug_philox(scr_ctx* ctx, int64_t count, const uint32_t* ctr4, uint32_t k0, uint32_t k1,
+                     uint32_t* out4);
+/* the noise the free-running stepper adds for (global cell, step) -> out[n] float64 */
+int scr_debug_noise(scr_ctx* ctx, int64_t global_cell, uint32_t step, double sigma, uint64_t seed,
+                    uint32_t stream, double* out /* n */);
+/* kernel launches issued by this context so far (bench.py reports gpu_launches) */
+int64_t scr_launch_count(const scr_ctx* ctx);
+/* device-time of the last scr_run_phase stepping kernel in milliseconds (CUDA events on the
+ * context's stream); < 0 if none yet */
+double scr_last_kernel_ms(const scr_ctx* ctx);
+/* accumulated device time (ms) and number of scr_run_phase stepping-kernel launches since the
+ * last reset; bench.py derives roofline.achieved from these */
+int scr_step_kernel_stats(scr_ctx* ctx, double* total_ms, int64_t* launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCRUTINY_B200_H */

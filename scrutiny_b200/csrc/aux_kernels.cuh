@@ -1,0 +1,177 @@
+// Layout, reduction, read-out and debug kernels (sm_100a).
+//   * pack/unpack between the reference's (genes, cells) float64 host layout and the cell-major,
+//     gene-permuted device state (MatriSeq.py:340-365 builds the former);
+//   * per-gene sums for transformData's gene means (MatriSeq.py:851);
+//   * the count read-out exp -> size factor -> clamp -> Poisson (MatriSeq.py:873-885).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "step_kernel.cuh"
+
+namespace scr {
+
+// staging (n x cnt, row-major float64, original gene order) -> state[(cell0+c)][internal gene]
+template <typename T>
+__global__ void pack_states_kernel(const double* __restrict__ stage, int64_t cnt, T* __restrict__ state,
+                                   int64_t ld, int64_t cell0, const int* __restrict__ perm, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // internal gene
+  if (i >= n_pad) return;
+  const int o = perm[i];
+  for (int64_t c = blockIdx.y; c < cnt; c += gridDim.y)
+    state[(cell0 + c) * ld + i] = o >= 0 ? static_cast<T>(stage[static_cast<int64_t>(o) * cnt + c]) : T(0);
+}
+
+template <typename T>
+__global__ void unpack_states_kernel(double* __restrict__ stage, int64_t cnt, const T* __restrict__ state,
+                                     int64_t ld, int64_t cell0, const int* __restrict__ perm, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  const int o = perm[i];
+  if (o < 0) return;
+  for (int64_t c = blockIdx.y; c < cnt; c += gridDim.y)
+    stage[static_cast<int64_t>(o) * cnt + c] = static_cast<double>(state[(cell0 + c) * ld + i]);
+}
+
+template <typename T>
+__global__ void broadcast_state_kernel(const double* __restrict__ x0, T* __restrict__ state, int64_t ld,
+                                       int64_t cells, const int* __restrict__ perm, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  const int o = perm[i];
+  const T v = o >= 0 ? static_cast<T>(x0[o]) : T(0);
+  for (int64_t c = blockIdx.y; c < cells; c += gridDim.y) state[c * ld + i] = v;
+}
+
+// sums[internal gene] += sum over this block's cells (float64 accumulation)
+template <typename T>
+__global__ void gene_sums_kernel(const T* __restrict__ state, int64_t ld, int64_t cells, int n_pad,
+                                 double* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  double acc = 0.0;
+  for (int64_t c = blockIdx.y; c < cells; c += gridDim.y) acc += static_cast<double>(state[c * ld + i]);
+  atomicAdd(&sums[i], acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// Poisson read-out.  Same algorithm family numpy's legacy generator uses behind
+// np.random.poisson (MatriSeq.py:884): multiplication method below lambda = 10, Hoermann's PTRS
+// transformed rejection above (W. Hoermann, Insurance: Mathematics and Economics 12 (1993)).
+// Restated in oracle/poisson_oracle.c; uniforms are consumed strictly in order so both sides
+// agree draw for draw.
+// ------------------------------------------------------------------------------------------
+struct UniformSource {
+  const double* supplied;   // nullptr -> Philox
+  int64_t sup_base;
+  int sup_count, used;
+  uint32_t c0, c2, c3, k0, k1, call;
+  uint32_t w[4];
+  int have;
+  int* err;
+  __device__ double next() {
+    if (supplied) {
+      if (used >= sup_count) { *err = 1; return 0.5; }
+      return supplied[sup_base + used++];
+    }
+    if (have == 0) {
+      philox4x32_10(c0, call++, c2, c3, k0, k1, w);
+      have = 4;
+    }
+    const uint32_t v = w[4 - have];
+    --have;
+    ++used;
+    return (static_cast<double>(v) + 0.5) * 2.3283064365386963e-10;   // (v + 1/2) / 2^32 in (0,1)
+  }
+};
+
+__device__ inline int poisson_draw(double lam, UniformSource& u) {
+  if (!(lam > 0.0)) return 0;
+  if (lam < 10.0) {
+    const double enlam = exp(-lam);
+    double prod = 1.0;
+    int k = 0;
+    for (;;) {
+      prod *= u.next();
+      if (prod > enlam) ++k; else return k;
+      if (k > 100000) return k;   // unreachable for lam < 10 unless the uniforms are degenerate
+    }
+  }
+  const double slam = sqrt(lam), loglam = log(lam);
+  const double b = 0.931 + 2.53 * slam;
+  const double a = -0.059 + 0.02483 * b;
+  const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+  const double vr = 0.9277 - 3.6224 / (b - 2.0);
+  for (int guard = 0; guard < 100000; ++guard) {
+    const double U = u.next() - 0.5;
+    const double V = u.next();
+    const double us = 0.5 - fabs(U);
+    const double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
+    if (us >= 0.07 && V <= vr) return static_cast<int>(kf);
+    if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+    if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-lam + kf * loglam - lgamma(kf + 1.0)))
+      return static_cast<int>(kf);
+  }
+  return static_cast<int>(lam);
+}
+
+// one CTA per cell of the chunk; threads stride over ORIGINAL genes so the output row is coalesced
+template <typename T>
+__global__ void counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ inv, int n,
+                              int64_t cell0, const double* __restrict__ shift, double exp_scale,
+                              const double* __restrict__ sizef, uint32_t k0, uint32_t k1, int64_t cell_offset,
+                              const double* __restrict__ uniforms, int draws, int32_t* __restrict__ out,
+                              double* __restrict__ lam_out, int* err) {
+  const int64_t c = cell0 + blockIdx.x;   // local slot
+  const uint64_t gid = static_cast<uint64_t>(cell_offset + c);
+  const double sf = sizef[c];
+  const T* row = state + c * ld;
+  for (int o = threadIdx.x; o < n; o += blockDim.x) {
+    const double x = static_cast<double>(row[inv[o]]);
+    double lam = exp(exp_scale * (x + shift[o])) * sf;
+    if (lam < 0.0) lam = 0.0;
+    UniformSource u;
+    u.supplied = uniforms;
+    u.sup_base = (c * n + o) * static_cast<int64_t>(draws);
+    u.sup_count = draws;
+    u.used = 0;
+    u.c0 = static_cast<uint32_t>(o);
+    u.c2 = static_cast<uint32_t>(gid);
+    u.c3 = static_cast<uint32_t>(gid >> 32);
+    u.k0 = k0; u.k1 = k1; u.call = 0; u.have = 0; u.err = err;
+    const int64_t oi = static_cast<int64_t>(blockIdx.x) * n + o;
+    out[oi] = poisson_draw(lam, u);
+    if (lam_out) lam_out[oi] = lam;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// debug / parity aids
+// ------------------------------------------------------------------------------------------
+__global__ void debug_philox_kernel(int64_t count, const uint32_t* __restrict__ ctr, uint32_t k0, uint32_t k1,
+                                    uint32_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= count) return;
+  uint32_t w[4];
+  philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], k0, k1, w);
+  for (int j = 0; j < 4; ++j) out[4 * i + j] = w[j];
+}
+
+// the noise step_kernel adds for (global cell, step): one thread per (block, lane)
+__global__ void debug_noise_kernel(int nb, uint32_t gid_lo, uint32_t gid_hi, uint32_t step, float rscale,
+                                   uint32_t k0, uint32_t k1, const int* __restrict__ perm, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb * 32) return;
+  const int b = t >> 5, lane = t & 31;
+  uint32_t w[4];
+  philox4x32_10(static_cast<uint32_t>(b * 32 + lane), step, gid_lo, gid_hi, k0, k1, w);
+  float a[4];
+  box_muller(w[0], w[1], rscale, a[0], a[1]);
+  box_muller(w[2], w[3], rscale, a[2], a[3]);
+  for (int j = 0; j < 4; ++j) {
+    const int o = perm[b * 128 + j * 32 + lane];
+    if (o >= 0) out[o] = static_cast<double>(a[j]);
+  }
+}
+
+}  // namespace scr

@@ -1,0 +1,222 @@
+// Host-side packing of the regulatory matrix into the operator the stepper reads.
+// Pure C++ (no CUDA) so the CPU test-suite can exercise it through scr_debug_host_matvec.
+//
+// Input: CSR of gc (rows = regulated gene; what developCell multiplies by, MatriSeq.py:530).
+// Output (all in the INTERNAL gene order):
+//   perm/inv      internal <-> original gene; order = long rows, then regulators (non-zero
+//                 out-degree, the only genes a row can read), then the rest; each class by
+//                 in-degree descending, so 32-row tiles have near-equal length
+//   tiles         sliced ELL: tile s = genes [32s, 32s+32), entry (s,k,lane) at
+//                 slice_off[s] + 32k + lane, at most `cap` entries per row
+//   chunks        the part of a row beyond `cap`, cut into pieces of `lv` entries; chunk v entry k
+//                 at k*nv_pad + v; ovf_start/ovf_cnt give each long row its chunk range
+//   wblk          128-gene blocks assigned to the wq warps of a cell group (LPT on a cost model)
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace scr {
+
+struct PackedOperator {
+  int n = 0, n_pad = 0, nb = 0, npp = 0, npp_blocks = 0, nlong = 0, nlong_blocks = 0;
+  int nv = 0, nv_pad = 0, lv = 0, cap = 0, wq = 1, wq_log2 = 0;
+  int64_t nnz = 0;
+  std::vector<int> perm, inv;
+  std::vector<int> slice_off;
+  std::vector<double> tile_val;
+  std::vector<int> tile_col;
+  std::vector<double> chunk_val;
+  std::vector<int> chunk_col;
+  std::vector<int> ovf_start, ovf_cnt;
+  std::vector<double> rowsum;   // internal order, length n_pad
+  std::vector<int> wblk_ptr, wblk;
+};
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32_t* col, const double* val,
+                          PackedOperator& op, std::string& err) {
+  if (n <= 0 || nnz < 0 || !rowptr || (nnz > 0 && (!col || !val))) { err = "bad CSR arguments"; return false; }
+  if (rowptr[0] != 0 || rowptr[n] != nnz) { err = "rowptr does not span nnz"; return false; }
+  for (int r = 0; r < n; ++r)
+    if (rowptr[r + 1] < rowptr[r]) { err = "rowptr not monotone"; return false; }
+  for (int64_t e = 0; e < nnz; ++e)
+    if (col[e] < 0 || col[e] >= n) { err = "column index out of range"; return false; }
+
+  op = PackedOperator();
+  op.n = n;
+  op.nnz = nnz;
+  op.n_pad = (n + 127) / 128 * 128;
+  op.nb = op.n_pad / 128;
+
+  std::vector<int> indeg(n), outdeg(n, 0);
+  for (int r = 0; r < n; ++r) indeg[r] = rowptr[r + 1] - rowptr[r];
+  for (int64_t e = 0; e < nnz; ++e) outdeg[col[e]]++;
+
+  const double mean_in = static_cast<double>(nnz) / n;
+  int cap = std::max(8, static_cast<int>(2.0 * mean_in + 0.999));
+  cap = env_int("SCR_ROW_CAP", cap);
+  if (cap < 1) cap = 1;
+  op.cap = cap;
+  op.lv = std::max(1, env_int("SCR_CHUNK_LEN", std::min(cap, 16)));
+
+  // ---- gene order ----
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  auto cls = [&](int g) { return indeg[g] > cap ? 0 : (outdeg[g] > 0 ? 1 : 2); };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    const int ca = cls(a), cb = cls(b);
+    if (ca != cb) return ca < cb;
+    return indeg[a] > indeg[b];
+  });
+  op.perm.assign(op.n_pad, -1);
+  op.inv.assign(n, -1);
+  int n_read = 0;
+  for (int i = 0; i < n; ++i) {
+    op.perm[i] = order[i];
+    op.inv[order[i]] = i;
+    if (cls(order[i]) == 0) op.nlong++;
+    if (cls(order[i]) <= 1) n_read++;
+  }
+  op.npp = std::min(op.n_pad, (n_read + 127) / 128 * 128);
+  op.npp_blocks = op.npp / 128;
+  op.nlong_blocks = (op.nlong + 127) / 128;
+
+  // ---- tiles ----
+  const int nslices = op.n_pad / 32;
+  op.slice_off.assign(nslices + 1, 0);
+  for (int s = 0; s < nslices; ++s) {
+    int len = 0;
+    for (int l = 0; l < 32; ++l) {
+      const int i = s * 32 + l;
+      if (i < n) len = std::max(len, std::min(indeg[op.perm[i]], cap));
+    }
+    op.slice_off[s + 1] = op.slice_off[s] + 32 * len;
+  }
+  const int nslots = op.slice_off[nslices];
+  op.tile_val.assign(nslots, 0.0);
+  op.tile_col.assign(nslots, 0);
+  op.rowsum.assign(op.n_pad, 0.0);
+
+  // ---- chunks of long rows ----
+  const int ovf_genes = op.nlong_blocks * 128;
+  op.ovf_start.assign(ovf_genes, 0);
+  op.ovf_cnt.assign(ovf_genes, 0);
+  int nv = 0;
+  for (int i = 0; i < op.nlong; ++i) {
+    const int extra = indeg[op.perm[i]] - cap;
+    const int pieces = (extra + op.lv - 1) / op.lv;
+    op.ovf_start[i] = nv;
+    op.ovf_cnt[i] = pieces;
+    nv += pieces;
+  }
+  op.nv = nv;
+  op.nv_pad = (nv + 31) / 32 * 32;
+  op.chunk_val.assign(static_cast<size_t>(op.lv) * op.nv_pad, 0.0);
+  op.chunk_col.assign(static_cast<size_t>(op.lv) * op.nv_pad, 0);
+
+  for (int i = 0; i < n; ++i) {
+    const int r = op.perm[i];
+    const int s = i / 32, lane = i % 32;
+    double sum = 0.0;
+    for (int k = 0; k < indeg[r]; ++k) {
+      const int64_t e = rowptr[r] + k;
+      const int ci = op.inv[col[e]];
+      sum += val[e];
+      if (k < cap) {
+        const int slot = op.slice_off[s] + 32 * k + lane;
+        op.tile_val[slot] = val[e];
+        op.tile_col[slot] = ci;
+      } else {
+        const int kk = k - cap;
+        const int v = op.ovf_start[i] + kk / op.lv;
+        const size_t slot = static_cast<size_t>(kk % op.lv) * op.nv_pad + v;
+        op.chunk_val[slot] = val[e];
+        op.chunk_col[slot] = ci;
+      }
+    }
+    op.rowsum[i] = sum;
+  }
+  // every column any row reads must live in the ping-ponged prefix
+  for (int slot = 0; slot < nslots; ++slot)
+    if (op.tile_val[slot] != 0.0 && op.tile_col[slot] >= op.npp) { err = "internal: column outside ping-pong prefix"; return false; }
+
+  // ---- warps per cell group and block -> warp assignment ----
+  int wq = 1;
+  while (wq * 2 <= std::min(8, op.nb)) wq *= 2;
+  const int wq_env = env_int("SCR_WARPS", 0);
+  if (wq_env == 1 || wq_env == 2 || wq_env == 4 || wq_env == 8 || wq_env == 16) wq = wq_env;
+  op.wq = wq;
+  op.wq_log2 = 0;
+  while ((1 << op.wq_log2) < wq) op.wq_log2++;
+
+  std::vector<double> cost(op.nb, 0.0);
+  for (int b = 0; b < op.nb; ++b) {
+    for (int j = 0; j < 4; ++j) {
+      const int s = b * 4 + j;
+      if (s * 32 < n) cost[b] += 140.0;                       // element-wise work of a live tile
+      cost[b] += 7.0 * (op.slice_off[s + 1] - op.slice_off[s]) / 32;
+    }
+    if (b < op.nlong_blocks)
+      for (int i = b * 128; i < b * 128 + 128; ++i) cost[b] += 0.2 * op.ovf_cnt[i];
+  }
+  std::vector<int> by_cost(op.nb);
+  std::iota(by_cost.begin(), by_cost.end(), 0);
+  std::stable_sort(by_cost.begin(), by_cost.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  std::vector<double> load(wq, 0.0);
+  std::vector<std::vector<int>> lists(wq);
+  for (int b : by_cost) {
+    int w = 0;
+    for (int k = 1; k < wq; ++k)
+      if (load[k] < load[w] - 1e-9 || (std::abs(load[k] - load[w]) <= 1e-9 && lists[k].size() < lists[w].size())) w = k;
+    lists[w].push_back(b);
+    load[w] += cost[b];
+  }
+  op.wblk_ptr.assign(wq + 1, 0);
+  op.wblk.clear();
+  for (int w = 0; w < wq; ++w) {
+    std::sort(lists[w].begin(), lists[w].end());
+    for (int b : lists[w]) op.wblk.push_back(b);
+    op.wblk_ptr[w + 1] = static_cast<int>(op.wblk.size());
+  }
+  return true;
+}
+
+// y = W x walking the packed structure exactly as the kernel does (tiles, then chunks)
+inline void host_matvec(const PackedOperator& op, const double* x, double* y) {
+  std::vector<double> xi(op.n_pad, 0.0), yi(op.n_pad, 0.0), part(std::max(op.nv_pad, 1), 0.0);
+  for (int i = 0; i < op.n_pad; ++i)
+    if (op.perm[i] >= 0) xi[i] = x[op.perm[i]];
+  for (int v = 0; v < op.nv_pad; ++v) {
+    double acc = 0.0;
+    for (int k = 0; k < op.lv; ++k) {
+      const size_t slot = static_cast<size_t>(k) * op.nv_pad + v;
+      acc += op.chunk_val[slot] * xi[op.chunk_col[slot]];
+    }
+    part[v] = acc;
+  }
+  for (int w = 0; w < op.wq; ++w)
+    for (int bi = op.wblk_ptr[w]; bi < op.wblk_ptr[w + 1]; ++bi) {
+      const int b = op.wblk[bi];
+      for (int j = 0; j < 4; ++j)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int s = b * 4 + j, i = s * 32 + lane;
+          double acc = 0.0;
+          for (int o = op.slice_off[s] + lane; o < op.slice_off[s + 1]; o += 32) acc += op.tile_val[o] * xi[op.tile_col[o]];
+          if (b < op.nlong_blocks)
+            for (int e = op.ovf_start[i]; e < op.ovf_start[i] + op.ovf_cnt[i]; ++e) acc += part[e];
+          yi[i] += acc;   // += so a block visited twice (a packing bug) shows up
+        }
+    }
+  for (int i = 0; i < op.n_pad; ++i)
+    if (op.perm[i] >= 0) y[op.perm[i]] = yi[i];
+}
+
+}  // namespace scr

@@ -1,0 +1,779 @@
+// C ABI of scrutiny_b200 (see include/scrutiny_b200.h for the contract and reference citations).
+#include "../../include/scrutiny_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "operator_pack.h"
+#include "step_kernel.cuh"
+
+using scr::Item;
+using scr::PackedOperator;
+
+namespace {
+std::string g_create_error;
+constexpr int kSmemDefault = 232448;   // 227 KB opt-in limit of sm_100
+}
+
+struct scr_ctx {
+  int device = -1;
+  int prec = SCR_F32;
+  bool host_only = false;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
+  mutable std::string err;
+  int sm_count = 148, smem_optin = kSmemDefault;
+
+  // operator
+  bool has_net = false;
+  PackedOperator op;
+  unsigned char *d_tab = nullptr, *d_w = nullptr;
+  int tab_bytes = 0, w_bytes = 0, off_slice = 0, off_ovfidx = 0, off_wblk_ptr = 0, off_wblk = 0, off_vrow = 0;
+  int *d_perm = nullptr, *d_inv = nullptr;
+  void *d_pc = nullptr, *d_bias = nullptr;
+  int q = 1;
+  bool w_smem = false;
+  size_t gbytes = 0, fixed_bytes = 0;
+
+  // cells
+  void* d_state = nullptr;
+  int64_t cells = 0, cell_offset = 0;
+
+  // scratch
+  Item* d_items = nullptr;
+  size_t items_cap = 0;
+  int* d_counter = nullptr;
+  int* d_err = nullptr;
+  double* d_stage = nullptr;
+  size_t stage_elems = 0;
+
+  // stats
+  int64_t launches = 0;
+  double last_ms = -1.0, total_step_ms = 0.0;
+  int64_t total_step_launches = 0;
+
+  size_t esize() const { return prec == SCR_F64 ? 8 : 4; }
+  int cpg() const { return prec == SCR_F64 ? 2 : 4; }
+};
+
+namespace {
+
+int fail(const scr_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return code;
+}
+int fail_cuda(const scr_ctx* ctx, cudaError_t e, const char* what) {
+  return fail(ctx, SCR_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                              \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call); \
+  } while (0)
+#define NEED_GPU()                                                                      \
+  do {                                                                                  \
+    if (!ctx) return SCR_E_ARG;                                                         \
+    if (ctx->host_only) return fail(ctx, SCR_E_CUDA, "host-only context: no CUDA device (there is no CPU fallback)"); \
+    CK(cudaSetDevice(ctx->device));                                                     \
+  } while (0)
+
+int align16(int x) { return (x + 15) & ~15; }
+
+template <typename T>
+void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std::vector<unsigned char>& w,
+                 int& off_slice, int& off_ovfidx, int& off_wblk_ptr, int& off_wblk, int& off_vrow) {
+  using WEnt = typename scr::Traits<T>::WEnt;
+  const int nslices = op.n_pad / 32;
+  off_slice = 0;
+  off_ovfidx = align16(off_slice + (nslices + 1) * 4);
+  off_wblk_ptr = align16(off_ovfidx + static_cast<int>(op.ovf_start.size()) * 8);
+  off_wblk = align16(off_wblk_ptr + (op.wq + 1) * 4);
+  const int total = align16(off_wblk + static_cast<int>(op.wblk.size()) * 4);
+  tab.assign(std::max(total, 16), 0);
+  std::memcpy(tab.data() + off_slice, op.slice_off.data(), (nslices + 1) * 4);
+  for (size_t i = 0; i < op.ovf_start.size(); ++i) {
+    int2 v = make_int2(op.ovf_start[i], op.ovf_cnt[i]);
+    std::memcpy(tab.data() + off_ovfidx + i * 8, &v, 8);
+  }
+  std::memcpy(tab.data() + off_wblk_ptr, op.wblk_ptr.data(), (op.wq + 1) * 4);
+  if (!op.wblk.empty()) std::memcpy(tab.data() + off_wblk, op.wblk.data(), op.wblk.size() * 4);
+
+  const size_t nslots = op.tile_val.size(), nch = op.chunk_val.size();
+  off_vrow = align16(static_cast<int>(nslots * sizeof(WEnt)));
+  const int wtotal = align16(off_vrow + static_cast<int>(nch * sizeof(WEnt)));
+  w.assign(std::max(wtotal, 16), 0);
+  for (size_t s = 0; s < nslots; ++s) {
+    WEnt e{};
+    e.v = static_cast<T>(op.tile_val[s]);
+    e.off = op.tile_col[s] * 16;
+    std::memcpy(w.data() + s * sizeof(WEnt), &e, sizeof(WEnt));
+  }
+  for (size_t s = 0; s < nch; ++s) {
+    WEnt e{};
+    e.v = static_cast<T>(op.chunk_val[s]);
+    e.off = op.chunk_col[s] * 16;
+    std::memcpy(w.data() + off_vrow + s * sizeof(WEnt), &e, sizeof(WEnt));
+  }
+}
+
+void free_network(scr_ctx* ctx) {
+  if (ctx->host_only) return;
+  cudaFree(ctx->d_tab); cudaFree(ctx->d_w); cudaFree(ctx->d_perm); cudaFree(ctx->d_inv);
+  cudaFree(ctx->d_pc); cudaFree(ctx->d_bias);
+  ctx->d_tab = ctx->d_w = nullptr; ctx->d_perm = ctx->d_inv = nullptr; ctx->d_pc = ctx->d_bias = nullptr;
+}
+
+int choose_config(scr_ctx* ctx) {
+  const PackedOperator& op = ctx->op;
+  const size_t pc_bytes = static_cast<size_t>(op.n_pad) * 2 * ctx->esize();
+  ctx->gbytes = scr::group_smem_bytes(op.n_pad, op.npp, op.nv_pad);
+  ctx->fixed_bytes = ctx->tab_bytes + pc_bytes + 16;
+  const long limit = ctx->smem_optin;
+  const long q_glob = (limit - static_cast<long>(ctx->fixed_bytes)) / static_cast<long>(ctx->gbytes);
+  const long q_smem = (limit - static_cast<long>(ctx->fixed_bytes) - ctx->w_bytes) / static_cast<long>(ctx->gbytes);
+  if (q_glob < 1)
+    return fail(ctx, SCR_E_RESOURCE, "n too large: one cell group does not fit in shared memory");
+  const int maxq = std::max(1, std::min(15, 16 / op.wq));
+  bool w_smem = q_smem >= 1 && q_smem >= std::min<long>(std::min<long>(q_glob, maxq), 2);
+  const int force = scr::env_int("SCR_W_SMEM", -1);
+  if (force == 0) w_smem = false;
+  if (force == 1 && q_smem >= 1) w_smem = true;
+  ctx->w_smem = w_smem;
+  int q = static_cast<int>(std::min<long>(w_smem ? q_smem : q_glob, maxq));
+  const int q_env = scr::env_int("SCR_GROUPS", 0);
+  if (q_env >= 1) q = std::min(q, q_env);
+  ctx->q = std::max(1, q);
+  return SCR_OK;
+}
+
+template <typename T, bool PROBE, bool SUPPLIED>
+int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
+  // few groups: spread them over SMs instead of stacking them in one CTA
+  int q = std::min(ctx->q, std::max(1, (nitems + ctx->sm_count - 1) / ctx->sm_count));
+  p.q = q;
+  const size_t smem = ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * ctx->gbytes;
+  const int threads = q * ctx->op.wq * 32;
+  auto kern = ctx->w_smem ? scr::step_kernel<T, true, PROBE, SUPPLIED> : scr::step_kernel<T, false, PROBE, SUPPLIED>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) return fail(ctx, SCR_E_RESOURCE, "stepper does not fit on an SM");
+  const int grid = std::max(1, std::min((nitems + q - 1) / q, ctx->sm_count * per_sm));
+  CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  kern<<<grid, threads, smem, ctx->stream>>>(p);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->launches++;
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_ms = ms;
+  if (!PROBE) { ctx->total_step_ms += ms; ctx->total_step_launches++; }
+  return SCR_OK;
+}
+
+template <typename T>
+int launch_step(scr_ctx* ctx, scr::StepParams<T>& p, int nitems, bool probe, bool supplied) {
+  if (probe) return supplied ? launch_step_t<T, true, true>(ctx, p, nitems) : launch_step_t<T, true, false>(ctx, p, nitems);
+  return supplied ? launch_step_t<T, false, true>(ctx, p, nitems) : launch_step_t<T, false, false>(ctx, p, nitems);
+}
+
+template <typename T>
+void fill_common(scr_ctx* ctx, scr::StepParams<T>& p) {
+  const PackedOperator& op = ctx->op;
+  std::memset(&p, 0, sizeof(p));
+  p.tab = ctx->d_tab; p.wblob = ctx->d_w; p.tab_bytes = ctx->tab_bytes; p.w_bytes = ctx->w_bytes;
+  p.off_slice = ctx->off_slice; p.off_ovfidx = ctx->off_ovfidx; p.off_wblk_ptr = ctx->off_wblk_ptr;
+  p.off_wblk = ctx->off_wblk; p.off_vrow = ctx->off_vrow;
+  p.n = op.n; p.n_pad = op.n_pad; p.npp = op.npp; p.nb = op.nb; p.npp_blocks = op.npp_blocks;
+  p.nlong_blocks = op.nlong_blocks; p.nv = op.nv; p.nv_pad = op.nv_pad; p.lv = op.lv;
+  p.wq = op.wq; p.wq_log2 = op.wq_log2; p.q = ctx->q;
+  p.pc = static_cast<const unsigned char*>(ctx->d_pc);
+  p.state = static_cast<T*>(ctx->d_state);
+  p.ld = op.n_pad;
+  p.counter = ctx->d_counter;
+  p.cell_offset = ctx->cell_offset;
+  p.perm = ctx->d_perm;
+}
+
+// proj/const (+mu) and the -mu*rowsum bias of one node, internal order
+template <typename T>
+int upload_node(scr_ctx* ctx, const double* proj, const double* cnst, double mu, scr::StepParams<T>& p) {
+  const PackedOperator& op = ctx->op;
+  std::vector<T> pc(static_cast<size_t>(op.n_pad) * 2, T(0));
+  for (int i = 0; i < op.n; ++i) {
+    pc[2 * i] = static_cast<T>(proj[op.perm[i]]);
+    pc[2 * i + 1] = static_cast<T>(cnst[op.perm[i]] + mu);
+  }
+  CK(cudaMemcpyAsync(ctx->d_pc, pc.data(), pc.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  p.bias = nullptr;
+  if (mu != 0.0) {
+    std::vector<T> bias(op.n_pad, T(0));
+    for (int i = 0; i < op.n; ++i) bias[i] = static_cast<T>(-mu * op.rowsum[i]);
+    CK(cudaMemcpyAsync(ctx->d_bias, bias.data(), bias.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    p.bias = static_cast<const T*>(ctx->d_bias);
+  }
+  CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+  return SCR_OK;
+}
+
+int ensure_items(scr_ctx* ctx, size_t count) {
+  if (count <= ctx->items_cap) return SCR_OK;
+  cudaFree(ctx->d_items);
+  ctx->d_items = nullptr;
+  ctx->items_cap = 0;
+  const size_t cap = std::max<size_t>(count, 1024);
+  CK(cudaMalloc(&ctx->d_items, cap * sizeof(Item)));
+  ctx->items_cap = cap;
+  return SCR_OK;
+}
+
+template <typename T>
+int upload_noise(scr_ctx* ctx, const double* noise, size_t count, T** d_noise) {
+  std::vector<T> h(count);
+  for (size_t i = 0; i < count; ++i) h[i] = static_cast<T>(noise[i]);
+  CK(cudaMalloc(d_noise, std::max<size_t>(count, 1) * sizeof(T)));
+  CK(cudaMemcpy(*d_noise, h.data(), count * sizeof(T), cudaMemcpyHostToDevice));
+  return SCR_OK;
+}
+
+template <typename T>
+int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t* steps, const int64_t* step_base,
+                const double* proj, const double* cnst, double dt, double sigma, double mu, uint64_t seed,
+                const double* noise, int64_t noise_steps) {
+  constexpr int CPG = scr::Traits<T>::CPG;
+  // longest first (counting sort on the step count), then groups of CPG consecutive cells
+  int smax = 0;
+  for (int64_t i = 0; i < m; ++i) {
+    if (cell_ids[i] < 0 || cell_ids[i] >= ctx->cells) return fail(ctx, SCR_E_ARG, "cell id out of range");
+    if (steps[i] < 0) return fail(ctx, SCR_E_ARG, "negative step count");
+    smax = std::max(smax, steps[i]);
+  }
+  if (noise && smax > noise_steps) return fail(ctx, SCR_E_ARG, "supplied noise shorter than the longest cell");
+  if (smax == 0) return SCR_OK;
+  std::vector<int64_t> bucket(static_cast<size_t>(smax) + 2, 0);
+  for (int64_t i = 0; i < m; ++i) if (steps[i] > 0) bucket[smax - steps[i] + 1]++;
+  for (int s = 0; s <= smax; ++s) bucket[s + 1] += bucket[s];
+  const int64_t live = bucket[smax];
+  std::vector<int64_t> order(live);
+  {
+    std::vector<int64_t> pos(bucket.begin(), bucket.end() - 1);
+    for (int64_t i = 0; i < m; ++i) if (steps[i] > 0) order[pos[smax - steps[i]]++] = i;
+  }
+  const int64_t nitems = (live + CPG - 1) / CPG;
+  if (nitems > 0x7fffffff) return fail(ctx, SCR_E_ARG, "too many cell groups");
+  std::vector<Item> items(nitems);
+  for (int64_t g = 0; g < nitems; ++g) {
+    Item& it = items[g];
+    std::memset(&it, 0, sizeof(it));
+    it.scale = 1.0;
+    for (int c = 0; c < 4; ++c) {
+      const int64_t k = g * CPG + c;
+      if (c < CPG && k < live) {
+        const int64_t i = order[k];
+        it.cell[c] = static_cast<int>(cell_ids[i]);
+        it.steps[c] = steps[i];
+        it.base[c] = static_cast<uint32_t>(step_base ? step_base[i] : 0);
+        it.row[c] = static_cast<int>(i);
+      } else {
+        it.cell[c] = -1;
+      }
+    }
+  }
+  int rc = ensure_items(ctx, items.size());
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->d_items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, ctx->stream));
+
+  scr::StepParams<T> p;
+  fill_common(ctx, p);
+  rc = upload_node<T>(ctx, proj, cnst, mu, p);
+  if (rc) return rc;
+  p.items = ctx->d_items;
+  p.nitems = static_cast<int>(nitems);
+  p.dt = static_cast<T>(dt);
+  p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma);
+  p.k0 = static_cast<uint32_t>(seed);
+  p.k1 = static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_STEP);
+  T* d_noise = nullptr;
+  if (noise) {
+    rc = upload_noise<T>(ctx, noise, static_cast<size_t>(m) * noise_steps * ctx->op.n, &d_noise);
+    if (rc) return rc;
+    p.noise = d_noise;
+    p.noise_steps = noise_steps;
+  }
+  rc = launch_step<T>(ctx, p, static_cast<int>(nitems), false, noise != nullptr);
+  cudaFree(d_noise);
+  return rc;
+}
+
+template <typename T>
+int probe_t(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_div, const double* proj,
+            const double* cnst, double dt, double sigma, double mu, double thresh, int32_t max_iter,
+            int32_t avg_num, uint64_t seed, uint32_t stream, const double* noise, int32_t* iters_out,
+            double* normdiff_out) {
+  constexpr int CPG = scr::Traits<T>::CPG;
+  const int nitems = (k + CPG - 1) / CPG;
+  std::vector<Item> items(nitems);
+  for (int g = 0; g < nitems; ++g) {
+    Item& it = items[g];
+    std::memset(&it, 0, sizeof(it));
+    for (int c = 0; c < 4; ++c) {
+      const int i = g * CPG + c;
+      if (c < CPG && i < k) {
+        if (sample_ids[i] < 0 || sample_ids[i] >= ctx->cells) return fail(ctx, SCR_E_ARG, "sample id out of range");
+        it.cell[c] = static_cast<int>(sample_ids[i]);
+        it.row[c] = i;
+      } else {
+        it.cell[c] = -1;
+      }
+    }
+    // one divisor per group: the ladder is laid out so that a group never mixes alphas
+    const int i0 = g * CPG;
+    it.scale = w_div ? 1.0 / w_div[i0] : 1.0;
+    if (w_div)
+      for (int c = 1; c < CPG && i0 + c < k; ++c)
+        if (w_div[i0 + c] != w_div[i0]) return fail(ctx, SCR_E_ARG, "w_div must be constant within a cell group");
+  }
+  int rc = ensure_items(ctx, items.size());
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->d_items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, ctx->stream));
+
+  scr::StepParams<T> p;
+  fill_common(ctx, p);
+  rc = upload_node<T>(ctx, proj, cnst, mu, p);
+  if (rc) return rc;
+  p.items = ctx->d_items;
+  p.nitems = nitems;
+  p.dt = static_cast<T>(dt);
+  p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma);
+  p.k0 = static_cast<uint32_t>(seed);
+  p.k1 = static_cast<uint32_t>(seed >> 32) ^ stream;
+  p.thresh = thresh;
+  p.max_iter = max_iter;
+  p.avg_num = avg_num;
+  int* d_iters = nullptr;
+  double* d_nd = nullptr;
+  T* d_noise = nullptr;
+  const size_t nd_count = static_cast<size_t>(k) * max_iter;
+  CK(cudaMalloc(&d_iters, k * sizeof(int)));
+  CK(cudaMalloc(&d_nd, nd_count * sizeof(double)));
+  CK(cudaMemsetAsync(d_nd, 0, nd_count * sizeof(double), ctx->stream));
+  p.iters_out = d_iters;
+  p.nd = d_nd;
+  if (noise) {
+    rc = upload_noise<T>(ctx, noise, nd_count * ctx->op.n, &d_noise);
+    if (rc) { cudaFree(d_iters); cudaFree(d_nd); return rc; }
+    p.noise = d_noise;
+    p.noise_steps = max_iter;
+  }
+  rc = launch_step<T>(ctx, p, nitems, true, noise != nullptr);
+  if (rc == SCR_OK) {
+    cudaError_t e = cudaMemcpy(iters_out, d_iters, k * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && normdiff_out) e = cudaMemcpy(normdiff_out, d_nd, nd_count * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail_cuda(ctx, e, "probe result copy");
+  }
+  cudaFree(d_iters); cudaFree(d_nd); cudaFree(d_noise);
+  return rc;
+}
+
+int ensure_stage(scr_ctx* ctx, size_t elems) {
+  if (elems <= ctx->stage_elems) return SCR_OK;
+  cudaFree(ctx->d_stage);
+  ctx->d_stage = nullptr;
+  ctx->stage_elems = 0;
+  CK(cudaMalloc(&ctx->d_stage, elems * sizeof(double)));
+  ctx->stage_elems = elems;
+  return SCR_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int scr_abi_version(void) { return 1; }
+
+int scr_create(scr_ctx** out, int device_ordinal, int precision) {
+  if (!out || (precision != SCR_F32 && precision != SCR_F64)) return fail(nullptr, SCR_E_ARG, "bad arguments");
+  scr_ctx* ctx = new scr_ctx();
+  ctx->prec = precision;
+  if (device_ordinal < 0) {   // packing-only context for the CPU test-suite; every GPU entry point refuses it
+    ctx->host_only = true;
+    *out = ctx;
+    return SCR_OK;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device_ordinal >= ndev) {
+    delete ctx;
+    return fail(nullptr, SCR_E_CUDA, e != cudaSuccess ? std::string("no CUDA device: ") + cudaGetErrorString(e)
+                                                       : std::string("device ordinal out of range"));
+  }
+  ctx->device = device_ordinal;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device_ordinal)) != cudaSuccess) {
+    delete ctx;
+    return fail_cuda(nullptr, e, "cudaSetDevice");
+  }
+  if (prop.major < 10) {
+    delete ctx;
+    return fail(nullptr, SCR_E_CUDA, "scrutiny_b200 is built for sm_100a only");
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_k[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_k[1], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_c[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_c[1], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->d_counter, sizeof(int))) != cudaSuccess || (e = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) {
+    delete ctx;
+    return fail_cuda(nullptr, e, "context setup");
+  }
+  *out = ctx;
+  return SCR_OK;
+}
+
+void scr_destroy(scr_ctx* ctx) {
+  if (!ctx) return;
+  if (!ctx->host_only) {
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_network(ctx);
+    cudaFree(ctx->d_state); cudaFree(ctx->d_items); cudaFree(ctx->d_counter); cudaFree(ctx->d_err); cudaFree(ctx->d_stage);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 2; ++i) { if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]); if (ctx->ev_c[i]) cudaEventDestroy(ctx->ev_c[i]); }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  }
+  delete ctx;
+}
+
+const char* scr_last_error(const scr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int scr_sync(scr_ctx* ctx) {
+  NEED_GPU();
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SCR_OK;
+}
+
+int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* rowptr, const int32_t* col, const double* val) {
+  if (!ctx) return SCR_E_ARG;
+  if (ctx->cells > 0 && ctx->has_net && n != ctx->op.n) return fail(ctx, SCR_E_STATE, "cells are allocated for a different n");
+  PackedOperator op;
+  std::string err;
+  if (!scr::pack_operator(n, nnz, rowptr, col, val, op, err)) return fail(ctx, SCR_E_ARG, err);
+  // the gene order must not change under allocated cells (alpha rescaling keeps the pattern, hence the order)
+  if (ctx->cells > 0 && ctx->has_net && op.perm != ctx->op.perm)
+    return fail(ctx, SCR_E_STATE, "network pattern changed while cells are allocated");
+  std::vector<unsigned char> tab, w;
+  if (ctx->prec == SCR_F64) build_blobs<double>(op, tab, w, ctx->off_slice, ctx->off_ovfidx, ctx->off_wblk_ptr, ctx->off_wblk, ctx->off_vrow);
+  else build_blobs<float>(op, tab, w, ctx->off_slice, ctx->off_ovfidx, ctx->off_wblk_ptr, ctx->off_wblk, ctx->off_vrow);
+  ctx->tab_bytes = static_cast<int>(tab.size());
+  ctx->w_bytes = static_cast<int>(w.size());
+  ctx->op = std::move(op);
+  ctx->has_net = false;
+  int rc = choose_config(ctx);
+  if (rc) return rc;
+  if (!ctx->host_only) {
+    CK(cudaSetDevice(ctx->device));
+    free_network(ctx);
+    const PackedOperator& o = ctx->op;
+    CK(cudaMalloc(&ctx->d_tab, tab.size()));
+    CK(cudaMalloc(&ctx->d_w, w.size()));
+    CK(cudaMalloc(&ctx->d_perm, o.n_pad * sizeof(int)));
+    CK(cudaMalloc(&ctx->d_inv, o.n * sizeof(int)));
+    CK(cudaMalloc(&ctx->d_pc, static_cast<size_t>(o.n_pad) * 2 * ctx->esize()));
+    CK(cudaMalloc(&ctx->d_bias, static_cast<size_t>(o.n_pad) * ctx->esize()));
+    CK(cudaMemcpy(ctx->d_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_w, w.data(), w.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_perm, o.perm.data(), o.n_pad * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_inv, o.inv.data(), o.n * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  ctx->has_net = true;
+  return SCR_OK;
+}
+
+int scr_set_network_dense(scr_ctx* ctx, int32_t n, const double* gc) {
+  if (!ctx || n <= 0 || !gc) return fail(ctx, SCR_E_ARG, "bad arguments");
+  std::vector<int32_t> rowptr(n + 1, 0), col;
+  std::vector<double> val;
+  for (int r = 0; r < n; ++r) {
+    for (int c = 0; c < n; ++c) {
+      const double v = gc[static_cast<size_t>(r) * n + c];
+      if (v != 0.0) { col.push_back(c); val.push_back(v); }
+    }
+    rowptr[r + 1] = static_cast<int32_t>(col.size());
+  }
+  return scr_set_network_csr(ctx, n, static_cast<int64_t>(col.size()), rowptr.data(), col.data(), val.data());
+}
+
+int scr_debug_host_matvec(const scr_ctx* ctx, const double* x, double* y) {
+  if (!ctx || !x || !y) return SCR_E_ARG;
+  if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
+  scr::host_matvec(ctx->op, x, y);
+  return SCR_OK;
+}
+
+int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count) {
+  if (!ctx || !out) return SCR_E_ARG;
+  if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
+  const PackedOperator& o = ctx->op;
+  const int64_t v[12] = {o.n_pad, o.npp, static_cast<int64_t>(o.tile_val.size()), o.nv, o.lv, o.cap, o.wq, ctx->q,
+                         static_cast<int64_t>(ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + ctx->q * ctx->gbytes),
+                         ctx->w_smem ? 1 : 0, ctx->cpg(), 1};
+  for (int i = 0; i < count && i < 12; ++i) out[i] = v[i];
+  return SCR_OK;
+}
+
+int scr_alloc_cells(scr_ctx* ctx, int64_t cells, int64_t global_cell_offset) {
+  NEED_GPU();
+  if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "set the network before allocating cells");
+  if (cells <= 0 || cells > 0x7fffffff) return fail(ctx, SCR_E_ARG, "bad cell count");
+  cudaFree(ctx->d_state);
+  ctx->d_state = nullptr;
+  ctx->cells = 0;
+  const size_t bytes = static_cast<size_t>(cells) * ctx->op.n_pad * ctx->esize();
+  CK(cudaMalloc(&ctx->d_state, bytes));
+  CK(cudaMemsetAsync(ctx->d_state, 0, bytes, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->cells = cells;
+  ctx->cell_offset = global_cell_offset;
+  return SCR_OK;
+}
+
+int scr_set_states(scr_ctx* ctx, int64_t cell0, int64_t count, const double* S, int64_t ld) {
+  NEED_GPU();
+  if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
+  if (cell0 < 0 || count < 0 || cell0 + count > ctx->cells || !S || ld < count) return fail(ctx, SCR_E_ARG, "bad range");
+  const int n = ctx->op.n, n_pad = ctx->op.n_pad;
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(count, (64LL << 20) / n));
+  int rc = ensure_stage(ctx, static_cast<size_t>(chunk) * n);
+  if (rc) return rc;
+  for (int64_t c0 = 0; c0 < count; c0 += chunk) {
+    const int64_t cnt = std::min(chunk, count - c0);
+    CK(cudaMemcpy2DAsync(ctx->d_stage, cnt * sizeof(double), S + c0, ld * sizeof(double), cnt * sizeof(double), n,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((n_pad + 127) / 128, static_cast<unsigned>(std::min<int64_t>(cnt, 4096)));
+    if (ctx->prec == SCR_F64)
+      scr::pack_states_kernel<double><<<grid, 128, 0, ctx->stream>>>(ctx->d_stage, cnt, static_cast<double*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
+    else
+      scr::pack_states_kernel<float><<<grid, 128, 0, ctx->stream>>>(ctx->d_stage, cnt, static_cast<float*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return SCR_OK;
+}
+
+int scr_set_states_broadcast(scr_ctx* ctx, const double* x0) {
+  NEED_GPU();
+  if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
+  if (!x0) return fail(ctx, SCR_E_ARG, "null state");
+  const int n = ctx->op.n, n_pad = ctx->op.n_pad;
+  int rc = ensure_stage(ctx, n);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->d_stage, x0, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grid((n_pad + 127) / 128, static_cast<unsigned>(std::min<int64_t>(ctx->cells, 8192)));
+  if (ctx->prec == SCR_F64)
+    scr::broadcast_state_kernel<double><<<grid, 128, 0, ctx->stream>>>(ctx->d_stage, static_cast<double*>(ctx->d_state), n_pad, ctx->cells, ctx->d_perm, n_pad);
+  else
+    scr::broadcast_state_kernel<float><<<grid, 128, 0, ctx->stream>>>(ctx->d_stage, static_cast<float*>(ctx->d_state), n_pad, ctx->cells, ctx->d_perm, n_pad);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SCR_OK;
+}
+
+int scr_get_states(scr_ctx* ctx, int64_t cell0, int64_t count, double* S, int64_t ld) {
+  NEED_GPU();
+  if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
+  if (cell0 < 0 || count < 0 || cell0 + count > ctx->cells || !S || ld < count) return fail(ctx, SCR_E_ARG, "bad range");
+  const int n = ctx->op.n, n_pad = ctx->op.n_pad;
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(count, (64LL << 20) / n));
+  int rc = ensure_stage(ctx, static_cast<size_t>(chunk) * n);
+  if (rc) return rc;
+  for (int64_t c0 = 0; c0 < count; c0 += chunk) {
+    const int64_t cnt = std::min(chunk, count - c0);
+    dim3 grid((n_pad + 127) / 128, static_cast<unsigned>(std::min<int64_t>(cnt, 4096)));
+    if (ctx->prec == SCR_F64)
+      scr::unpack_states_kernel<double><<<grid, 128, 0, ctx->stream>>>(ctx->d_stage, cnt, static_cast<const double*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
+    else
+      scr::unpack_states_kernel<float><<<grid, 128, 0, ctx->stream>>>(ctx->d_stage, cnt, static_cast<const float*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpy2DAsync(S + c0, ld * sizeof(double), ctx->d_stage, cnt * sizeof(double), cnt * sizeof(double), n,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return SCR_OK;
+}
+
+int scr_run_phase(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t* steps, const int64_t* step_base,
+                  const double* proj, const double* cnst, double dt, double sigma, double mu, uint64_t seed,
+                  const double* noise, int64_t noise_steps) {
+  NEED_GPU();
+  if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
+  if (m < 0 || (m > 0 && (!cell_ids || !steps)) || !proj || !cnst) return fail(ctx, SCR_E_ARG, "bad arguments");
+  if (m == 0) return SCR_OK;
+  if (ctx->prec == SCR_F64)
+    return run_phase_t<double>(ctx, m, cell_ids, steps, step_base, proj, cnst, dt, sigma, mu, seed, noise, noise_steps);
+  return run_phase_t<float>(ctx, m, cell_ids, steps, step_base, proj, cnst, dt, sigma, mu, seed, noise, noise_steps);
+}
+
+int scr_probe(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_div, const double* proj,
+              const double* cnst, double dt, double sigma, double mu, double thresh, int32_t max_iter, int32_t avg_num,
+              uint64_t seed, uint32_t stream, const double* noise, int32_t* iters_out, double* normdiff_out) {
+  NEED_GPU();
+  if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
+  if (k <= 0 || !sample_ids || !proj || !cnst || !iters_out || max_iter <= 0 || avg_num <= 0)
+    return fail(ctx, SCR_E_ARG, "bad arguments");
+  if (ctx->prec == SCR_F64)
+    return probe_t<double>(ctx, k, sample_ids, w_div, proj, cnst, dt, sigma, mu, thresh, max_iter, avg_num, seed, stream, noise, iters_out, normdiff_out);
+  return probe_t<float>(ctx, k, sample_ids, w_div, proj, cnst, dt, sigma, mu, thresh, max_iter, avg_num, seed, stream, noise, iters_out, normdiff_out);
+}
+
+int scr_gene_sums(scr_ctx* ctx, double* sums_out) {
+  NEED_GPU();
+  if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
+  if (!sums_out) return fail(ctx, SCR_E_ARG, "null output");
+  const int n = ctx->op.n, n_pad = ctx->op.n_pad;
+  int rc = ensure_stage(ctx, n_pad);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(ctx->d_stage, 0, n_pad * sizeof(double), ctx->stream));
+  dim3 grid((n_pad + 127) / 128, static_cast<unsigned>(std::min<int64_t>(ctx->cells, 2048)));
+  if (ctx->prec == SCR_F64)
+    scr::gene_sums_kernel<double><<<grid, 128, 0, ctx->stream>>>(static_cast<const double*>(ctx->d_state), n_pad, ctx->cells, n_pad, ctx->d_stage);
+  else
+    scr::gene_sums_kernel<float><<<grid, 128, 0, ctx->stream>>>(static_cast<const float*>(ctx->d_state), n_pad, ctx->cells, n_pad, ctx->d_stage);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  std::vector<double> h(n_pad);
+  CK(cudaMemcpyAsync(h.data(), ctx->d_stage, n_pad * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i) sums_out[ctx->op.perm[i]] = h[i];
+  return SCR_OK;
+}
+
+int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double* size_factors, uint64_t seed,
+               const double* uniforms, int32_t draws_per_entry, int32_t* counts_out, int out_on_device, double* lambda_out) {
+  NEED_GPU();
+  if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
+  if (!shift || !size_factors || !counts_out) return fail(ctx, SCR_E_ARG, "bad arguments");
+  const int n = ctx->op.n;
+  const int64_t cells = ctx->cells;
+  double *d_shift = nullptr, *d_size = nullptr, *d_uni = nullptr, *d_lam = nullptr;
+  int32_t* d_buf[2] = {nullptr, nullptr};
+  int rc = SCR_OK;
+  auto cleanup = [&]() { cudaFree(d_shift); cudaFree(d_size); cudaFree(d_uni); cudaFree(d_lam); cudaFree(d_buf[0]); cudaFree(d_buf[1]); };
+#define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
+  CKC(cudaMalloc(&d_shift, n * sizeof(double)));
+  CKC(cudaMalloc(&d_size, cells * sizeof(double)));
+  CKC(cudaMemcpyAsync(d_shift, shift, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemcpyAsync(d_size, size_factors, cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+  if (uniforms) {
+    const size_t cnt = static_cast<size_t>(cells) * n * draws_per_entry;
+    CKC(cudaMalloc(&d_uni, cnt * sizeof(double)));
+    CKC(cudaMemcpyAsync(d_uni, uniforms, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (lambda_out) CKC(cudaMalloc(&d_lam, static_cast<size_t>(cells) * n * sizeof(double)));
+  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_COUNTS);
+  auto launch = [&](int64_t c0, int64_t cnt, int32_t* out, double* lam) -> cudaError_t {
+    if (ctx->prec == SCR_F64)
+      scr::counts_kernel<double><<<static_cast<unsigned>(cnt), 256, 0, ctx->stream>>>(static_cast<const double*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, n, c0, d_shift, exp_scale, d_size, k0, k1, ctx->cell_offset, d_uni, draws_per_entry, out, lam, ctx->d_err);
+    else
+      scr::counts_kernel<float><<<static_cast<unsigned>(cnt), 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, n, c0, d_shift, exp_scale, d_size, k0, k1, ctx->cell_offset, d_uni, draws_per_entry, out, lam, ctx->d_err);
+    ctx->launches++;
+    return cudaGetLastError();
+  };
+  if (out_on_device) {
+    CKC(launch(0, cells, counts_out, d_lam));
+  } else {
+    // double-buffered: the Poisson kernel of chunk i+1 overlaps the D2H copy of chunk i
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(cells, (256LL << 20) / (static_cast<int64_t>(n) * 4)));
+    CKC(cudaMalloc(&d_buf[0], static_cast<size_t>(chunk) * n * 4));
+    if (cells > chunk) CKC(cudaMalloc(&d_buf[1], static_cast<size_t>(chunk) * n * 4));
+    int used[2] = {0, 0};
+    int64_t ci = 0;
+    for (int64_t c0 = 0; c0 < cells; c0 += chunk, ++ci) {
+      const int b = static_cast<int>(ci & 1);
+      const int64_t cnt = std::min(chunk, cells - c0);
+      if (used[b]) CKC(cudaStreamWaitEvent(ctx->stream, ctx->ev_c[b], 0));
+      CKC(launch(c0, cnt, d_buf[b], d_lam ? d_lam + c0 * n : nullptr));
+      CKC(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+      CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[b], 0));
+      CKC(cudaMemcpyAsync(counts_out + c0 * n, d_buf[b], static_cast<size_t>(cnt) * n * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      CKC(cudaEventRecord(ctx->ev_c[b], ctx->copy_stream));
+      used[b] = 1;
+    }
+    CKC(cudaStreamSynchronize(ctx->copy_stream));
+  }
+  CKC(cudaStreamSynchronize(ctx->stream));
+  if (lambda_out) CKC(cudaMemcpy(lambda_out, d_lam, static_cast<size_t>(cells) * n * sizeof(double), cudaMemcpyDeviceToHost));
+  int herr = 0;
+  CKC(cudaMemcpy(&herr, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+#undef CKC
+  cleanup();
+  if (herr) return fail(ctx, SCR_E_DRAWS, "supplied uniforms exhausted (raise draws_per_entry)");
+  return rc;
+}
+
+int scr_debug_philox(scr_ctx* ctx, int64_t count, const uint32_t* ctr4, uint32_t k0, uint32_t k1, uint32_t* out4) {
+  NEED_GPU();
+  if (count <= 0 || !ctr4 || !out4) return fail(ctx, SCR_E_ARG, "bad arguments");
+  uint32_t *d_in = nullptr, *d_out = nullptr;
+  CK(cudaMalloc(&d_in, count * 16));
+  CK(cudaMalloc(&d_out, count * 16));
+  CK(cudaMemcpy(d_in, ctr4, count * 16, cudaMemcpyHostToDevice));
+  scr::debug_philox_kernel<<<static_cast<unsigned>((count + 127) / 128), 128, 0, ctx->stream>>>(count, d_in, k0, k1, d_out);
+  ctx->launches++;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(out4, d_out, count * 16, cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_out);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "debug_philox");
+  return SCR_OK;
+}
+
+int scr_debug_noise(scr_ctx* ctx, int64_t global_cell, uint32_t step, double sigma, uint64_t seed, uint32_t stream, double* out) {
+  NEED_GPU();
+  if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
+  if (!out) return fail(ctx, SCR_E_ARG, "null output");
+  const int n = ctx->op.n, nb = ctx->op.nb;
+  int rc = ensure_stage(ctx, n);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(ctx->d_stage, 0, n * sizeof(double), ctx->stream));
+  const uint64_t gid = static_cast<uint64_t>(global_cell);
+  scr::debug_noise_kernel<<<(nb * 32 + 127) / 128, 128, 0, ctx->stream>>>(
+      nb, static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), step,
+      static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma), static_cast<uint32_t>(seed),
+      static_cast<uint32_t>(seed >> 32) ^ stream, ctx->d_perm, ctx->d_stage);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(out, ctx->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SCR_OK;
+}
+
+int64_t scr_launch_count(const scr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+double scr_last_kernel_ms(const scr_ctx* ctx) { return ctx ? ctx->last_ms : -1.0; }
+int scr_step_kernel_stats(scr_ctx* ctx, double* total_ms, int64_t* launches, int reset) {
+  if (!ctx) return SCR_E_ARG;
+  if (total_ms) *total_ms = ctx->total_step_ms;
+  if (launches) *launches = ctx->total_step_launches;
+  if (reset) { ctx->total_step_ms = 0.0; ctx->total_step_launches = 0; }
+  return SCR_OK;
+}
+
+}  // extern "C"

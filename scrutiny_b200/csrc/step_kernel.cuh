@@ -1,0 +1,449 @@
+// Persistent time-stepping kernel of the MatriSeq hot path (sm_100a).
+//
+// Replaces the per-cell Python loops findCellNextState x developCell
+// (reference MatriSeq.py:683-736, 503-537) and, in PROBE mode, the sampled-cell convergence loop of
+// findOptimalIterations / findOptimalAlpha (MatriSeq.py:650-669, 456-482).
+//
+// Design (DESIGN.md "Stepper"):
+//   * a work item is a GROUP of CPG cells (4 x fp32 or 2 x fp64) whose states sit interleaved in
+//     shared memory as x[gene][cell] -- 16 bytes per gene -- for ALL timesteps of the phase;
+//   * WQ warps own one group; lane (blk, lane) owns genes blk*128 + j*32 + lane, j = 0..3, so one
+//     Philox4x32-10 call yields the four normals of one cell and every smem access is a
+//     conflict-free 128-bit row;
+//   * W is a sliced-ELL operator over permuted genes (long rows first, regulators next, rest by
+//     in-degree) so that 32-row tiles are homogeneous; rows longer than `cap` spill into fixed
+//     length chunks evaluated by all lanes first (phase A) and added by the owner (phase B);
+//   * only the leading `npp` genes (those any row can read) are ping-ponged between two buffers;
+//     the rest are updated in place, which is what lets several groups share one SM;
+//   * operator tables + per-node proj/const are staged once per CTA with a bulk async copy
+//     (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier;
+//   * CTAs are persistent and pull groups (sorted by step count, longest first) from an atomic
+//     counter; each group synchronises on its own named barrier.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace scr {
+
+// ------------------------------------------------------------------------------------------
+// small PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ptx_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ptx_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ptx_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ptx_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ptx_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ptx_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  Checked bit-for-bit against oracle/philox_ref.py.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
+    c1 = static_cast<uint32_t>(p1);
+    c3 = static_cast<uint32_t>(p0);
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// two N(0, sigma^2) values from two words: u1 = 2 - f(wa) in (0,1], theta = 2*pi*f(wb) - 3*pi,
+// f(w) = float in [1,2) built from the top 23 bits.  rscale = -2*ln(2)*sigma^2.
+__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float rscale, float& n_cos, float& n_sin) {
+  const float f1 = __uint_as_float(0x3f800000u | (wa >> 9));
+  const float f2 = __uint_as_float(0x3f800000u | (wb >> 9));
+  const float r = ptx_sqrt(fabsf(ptx_lg2(2.0f - f1) * rscale));   // |.|: never NaN if lg2(1-eps) rounds positive
+  const float th = fmaf(f2, 6.28318530717958647692f, -9.42477796076937971538f);
+  n_cos = r * ptx_cos(th);
+  n_sin = r * ptx_sin(th);
+}
+
+// accurate tanh.  fp32: 1 - 2/(1+e^{2|z|}) with ex2/rcp approximations: absolute error ~2e-7,
+// which enters the state scaled by dt (DESIGN.md "Precision").  fp64: CUDA libm.
+__device__ __forceinline__ float tanh_acc(float z) {
+  const float e = ptx_ex2(fabsf(z) * 2.88539008177792681472f);  // 2*log2(e)
+  const float t = fmaf(-2.0f, ptx_rcp(e + 1.0f), 1.0f);
+  return copysignf(t, z);
+}
+__device__ __forceinline__ double tanh_acc(double z) { return tanh(z); }
+
+// ------------------------------------------------------------------------------------------
+// types
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Traits;
+template <> struct Traits<float> {
+  static constexpr int CPG = 4;
+  struct __align__(8) WEnt { float v; int off; };
+  using PC = float2;
+};
+template <> struct Traits<double> {
+  static constexpr int CPG = 2;
+  struct __align__(16) WEnt { double v; int off; int pad; };
+  using PC = double2;
+};
+
+// 16-byte row of one gene across the group's cells
+template <typename T> struct __align__(16) Row { T v[16 / sizeof(T)]; };
+
+struct __align__(16) Item {   // one cell group
+  int cell[4];                // local slots, -1 = empty lane of the group
+  int steps[4];               // iterations to run (0 for empty)
+  uint32_t base[4];           // iterations already done (noise key)
+  int row[4];                 // position in the caller's list (supplied noise / probe outputs)
+  double scale;               // PROBE: multiplies W (1/alpha ladder, MatriSeq.py:461)
+  double pad_;
+};
+
+template <typename T> struct StepParams {
+  // packed operator (global copies; staged to smem by the kernel)
+  const unsigned char* tab;   // small tables blob
+  const unsigned char* wblob; // tile entries, then long-row chunk entries
+  int tab_bytes, w_bytes;     // multiples of 16
+  int off_slice, off_ovfidx, off_wblk_ptr, off_wblk;  // byte offsets inside tab
+  int off_vrow;               // byte offset of chunk entries inside wblob
+  int n, n_pad, npp, nb, npp_blocks, nlong_blocks, nv, nv_pad, lv;
+  int wq, wq_log2, q;
+  // per-phase
+  const unsigned char* pc;    // n_pad x PC (proj, const + mu), internal order
+  const T* bias;              // n_pad (-mu * rowsum) or nullptr
+  T* state;                   // [cells][n_pad]
+  int64_t ld;
+  const Item* items;
+  int nitems;
+  int* counter;
+  T dt;
+  float rscale;               // -2 ln2 sigma^2
+  uint32_t k0, k1;
+  int64_t cell_offset;
+  // supplied noise (parity mode): [row][noise_steps][n] in ORIGINAL gene order
+  const T* noise;
+  int64_t noise_steps;
+  const int* perm;            // internal -> original gene (or -1)
+  // probe
+  double thresh;
+  int max_iter, avg_num;
+  int* iters_out;
+  double* nd;                 // [k][max_iter]
+};
+
+__host__ __device__ inline size_t group_smem_bytes(int n_pad, int npp, int nv_pad) {
+  return static_cast<size_t>(n_pad + npp + nv_pad) * 16 + 8 * 16 + 64;
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <typename T, bool W_SMEM, bool PROBE, bool SUPPLIED>
+__global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
+  using TR = Traits<T>;
+  using WEnt = typename TR::WEnt;
+  using PC = typename TR::PC;
+  using RowT = Row<T>;
+  constexpr int CPG = TR::CPG;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* s_tab = smem;
+  unsigned char* s_pc = s_tab + p.tab_bytes;
+  unsigned char* s_w = s_pc + static_cast<size_t>(p.n_pad) * sizeof(PC);
+  unsigned char* s_groups = s_w + (W_SMEM ? p.w_bytes : 0);
+  const size_t gbytes = group_smem_bytes(p.n_pad, p.npp, p.nv_pad);
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_groups + static_cast<size_t>(p.q) * gbytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp >> p.wq_log2, wq = warp & (p.wq - 1);
+  const int qthreads = p.wq * 32, qtid = wq * 32 + lane, bar_id = 1 + grp;
+
+  // ---- stage operator tables and the node's proj/const with the bulk-copy engine ----
+  if (threadIdx.x == 0) {
+    mbar_init(s_mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t pc_bytes = static_cast<uint32_t>(p.n_pad * sizeof(PC));
+    mbar_expect_tx(s_mbar, p.tab_bytes + pc_bytes + (W_SMEM ? p.w_bytes : 0));
+    bulk_g2s(s_tab, p.tab, p.tab_bytes, s_mbar);
+    bulk_g2s(s_pc, p.pc, pc_bytes, s_mbar);
+    if (W_SMEM) bulk_g2s(s_w, p.wblob, p.w_bytes, s_mbar);
+  }
+  mbar_wait(s_mbar, 0);
+
+  const int* slice_off = reinterpret_cast<const int*>(s_tab + p.off_slice);
+  const int2* ovfidx = reinterpret_cast<const int2*>(s_tab + p.off_ovfidx);
+  const int* wblk_ptr = reinterpret_cast<const int*>(s_tab + p.off_wblk_ptr);
+  const int* wblk = reinterpret_cast<const int*>(s_tab + p.off_wblk);
+  const unsigned char* wbase = W_SMEM ? s_w : p.wblob;
+  const WEnt* wtile = reinterpret_cast<const WEnt*>(wbase);
+  const WEnt* wchunk = reinterpret_cast<const WEnt*>(wbase + p.off_vrow);
+  const PC* pcs = reinterpret_cast<const PC*>(s_pc);
+
+  unsigned char* bufA = s_groups + static_cast<size_t>(grp) * gbytes;
+  unsigned char* bufB = bufA + static_cast<size_t>(p.n_pad) * 16;
+  RowT* ovf = reinterpret_cast<RowT*>(bufB + static_cast<size_t>(p.npp) * 16);
+  RowT* red = ovf + p.nv_pad;
+  volatile int* ctrl = reinterpret_cast<volatile int*>(red + 8);
+
+  const int my_b0 = wblk_ptr[wq], my_b1 = wblk_ptr[wq + 1];
+
+  for (;;) {
+    if (qtid == 0) ctrl[0] = atomicAdd(p.counter, 1);
+    named_bar_sync(bar_id, qthreads);
+    const int item_idx = ctrl[0];
+    if (item_idx >= p.nitems) break;
+    const Item it = p.items[item_idx];
+
+    // ---- load the group's states: CPG cell rows -> interleaved x[gene][cell] ----
+    for (int g0 = qtid * CPG; g0 < p.n_pad; g0 += qthreads * CPG) {
+      RowT r[CPG];
+#pragma unroll
+      for (int c = 0; c < CPG; ++c) {
+        if (it.cell[c] >= 0) {
+          r[c] = *reinterpret_cast<const RowT*>(p.state + static_cast<int64_t>(it.cell[c]) * p.ld + g0);
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < CPG; ++jj) r[c].v[jj] = T(0);
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < CPG; ++jj) {
+        RowT o;
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) o.v[c] = r[c].v[jj];
+        *reinterpret_cast<RowT*>(bufA + static_cast<size_t>(g0 + jj) * 16) = o;
+      }
+    }
+    named_bar_sync(bar_id, qthreads);
+
+    unsigned char* cur = bufA;   // holds the current values of the ping-ponged genes
+    unsigned char* oth = bufB;
+    int smax = 0;
+    uint32_t gid_lo[CPG], gid_hi[CPG];
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) {
+      smax = max(smax, it.steps[c]);
+      const uint64_t gid = static_cast<uint64_t>(p.cell_offset + (it.cell[c] >= 0 ? it.cell[c] : 0));
+      gid_lo[c] = static_cast<uint32_t>(gid);
+      gid_hi[c] = static_cast<uint32_t>(gid >> 32);
+    }
+    uint32_t alive = 0;       // PROBE: bit c set while cell c is still iterating
+    int iters[CPG];
+    if (PROBE) {
+      smax = p.max_iter;
+#pragma unroll
+      for (int c = 0; c < CPG; ++c) { iters[c] = 0; if (it.cell[c] >= 0) alive |= 1u << c; }
+    }
+    const T wscale = PROBE ? static_cast<T>(it.scale) : T(1);
+
+    for (int s = 0; s < smax; ++s) {
+      // -------- phase A: chunks of rows longer than the cap --------
+      if (p.nv > 0) {
+        for (int v = qtid; v < p.nv_pad; v += qthreads) {
+          T acc[CPG];
+#pragma unroll
+          for (int c = 0; c < CPG; ++c) acc[c] = T(0);
+          for (int k = 0; k < p.lv; ++k) {
+            const WEnt e = wchunk[k * p.nv_pad + v];
+            const RowT xv = *reinterpret_cast<const RowT*>(cur + e.off);
+#pragma unroll
+            for (int c = 0; c < CPG; ++c) acc[c] = fma(e.v, xv.v[c], acc[c]);
+          }
+          RowT o;
+#pragma unroll
+          for (int c = 0; c < CPG; ++c) o.v[c] = acc[c];
+          ovf[v] = o;
+        }
+        named_bar_sync(bar_id, qthreads);
+      }
+
+      T dsum[CPG];
+#pragma unroll
+      for (int c = 0; c < CPG; ++c) dsum[c] = T(0);
+
+      // -------- phase B: tiles + element-wise update, one 128-gene block at a time --------
+      for (int bi = my_b0; bi < my_b1; ++bi) {
+        const int b = wblk[bi];
+        const int gbase = b * 128 + lane;
+        T acc[4][CPG];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int c = 0; c < CPG; ++c) acc[j][c] = T(0);
+          const int o0 = slice_off[b * 4 + j], o1 = slice_off[b * 4 + j + 1];
+          for (int o = o0 + lane; o < o1; o += 32) {
+            const WEnt e = wtile[o];
+            const RowT xv = *reinterpret_cast<const RowT*>(cur + e.off);
+#pragma unroll
+            for (int c = 0; c < CPG; ++c) acc[j][c] = fma(e.v, xv.v[c], acc[j][c]);
+          }
+        }
+        if (b < p.nlong_blocks) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int2 oi = ovfidx[gbase + j * 32];
+            for (int e = oi.x; e < oi.x + oi.y; ++e) {
+              const RowT pv = ovf[e];
+#pragma unroll
+              for (int c = 0; c < CPG; ++c) acc[j][c] += pv.v[c];
+            }
+          }
+        }
+        const bool pp = b < p.npp_blocks;
+        const unsigned char* src = pp ? cur : bufA;
+        unsigned char* dst = pp ? oth : bufA;
+        RowT xo[4];
+        PC pcv[4];
+        T bz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int g = gbase + j * 32;
+          xo[j] = *reinterpret_cast<const RowT*>(src + static_cast<size_t>(g) * 16);
+          pcv[j] = pcs[g];
+          bz[j] = p.bias ? p.bias[g] : T(0);
+        }
+        int og[4];
+        if (SUPPLIED) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) og[j] = p.perm[gbase + j * 32];
+        }
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) {
+          const bool active = PROBE ? ((alive >> c) & 1u) : (s < it.steps[c]);
+          if (active) {   // uniform over the group's warps
+            T nz[4];
+            if (SUPPLIED) {
+              const int64_t nbase = (static_cast<int64_t>(it.row[c]) * p.noise_steps + s) * p.n;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) nz[j] = og[j] >= 0 ? p.noise[nbase + og[j]] : T(0);
+            } else {
+              uint32_t w[4];
+              philox4x32_10(static_cast<uint32_t>(b * 32 + lane), it.base[c] + static_cast<uint32_t>(s),
+                            gid_lo[c], gid_hi[c], p.k0, p.k1, w);
+              float a0, a1, a2, a3;
+              box_muller(w[0], w[1], p.rscale, a0, a1);
+              box_muller(w[2], w[3], p.rscale, a2, a3);
+              nz[0] = a0; nz[1] = a1; nz[2] = a2; nz[3] = a3;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const T x = xo[j].v[c];
+              T drive = acc[j][c];
+              if (PROBE) drive *= wscale;
+              const T z = drive + bz[j] + nz[j];
+              const T t = tanh_acc(z);
+              const T x1 = fma(p.dt, t - x, x);
+              const T xn = fma(pcv[j].x, x1, pcv[j].y);
+              if (PROBE) dsum[c] += fabs(xn - x);
+              xo[j].v[c] = xn;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<RowT*>(dst + static_cast<size_t>(gbase + j * 32) * 16) = xo[j];
+      }
+
+      if (PROBE) {
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) {
+#pragma unroll
+          for (int sh = 16; sh > 0; sh >>= 1) dsum[c] += __shfl_xor_sync(0xffffffffu, dsum[c], sh);
+        }
+        if (lane == 0) {
+          RowT o;
+#pragma unroll
+          for (int c = 0; c < CPG; ++c) o.v[c] = dsum[c];
+          red[wq] = o;
+        }
+      }
+      named_bar_sync(bar_id, qthreads);   // end of step: every new value is in place
+      { unsigned char* t = cur; cur = oth; oth = t; }
+
+      if (PROBE) {
+        if (qtid == 0) {
+#pragma unroll
+          for (int c = 0; c < CPG; ++c) {
+            if ((alive >> c) & 1u) {
+              double tot = 0.0;
+              for (int w = 0; w < p.wq; ++w) tot += static_cast<double>(red[w].v[c]);
+              double* trace = p.nd + static_cast<int64_t>(it.row[c]) * p.max_iter;
+              trace[s] = tot / (static_cast<double>(p.n) * static_cast<double>(p.dt));
+              iters[c] = s + 1;
+              if (s >= p.avg_num - 1) {
+                double acc = 0.0;
+                for (int i = s - p.avg_num + 1; i <= s; ++i) acc += trace[i];
+                if (acc / p.avg_num <= p.thresh) alive &= ~(1u << c);
+              }
+            }
+          }
+          ctrl[1] = static_cast<int>(alive);
+        }
+        named_bar_sync(bar_id, qthreads);
+        alive = static_cast<uint32_t>(ctrl[1]);
+        if (alive == 0) break;
+      }
+    }
+
+    if (PROBE) {
+      if (qtid == 0) {
+#pragma unroll
+        for (int c = 0; c < CPG; ++c)
+          if (it.cell[c] >= 0) p.iters_out[it.row[c]] = iters[c];
+      }
+    } else {
+      // ---- write the group back: interleaved -> CPG cell rows ----
+      for (int g0 = qtid * CPG; g0 < p.n_pad; g0 += qthreads * CPG) {
+        const unsigned char* src = (g0 < p.npp) ? cur : bufA;
+        RowT r[CPG];
+#pragma unroll
+        for (int jj = 0; jj < CPG; ++jj) {
+          const RowT o = *reinterpret_cast<const RowT*>(src + static_cast<size_t>(g0 + jj) * 16);
+#pragma unroll
+          for (int c = 0; c < CPG; ++c) r[c].v[jj] = o.v[c];
+        }
+#pragma unroll
+        for (int c = 0; c < CPG; ++c)
+          if (it.cell[c] >= 0)
+            *reinterpret_cast<RowT*>(p.state + static_cast<int64_t>(it.cell[c]) * p.ld + g0) = r[c];
+      }
+    }
+    named_bar_sync(bar_id, qthreads);   // smem is reused by the next group
+  }
+}
+
+}  // namespace scr

@@ -1,0 +1,202 @@
+"""Thin object wrapper over the C ABI: one ``Engine`` = one ``scr_ctx`` = one GPU.
+
+This is host plumbing only (argument marshalling, error codes -> exceptions); every
+computation happens in the CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .network import dense_to_csr
+
+F32, F64 = 0, 1
+STREAM_STEP, STREAM_PROBE, STREAM_COUNTS, STREAM_ALPHA = 0, 1, 2, 16
+
+
+class ScrutinyError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("scrutiny_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype)) if a is not None else None
+
+
+class Engine:
+    def __init__(self, device=0, precision="f32"):
+        self._lib = _lib.load()
+        self._ctx = _lib.c_ctx()
+        self.precision = precision
+        prec = {"f32": F32, "f64": F64}[precision]
+        rc = self._lib.scr_create(C.byref(self._ctx), int(device), prec)
+        if rc != 0:
+            msg = self._lib.scr_last_error(None)
+            raise ScrutinyError(rc, msg.decode() if msg else "scr_create failed")
+        self.n = None
+        self.cells = 0
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.scr_last_error(self._ctx)
+            raise ScrutinyError(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.scr_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- network ----------------------------------------------------------------------------
+    def set_network(self, gc=None, csr=None, n=None):
+        """``gc``: dense (n, n) float64 as the reference passes it (already divided by alpha),
+        or ``csr=(rowptr, col, val)``."""
+        if csr is None:
+            gc = np.asarray(gc)
+            n = gc.shape[0]
+            csr = dense_to_csr(gc)
+        rowptr, col, val = csr
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        val = _f64(val)
+        n = int(n if n is not None else len(rowptr) - 1)
+        self._check(self._lib.scr_set_network_csr(self._ctx, n, len(val), _ptr(rowptr, C.c_int32),
+                                                  _ptr(col, C.c_int32), _ptr(val, C.c_double)))
+        self.n = n
+
+    def host_matvec(self, x):
+        x = _f64(x)
+        y = np.zeros(self.n)
+        self._check(self._lib.scr_debug_host_matvec(self._ctx, _ptr(x, C.c_double), _ptr(y, C.c_double)))
+        return y
+
+    def layout(self):
+        out = np.zeros(12, dtype=np.int64)
+        self._check(self._lib.scr_get_layout(self._ctx, _ptr(out, C.c_int64), 12))
+        keys = ("n_pad", "pingpong_genes", "tile_slots", "chunks", "chunk_len", "row_cap",
+                "warps_per_group", "groups_per_cta", "smem_bytes", "operator_in_smem",
+                "cells_per_group", "ctas_per_sm")
+        return dict(zip(keys, (int(v) for v in out)))
+
+    # -- states -----------------------------------------------------------------------------
+    def alloc_cells(self, cells, global_offset=0):
+        self._check(self._lib.scr_alloc_cells(self._ctx, int(cells), int(global_offset)))
+        self.cells = int(cells)
+
+    def set_states(self, S, cell0=0):
+        """S: (n, count) float64 view (row stride may exceed count)."""
+        S = np.asarray(S, dtype=np.float64)
+        if S.strides[1] != 8:
+            S = np.ascontiguousarray(S)
+        self._check(self._lib.scr_set_states(self._ctx, int(cell0), S.shape[1], _ptr(S, C.c_double),
+                                             S.strides[0] // 8))
+
+    def set_states_broadcast(self, x0):
+        x0 = _f64(x0)
+        self._check(self._lib.scr_set_states_broadcast(self._ctx, _ptr(x0, C.c_double)))
+
+    def get_states(self, cell0=0, count=None, out=None):
+        count = self.cells - cell0 if count is None else count
+        if out is None:
+            out = np.empty((self.n, count))
+        assert out.dtype == np.float64 and out.strides[1] == 8
+        self._check(self._lib.scr_get_states(self._ctx, int(cell0), int(count), _ptr(out, C.c_double),
+                                             out.strides[0] // 8))
+        return out
+
+    # -- hot path ---------------------------------------------------------------------------
+    def run_phase(self, cell_ids, steps, proj, const, step_base=None, dt=0.01, sigma=0.05, mu=0.0,
+                  seed=0, noise=None):
+        cell_ids = np.ascontiguousarray(cell_ids, dtype=np.int64)
+        steps = np.ascontiguousarray(steps, dtype=np.int32)
+        base = None if step_base is None else np.ascontiguousarray(step_base, dtype=np.int64)
+        proj, const = _f64(proj), _f64(const)
+        nsteps = 0
+        if noise is not None:
+            noise = _f64(noise)
+            assert noise.ndim == 3 and noise.shape[0] == len(cell_ids) and noise.shape[2] == self.n
+            nsteps = noise.shape[1]
+        self._check(self._lib.scr_run_phase(self._ctx, len(cell_ids), _ptr(cell_ids, C.c_int64),
+                                            _ptr(steps, C.c_int32), _ptr(base, C.c_int64),
+                                            _ptr(proj, C.c_double), _ptr(const, C.c_double), dt, sigma, mu,
+                                            int(seed) & (2 ** 64 - 1), _ptr(noise, C.c_double), nsteps))
+
+    def probe(self, sample_ids, proj, const, dt=0.01, sigma=0.05, mu=0.0, thresh=0.1, max_iter=500,
+              avg_num=20, seed=0, stream=STREAM_PROBE, w_div=None, noise=None, want_trace=False):
+        ids = np.ascontiguousarray(sample_ids, dtype=np.int64)
+        k = len(ids)
+        proj, const = _f64(proj), _f64(const)
+        wd = None if w_div is None else _f64(w_div)
+        nz = None
+        if noise is not None:
+            nz = _f64(noise)
+            assert nz.shape == (k, max_iter, self.n)
+        iters = np.zeros(k, dtype=np.int32)
+        trace = np.zeros((k, max_iter)) if want_trace else None
+        self._check(self._lib.scr_probe(self._ctx, k, _ptr(ids, C.c_int64), _ptr(wd, C.c_double),
+                                        _ptr(proj, C.c_double), _ptr(const, C.c_double), dt, sigma, mu, thresh,
+                                        int(max_iter), int(avg_num), int(seed) & (2 ** 64 - 1), int(stream),
+                                        _ptr(nz, C.c_double), _ptr(iters, C.c_int32), _ptr(trace, C.c_double)))
+        return (iters, trace) if want_trace else iters
+
+    def gene_sums(self):
+        out = np.zeros(self.n)
+        self._check(self._lib.scr_gene_sums(self._ctx, _ptr(out, C.c_double)))
+        return out
+
+    def counts(self, shift, size_factors, exp_scale=1.0, seed=0, uniforms=None, out=None, out_device_ptr=None,
+               want_lambda=False):
+        """Returns int32 (cells, n) (host) unless ``out_device_ptr`` (int) is given."""
+        shift, size_factors = _f64(shift), _f64(size_factors)
+        assert len(size_factors) == self.cells and len(shift) == self.n
+        uni, draws = None, 0
+        if uniforms is not None:
+            uni = _f64(uniforms)
+            assert uni.shape[:2] == (self.cells, self.n)
+            draws = uni.shape[2]
+        lam = np.zeros((self.cells, self.n)) if want_lambda else None
+        if out_device_ptr is not None:
+            ptr, on_dev = C.c_void_p(int(out_device_ptr)), 1
+        else:
+            if out is None:
+                out = np.empty((self.cells, self.n), dtype=np.int32)
+            assert out.dtype == np.int32 and out.flags.c_contiguous
+            ptr, on_dev = C.c_void_p(out.ctypes.data), 0
+        self._check(self._lib.scr_counts(self._ctx, _ptr(shift, C.c_double), float(exp_scale),
+                                         _ptr(size_factors, C.c_double), int(seed) & (2 ** 64 - 1),
+                                         _ptr(uni, C.c_double), int(draws), ptr, on_dev, _ptr(lam, C.c_double)))
+        return (out, lam) if want_lambda else out
+
+    # -- debug ------------------------------------------------------------------------------
+    def debug_philox(self, ctr4, k0, k1):
+        ctr = np.ascontiguousarray(ctr4, dtype=np.uint32).reshape(-1, 4)
+        out = np.zeros_like(ctr)
+        self._check(self._lib.scr_debug_philox(self._ctx, len(ctr), _ptr(ctr, C.c_uint32), int(k0), int(k1),
+                                               _ptr(out, C.c_uint32)))
+        return out
+
+    def debug_noise(self, global_cell, step, sigma=0.05, seed=0, stream=STREAM_STEP):
+        out = np.zeros(self.n)
+        self._check(self._lib.scr_debug_noise(self._ctx, int(global_cell), int(step), float(sigma),
+                                              int(seed) & (2 ** 64 - 1), int(stream), _ptr(out, C.c_double)))
+        return out
+
+    def launch_count(self):
+        return int(self._lib.scr_launch_count(self._ctx))
+
+    def step_kernel_stats(self, reset=False):
+        ms = C.c_double(0)
+        n = C.c_int64(0)
+        self._check(self._lib.scr_step_kernel_stats(self._ctx, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value

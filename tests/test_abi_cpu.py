@@ -1,0 +1,98 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol the header declares,
+refuses to compute without a GPU, and the packed operator (gene permutation, sliced-ELL tiles,
+long-row chunks, warp assignment) reproduces W x exactly as a plain product does."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from scrutiny_b200 import _lib, engine
+from scrutiny_b200.network import dense_to_csr, trrust_adjacency
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header():
+    header = open(os.path.join(ROOT, "include", "scrutiny_b200.h")).read()
+    declared = set(re.findall(r"\b(scr_[a-z0-9_]+)\s*\(", header))
+    declared -= {"scr_ctx"}
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), "library does not export " + name
+    assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    assert lib.scr_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    eng = engine.Engine(device=-1)          # packing-only context
+    eng.set_network(np.eye(8) * 0.5)
+    with pytest.raises(engine.ScrutinyError) as e:
+        eng.alloc_cells(4)
+    assert e.value.code == -2
+    with pytest.raises(engine.ScrutinyError):
+        eng.run_phase([0], [1], np.ones(8), np.zeros(8))
+
+
+def power_law_like(n, seed, heavy=0):
+    rng = np.random.RandomState(seed)
+    W = np.zeros((n, n))
+    deg = np.minimum((0.5 * (1 - rng.rand(n)) ** (-1 / 1.05) + 0.5).astype(int), n)
+    regs = rng.choice(n, size=min(n, max(2, n // 3)), replace=False)
+    for r in range(n):
+        k = min(deg[r], len(regs))
+        W[r, rng.choice(regs, size=k, replace=False)] = rng.randn(k)
+    for r in range(heavy):
+        W[rng.randint(n), :] = rng.randn(n) * (rng.rand(n) < 0.6)
+    return W
+
+
+@pytest.mark.parametrize("n,seed,heavy", [(1, 0, 0), (31, 1, 0), (64, 2, 1), (129, 3, 2), (500, 4, 3),
+                                          (1000, 5, 0), (3000, 6, 2)])
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_packed_operator_matches_dense(n, seed, heavy, prec):
+    W = power_law_like(n, seed, heavy)
+    eng = engine.Engine(device=-1, precision=prec)
+    eng.set_network(W)
+    rng = np.random.RandomState(99)
+    for _ in range(2):
+        x = rng.randn(n)
+        y = eng.host_matvec(x)
+        ref = W @ x
+        assert np.allclose(y, ref, rtol=1e-12, atol=1e-12 * max(1.0, np.abs(ref).max()))
+    lay = eng.layout()
+    assert lay["n_pad"] % 128 == 0 and lay["n_pad"] >= n
+    assert lay["smem_bytes"] <= 232448
+
+
+def test_dense_and_empty_networks():
+    rng = np.random.RandomState(3)
+    W = rng.randn(200, 200)                       # fully dense: no long-row chunks expected
+    eng = engine.Engine(device=-1)
+    eng.set_network(W)
+    assert eng.layout()["chunks"] == 0
+    x = rng.randn(200)
+    assert np.allclose(eng.host_matvec(x), W @ x, rtol=1e-12, atol=1e-10)
+    eng.set_network(np.zeros((40, 40)))           # no edges at all
+    assert np.array_equal(eng.host_matvec(np.ones(40)), np.zeros(40))
+
+
+def test_trrust_layout_keeps_two_groups_resident():
+    adj = trrust_adjacency()
+    rng = np.random.RandomState(0)
+    W = adj * rng.rand(*adj.shape)
+    eng = engine.Engine(device=-1)
+    eng.set_network(csr=dense_to_csr(W), n=adj.shape[0])
+    lay = eng.layout()
+    x = rng.randn(adj.shape[0])
+    assert np.allclose(eng.host_matvec(x), W @ x, rtol=1e-12, atol=1e-10)
+    assert lay["groups_per_cta"] >= 2 and lay["pingpong_genes"] <= 1024, lay
+
+
+def test_bad_arguments_are_reported():
+    eng = engine.Engine(device=-1)
+    with pytest.raises(engine.ScrutinyError) as e:
+        eng.set_network(csr=(np.array([0, 2, 1]), np.array([0, 1]), np.array([1.0, 2.0])), n=2)
+    assert e.value.code == -1
+    with pytest.raises(engine.ScrutinyError):
+        eng.set_network(csr=(np.array([0, 1, 2]), np.array([0, 5]), np.array([1.0, 2.0])), n=2)
