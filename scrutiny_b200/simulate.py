@@ -1,0 +1,247 @@
+"""Host scheduler of the lineage simulation: turns the cell-type tree into per-node GPU phases.
+
+Restates the control flow of ``findAllNextStates`` / ``findOptimalIterations`` /
+``transformData`` (reference MatriSeq.py:540-680, 816-891) around the CUDA engine:
+
+  for every node in depth-first order (MS:607-612):
+      record the type of its member cells                               (MS:576)
+      T  <- probe: sample cells, step copies to convergence             (MS:583-586, 616-680)
+      members step k ~ U{0..T} (or Poisson(T)), descendants step T      (MS:587-605)
+
+Cells are sharded over ranks by contiguous global id; the network, proj/const and every host
+random draw are replicated (all ranks hold the same ``numpy.random`` / ``random`` state), the
+probe's iteration sum is the only value exchanged per node, the per-gene sums the only value
+exchanged in the read-out.  Noise is keyed by global cell id, so the result does not depend on
+the number of ranks.
+"""
+import random
+
+import numpy as np
+
+from .engine import STREAM_PROBE
+
+
+class Comm:
+    """Sum all-reduce over ranks.  Single process: identity.  With torch.distributed initialised
+    (NCCL on GPU boxes, gloo in CPU tests) it reduces through a tensor on ``device``."""
+
+    def __init__(self, device=None):
+        self.rank, self.world = 0, 1
+        self._dist = None
+        self._device = device
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self._dist = dist
+                self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+
+    def allreduce_sum(self, arr):
+        arr = np.asarray(arr, dtype=np.float64)
+        if self._dist is None or self.world == 1:
+            return arr
+        import torch
+        t = torch.from_numpy(arr.copy())
+        if self._device is not None:
+            t = t.to(self._device)
+        self._dist.all_reduce(t)
+        return t.cpu().numpy()
+
+
+def shard_bounds(cells, rank, world):
+    """Contiguous [lo, hi) of global cell ids owned by ``rank`` (multiples of 4 except the tail)."""
+    per = -(-cells // world)
+    per = -(-per // 4) * 4
+    lo = min(cells, rank * per)
+    return lo, min(cells, lo + per)
+
+
+class LineageSimulation:
+    """One rank's share of a MatriSeq run.  ``engine`` must hold the network and ``hi - lo`` cells
+    allocated with ``global_offset = lo``."""
+
+    def __init__(self, engine, cells, lo=0, hi=None, comm=None, seed=1337, verbose=False):
+        self.eng = engine
+        self.cells = int(cells)
+        self.lo, self.hi = int(lo), int(cells if hi is None else hi)
+        self.comm = comm or Comm()
+        self.seed = int(seed)
+        self.verbose = verbose
+        self.node_iterations = {}
+        self.phase_log = []
+        self.plan = None
+
+    # -- probe ---------------------------------------------------------------------------------
+    def optimal_iterations(self, members, proj, const, timeStep=0.01, noiseDisp=0.05, convergenceThreshold=0.1,
+                           maxNumIterations=500, convDistAvgNum=20, numToSample=50, geneMeanLevels=0.0, tag=0):
+        """findOptimalIterations (MS:616-680) on the GPU.  ``random.sample`` consumes the same
+        stream position as the reference (MS:644)."""
+        cols = random.sample(list(members) if not isinstance(members, list) else members, numToSample)
+        cols = np.asarray(cols, dtype=np.int64)
+        mine = cols[(cols >= self.lo) & (cols < self.hi)]
+        total = 0.0
+        if len(mine):
+            it = self.eng.probe(mine - self.lo, proj, const, dt=timeStep, sigma=noiseDisp, mu=geneMeanLevels,
+                                thresh=convergenceThreshold, max_iter=maxNumIterations, avg_num=convDistAvgNum,
+                                seed=self.seed + 7919 * (tag + 1), stream=STREAM_PROBE)
+            total = float(it.sum())
+        total = float(self.comm.allreduce_sum(np.array([total]))[0])
+        return int(total / numToSample) - convDistAvgNum            # MS:672-673
+
+    # -- one node -------------------------------------------------------------------------------
+    def run_node(self, node, cellTypesRecord, totalCellIterations, timeStep=0.01, noiseDisp=0.05,
+                 convergenceThreshold=0.1, maxNumIterations=500, convDistAvgNum=20, cellsToSample=50,
+                 cellDevelopmentMode=True, geneMeanLevels=0.0, fixed_iterations=None):
+        members = np.asarray(node.cellTypeMembers, dtype=np.int64)
+        if len(members):
+            cellTypesRecord[members] = int(node.identifier)                      # MS:576
+        if len(members) == 0:                                                    # MS:579-580
+            return 0
+        if fixed_iterations is None:
+            T = self.optimal_iterations(node.cellTypeMembers, node.proj, node.const, timeStep, noiseDisp,
+                                        convergenceThreshold, maxNumIterations, convDistAvgNum, cellsToSample,
+                                        geneMeanLevels, tag=int(node.identifier))
+        else:
+            T = int(fixed_iterations)
+        self.node_iterations[int(node.identifier)] = T
+        if self.verbose:
+            print("Average Iterations: ", T)
+        if cellDevelopmentMode:                                                  # MS:588-591
+            k = np.random.randint(0, T + 1, size=len(members))
+        else:
+            k = np.random.poisson(T, size=len(members))
+        below = np.asarray(node.childCellTypeMembers, dtype=np.int64)
+        ids = np.concatenate([members, below])
+        steps = np.concatenate([k.astype(np.int64), np.full(len(below), T, dtype=np.int64)])
+        own = (ids >= self.lo) & (ids < self.hi)
+        loc_ids, loc_steps = ids[own], steps[own]
+        if len(loc_ids) and loc_steps.max() > 0:
+            self.eng.run_phase(loc_ids - self.lo, loc_steps, node.proj, node.const,
+                               step_base=totalCellIterations[loc_ids], dt=timeStep, sigma=noiseDisp,
+                               mu=geneMeanLevels, seed=self.seed)
+        self.phase_log.append((int(node.identifier), T, int(loc_steps.sum()) if len(loc_ids) else 0))
+        totalCellIterations[ids] += steps                                        # MS:597, 605 (replicated)
+        return T
+
+    # -- whole tree ---------------------------------------------------------------------------
+    def run_tree(self, tree, start, cellTypesRecord, totalCellIterations, fixed_iterations=None, **kw):
+        for node in tree.walk(start):
+            self.run_node(node, cellTypesRecord, totalCellIterations, fixed_iterations=fixed_iterations, **kw)
+
+    # -- read-out -----------------------------------------------------------------------------
+    def gene_shift(self, shape=0.35, rate=0.19, expScale=1.0, geneScale=0.0, expLambda=0.0, gammaDistMean=True):
+        """Per-gene additive shift of MS:851-871 (global means via one all-reduce of n doubles)."""
+        sums = self.comm.allreduce_sum(self.eng.gene_sums())
+        means = sums / self.cells
+        order = np.argsort(means)
+        n = len(means)
+        shift = np.empty(n)
+        if gammaDistMean:
+            target = np.sort(np.log(np.random.gamma(shape, scale=1 / rate, size=n)) / expScale)
+            shift[order] = target - means[order]
+        else:
+            target = np.sort((geneScale + expLambda) / expScale + -1 * np.random.exponential(expLambda, size=n))
+            shift[order] = target
+        return shift
+
+    def counts(self, cellRadiusDisp=0.14, expScale=1.0, out=None, out_device_ptr=None, **kw):
+        """transformData (MS:816-891) for this rank's cells.  Returns (counts (cells_local, n) int32,
+        all cellSizeFactors)."""
+        shift = self.gene_shift(expScale=expScale, **kw)
+        size = np.random.normal(loc=1, scale=cellRadiusDisp, size=self.cells) ** 3   # MS:875-876
+        got = self.eng.counts(shift, size[self.lo:self.hi], exp_scale=expScale, seed=self.seed,
+                              out=out, out_device_ptr=out_device_ptr)
+        return got, size
+
+    # =========================================================================================
+    # prepared (scalable) mode: all per-cell bookkeeping is rank-local, every per-cell random
+    # draw is a pure function of (seed, node, GLOBAL cell id) so that the result does not depend
+    # on the number of ranks.  Distributionally identical to run_node (k ~ U{0..T}, MS:589;
+    # size factor ~ N(1, sd)^3, MS:875-876); used by bench.py and for >= 10^6 cells.
+    # =========================================================================================
+    def prepare(self, tree):
+        """Per node: global member ids (for the probe sample) and the LOCAL slots of this rank's
+        members / descendant cells.  Done once per tree."""
+        self.plan = []
+        for node in tree.walk():
+            mem = np.asarray(node.cellTypeMembers, dtype=np.int64)
+            below = np.asarray(node.childCellTypeMembers, dtype=np.int64)
+            self.plan.append(dict(node=node, members=mem,
+                                  mem_loc=mem[(mem >= self.lo) & (mem < self.hi)] - self.lo,
+                                  below_loc=below[(below >= self.lo) & (below < self.hi)] - self.lo))
+        return self
+
+    def run_all(self, tree=None, counts_out=None, counts_dev_ptr=None, seed=None, timeStep=0.01, noiseDisp=0.05,
+                convergenceThreshold=0.1, maxNumIterations=500, convDistAvgNum=20, cellsToSample=50,
+                geneMeanLevels=0.0, fixed_iterations=None, cellRadiusDisp=0.14, expScale=1.0, do_counts=True):
+        """findAllNextStates + transformData for this rank's shard (tree prepared beforehand).
+        Returns dict(global_cell_steps, local_cell_steps, h2d_bytes, iterations, types, size_factors)."""
+        if self.plan is None:
+            self.prepare(tree)
+        if seed is not None:
+            self.seed = int(seed)
+            np.random.seed(self.seed % (2 ** 32))                                # replicated host draws
+            random.seed(self.seed)
+        nloc = self.hi - self.lo
+        iters = np.zeros(nloc, dtype=np.int64)
+        types = np.zeros(nloc, dtype=np.int64)
+        local_steps, h2d = 0, 0
+        self.node_iterations = {}
+        for p in self.plan:
+            node, mem = p["node"], p["members"]
+            if len(mem) == 0:                                                    # MS:579-580
+                continue
+            types[p["mem_loc"]] = int(node.identifier)
+            if fixed_iterations is None:
+                pick = mem[random.sample(range(len(mem)), cellsToSample)]        # same stream as MS:644
+                mine = pick[(pick >= self.lo) & (pick < self.hi)] - self.lo
+                total = 0.0
+                if len(mine):
+                    it = self.eng.probe(mine, node.proj, node.const, dt=timeStep, sigma=noiseDisp, mu=geneMeanLevels,
+                                        thresh=convergenceThreshold, max_iter=maxNumIterations,
+                                        avg_num=convDistAvgNum, seed=self.seed + 7919 * (int(node.identifier) + 1),
+                                        stream=STREAM_PROBE)
+                    total = float(it.sum())
+                total = float(self.comm.allreduce_sum(np.array([total]))[0])
+                T = int(total / cellsToSample) - convDistAvgNum
+            else:
+                T = int(fixed_iterations)
+            self.node_iterations[int(node.identifier)] = T
+            u = hashed_uniform(self.seed, 2 * int(node.identifier) + 11, p["mem_loc"] + self.lo)
+            k = np.minimum((u * (T + 1)).astype(np.int64), T)
+            ids = np.concatenate([p["mem_loc"], p["below_loc"]])
+            steps = np.concatenate([k, np.full(len(p["below_loc"]), T, dtype=np.int64)])
+            if len(ids) and steps.max() > 0:
+                self.eng.run_phase(ids, steps, node.proj, node.const, step_base=iters[ids], dt=timeStep,
+                                   sigma=noiseDisp, mu=geneMeanLevels, seed=self.seed)
+                h2d += len(ids) * 20 + 16 * len(node.proj)
+            iters[ids] += steps
+            local_steps += int(steps.sum())
+        size = None
+        if do_counts:
+            shift = self.gene_shift(expScale=expScale)
+            gid = np.arange(self.lo, self.hi, dtype=np.int64)
+            u1 = 1.0 - hashed_uniform(self.seed, 5, gid)
+            u2 = hashed_uniform(self.seed, 6, gid)
+            z = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+            size = (1.0 + cellRadiusDisp * z) ** 3                               # MS:875-876
+            self.eng.counts(shift, size, exp_scale=expScale, seed=self.seed, out=counts_out,
+                            out_device_ptr=counts_dev_ptr)
+            h2d += shift.nbytes + size.nbytes
+        glob = float(self.comm.allreduce_sum(np.array([float(local_steps)]))[0])
+        return dict(global_cell_steps=glob, local_cell_steps=local_steps, h2d_bytes=h2d, iterations=iters,
+                    types=types, size_factors=size)
+
+
+def hashed_uniform(seed, salt, ids):
+    """U[0,1) as a pure function of (seed, salt, id): splitmix64 finaliser, 53 bits."""
+    with np.errstate(over="ignore"):
+        x = np.asarray(ids, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        x = x + np.uint64((int(seed) * 0xD1342543DE82EF95 + int(salt) * 0xBF58476D1CE4E5B9) % (2 ** 64))
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    return (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)

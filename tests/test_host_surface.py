@@ -1,0 +1,66 @@
+"""Host-side pieces of the MatriSeq-compatible module against the reference's golden outputs
+(tree construction, initial states) and the multi-rank bookkeeping of the scheduler."""
+import numpy as np
+
+from conftest import seed_all
+
+
+def test_tree_and_initial_states_match_reference(golden):
+    import scrutiny_b200.MatriSeq as ms
+    g = golden("pipeline")
+    ms.init(outputDir=None, seed=1337, verbose=False)
+    n, cells = 40, 166
+    gc, tf = ms.generateGeneCorrelationMatrix(n, "SimulatedPowerLaw", powerLawExponent=2.3)
+    assert np.array_equal(gc, g["gc_unscaled"]) and np.array_equal(tf, g["tf"])
+    tree, projM, constM = ms.formCellTypeTree(n, cells, [-1, 0, 0], [56, 50, 60], [0.1, 0.15, 0.2], tf, [0, 0, 0])
+    assert np.array_equal(projM, g["projM"]) and np.array_equal(constM, g["constM"])
+    for t in range(3):
+        assert list(tree[t].cellTypeMembers) == list(g["members%d" % t])
+    assert list(tree.head().children) == list(g["head_children"])
+    assert list(tree[0].childCellTypeMembers) == list(g["child_members0"])
+    assert list(tree.head().childCellTypeMembers) == list(tree[0].childCellTypeMembers) + list(tree[0].cellTypeMembers)
+    init = ms.generateInitialStates(n, cells)
+    assert np.array_equal(init, g["init"])
+    order = [nd.identifier for nd in tree.walk()]
+    assert order == [-1, 0, 1, 2]
+
+
+def test_invalid_structure_raises_like_reference():
+    import pytest
+    import scrutiny_b200.MatriSeq as ms
+    ms.init(outputDir=None, verbose=False)
+    with pytest.raises(Exception, match="Invalid network structure"):
+        ms.generateGeneCorrelationMatrix(10, "Nope")
+
+
+def test_initial_states_per_cell_branch():
+    import scrutiny_b200.MatriSeq as ms
+    from oracle import matriseq_port as port
+    seed_all(3)
+    a = ms.generateInitialStates(7, 5, sameInitialCell=False, geneMeanLevels=0.25)
+    seed_all(3)
+    b = port.initial_states(7, 5, sameInitialCell=False, geneMeanLevels=0.25)
+    assert np.array_equal(a, b)
+
+
+def test_shard_bounds_cover_all_cells():
+    from scrutiny_b200.simulate import shard_bounds
+    for cells in (1, 7, 100, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(cells, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == cells
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b
+            assert all(lo % 4 == 0 for lo, hi in spans if lo < cells)
+
+
+def test_save_data_writes_the_seven_artefacts(tmp_path):
+    import scrutiny_b200.MatriSeq as ms
+    ms.init(outputDir=str(tmp_path / "out"), verbose=False)
+    n, cells = 4, 3
+    ms.saveData(np.ones((n, cells)), np.zeros(cells, dtype="int64"), np.eye(n), np.ones((2, n)), np.zeros((2, n)),
+                np.ones(cells), np.arange(cells) * 0.01)
+    for name in ("synthscRNAseq", "cellTypesRecord", "gc", "projMatrix", "constMatrix", "cellSizeFactors",
+                 "synthPseudotimes"):
+        assert (tmp_path / "out" / (name + ".npy")).exists()
+    assert np.load(tmp_path / "out" / "synthscRNAseq.npy").shape == (n, cells)
