@@ -6,8 +6,9 @@
 //   perm/inv      internal <-> original gene; order = long rows, then regulators (non-zero
 //                 out-degree, the only genes a row can read), then the rest; each class by
 //                 in-degree descending, so 32-row tiles have near-equal length
-//   tiles         sliced ELL: tile s = genes [32s, 32s+32), entry (s,k,lane) at
-//                 slice_off[s] + 32k + lane, at most `cap` entries per row
+//   tiles         blocked ELL: block b = genes [128b, 128b+128); lane l owns rows 128b + 32j + l
+//                 (j = 0..3); entry k of that row sits at slice_off[b] + (4k + j)*32 + l, so one
+//                 loop trip feeds four independent gathers per lane; at most `cap` entries per row
 //   chunks        the part of a row beyond `cap`, cut into pieces of `lv` entries; chunk v entry k
 //                 at k*nv_pad + v; ovf_start/ovf_cnt give each long row its chunk range
 //   wblk          128-gene blocks assigned to the wq warps of a cell group (LPT on a cost model)
@@ -90,17 +91,16 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
   op.nlong_blocks = (op.nlong + 127) / 128;
 
   // ---- tiles ----
-  const int nslices = op.n_pad / 32;
-  op.slice_off.assign(nslices + 1, 0);
-  for (int s = 0; s < nslices; ++s) {
+  op.slice_off.assign(op.nb + 1, 0);
+  for (int b = 0; b < op.nb; ++b) {
     int len = 0;
-    for (int l = 0; l < 32; ++l) {
-      const int i = s * 32 + l;
+    for (int l = 0; l < 128; ++l) {
+      const int i = b * 128 + l;
       if (i < n) len = std::max(len, std::min(indeg[op.perm[i]], cap));
     }
-    op.slice_off[s + 1] = op.slice_off[s] + 32 * len;
+    op.slice_off[b + 1] = op.slice_off[b] + 128 * len;
   }
-  const int nslots = op.slice_off[nslices];
+  const int nslots = op.slice_off[op.nb];
   op.tile_val.assign(nslots, 0.0);
   op.tile_col.assign(nslots, 0);
   op.rowsum.assign(op.n_pad, 0.0);
@@ -124,14 +124,14 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
 
   for (int i = 0; i < n; ++i) {
     const int r = op.perm[i];
-    const int s = i / 32, lane = i % 32;
+    const int blk = i / 128, j = (i % 128) / 32, lane = i % 32;
     double sum = 0.0;
     for (int k = 0; k < indeg[r]; ++k) {
       const int64_t e = rowptr[r] + k;
       const int ci = op.inv[col[e]];
       sum += val[e];
       if (k < cap) {
-        const int slot = op.slice_off[s] + 32 * k + lane;
+        const int slot = op.slice_off[blk] + (4 * k + j) * 32 + lane;
         op.tile_val[slot] = val[e];
         op.tile_col[slot] = ci;
       } else {
@@ -159,11 +159,9 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
 
   std::vector<double> cost(op.nb, 0.0);
   for (int b = 0; b < op.nb; ++b) {
-    for (int j = 0; j < 4; ++j) {
-      const int s = b * 4 + j;
-      if (s * 32 < n) cost[b] += 140.0;                       // element-wise work of a live tile
-      cost[b] += 7.0 * (op.slice_off[s + 1] - op.slice_off[s]) / 32;
-    }
+    for (int j = 0; j < 4; ++j)
+      if ((b * 4 + j) * 32 < n) cost[b] += 140.0;               // element-wise work of a live 32-row tile
+    cost[b] += 26.0 * (op.slice_off[b + 1] - op.slice_off[b]) / 128;   // one trip = 4 gathers + 16 FMAs
     if (b < op.nlong_blocks)
       for (int i = b * 128; i < b * 128 + 128; ++i) cost[b] += 0.2 * op.ovf_cnt[i];
   }
@@ -207,9 +205,9 @@ inline void host_matvec(const PackedOperator& op, const double* x, double* y) {
       const int b = op.wblk[bi];
       for (int j = 0; j < 4; ++j)
         for (int lane = 0; lane < 32; ++lane) {
-          const int s = b * 4 + j, i = s * 32 + lane;
+          const int i = b * 128 + j * 32 + lane;
           double acc = 0.0;
-          for (int o = op.slice_off[s] + lane; o < op.slice_off[s + 1]; o += 32) acc += op.tile_val[o] * xi[op.tile_col[o]];
+          for (int o = op.slice_off[b] + lane; o < op.slice_off[b + 1]; o += 128) acc += op.tile_val[o + j * 32] * xi[op.tile_col[o + j * 32]];
           if (b < op.nlong_blocks)
             for (int e = op.ovf_start[i]; e < op.ovf_start[i] + op.ovf_cnt[i]; ++e) acc += part[e];
           yi[i] += acc;   // += so a block visited twice (a packing bug) shows up

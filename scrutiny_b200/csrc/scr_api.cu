@@ -90,7 +90,7 @@ template <typename T>
 void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std::vector<unsigned char>& w,
                  int& off_slice, int& off_ovfidx, int& off_wblk_ptr, int& off_wblk, int& off_vrow) {
   using WEnt = typename scr::Traits<T>::WEnt;
-  const int nslices = op.n_pad / 32;
+  const int nslices = op.nb;   // one offset per 128-gene block
   off_slice = 0;
   off_ovfidx = align16(off_slice + (nslices + 1) * 4);
   off_wblk_ptr = align16(off_ovfidx + static_cast<int>(op.ovf_start.size()) * 8);
@@ -300,8 +300,7 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
   p.nitems = static_cast<int>(nitems);
   p.dt = static_cast<T>(dt);
   p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma);
-  p.k0 = static_cast<uint32_t>(seed);
-  p.k1 = static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_STEP);
+  scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_STEP), p.rk);
   T* d_noise = nullptr;
   if (noise) {
     rc = upload_noise<T>(ctx, noise, static_cast<size_t>(m) * noise_steps * ctx->op.n, &d_noise);
@@ -354,8 +353,7 @@ int probe_t(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_
   p.nitems = nitems;
   p.dt = static_cast<T>(dt);
   p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma);
-  p.k0 = static_cast<uint32_t>(seed);
-  p.k1 = static_cast<uint32_t>(seed >> 32) ^ stream;
+  scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ stream, p.rk);
   p.thresh = thresh;
   p.max_iter = max_iter;
   p.avg_num = avg_num;

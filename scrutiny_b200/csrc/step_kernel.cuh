@@ -83,15 +83,48 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// same function with the ten round keys precomputed on the host (kernel parameters live in the
+// constant bank, so each XOR takes its key as an immediate-like operand: no key arithmetic at all)
+struct RoundKeys { uint32_t k[20]; };
+inline void make_round_keys(uint32_t k0, uint32_t k1, RoundKeys& rk) {
+  for (int r = 0; r < 10; ++r) {
+    rk.k[2 * r] = k0;
+    rk.k[2 * r + 1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 const RoundKeys& rk, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ rk.k[2 * r];
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ rk.k[2 * r + 1];
+    c1 = static_cast<uint32_t>(p1);
+    c3 = static_cast<uint32_t>(p0);
+    c0 = n0;
+    c2 = n2;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 // two N(0, sigma^2) values from two words: u1 = 2 - f(wa) in (0,1], theta = 2*pi*f(wb) - 3*pi,
 // f(w) = float in [1,2) built from the top 23 bits.  rscale = -2*ln(2)*sigma^2.
-__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float rscale, float& n_cos, float& n_sin) {
+__device__ __forceinline__ void box_muller_polar(uint32_t wa, uint32_t wb, float rscale, float& r, float& c, float& sn) {
   const float f1 = __uint_as_float(0x3f800000u | (wa >> 9));
   const float f2 = __uint_as_float(0x3f800000u | (wb >> 9));
-  const float r = ptx_sqrt(fabsf(ptx_lg2(2.0f - f1) * rscale));   // |.|: never NaN if lg2(1-eps) rounds positive
+  r = ptx_sqrt(fabsf(ptx_lg2(2.0f - f1) * rscale));   // |.|: never NaN if lg2(1-eps) rounds positive
   const float th = fmaf(f2, 6.28318530717958647692f, -9.42477796076937971538f);
-  n_cos = r * ptx_cos(th);
-  n_sin = r * ptx_sin(th);
+  c = ptx_cos(th);
+  sn = ptx_sin(th);
+}
+__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float rscale, float& n_cos, float& n_sin) {
+  float r, c, sn;
+  box_muller_polar(wa, wb, rscale, r, c, sn);
+  n_cos = r * c;
+  n_sin = r * sn;
 }
 
 // accurate tanh.  fp32: 1 - 2/(1+e^{2|z|}) with ex2/rcp approximations: absolute error ~2e-7,
@@ -102,6 +135,11 @@ __device__ __forceinline__ float tanh_acc(float z) {
   return copysignf(t, z);
 }
 __device__ __forceinline__ double tanh_acc(double z) { return tanh(z); }
+
+// drive + r*u.  fp32: one FFMA.  fp64: the float product first, so the value added is exactly the
+// float the noise dump (scr_debug_noise) reports.
+__device__ __forceinline__ float add_noise(float drive, float r, float u) { return fmaf(r, u, drive); }
+__device__ __forceinline__ double add_noise(double drive, float r, float u) { return drive + static_cast<double>(r * u); }
 
 // ------------------------------------------------------------------------------------------
 // types
@@ -149,7 +187,7 @@ template <typename T> struct StepParams {
   int* counter;
   T dt;
   float rscale;               // -2 ln2 sigma^2
-  uint32_t k0, k1;
+  RoundKeys rk;               // Philox round keys of (seed, stream)
   int64_t cell_offset;
   // supplied noise (parity mode): [row][noise_steps][n] in ORIGINAL gene order
   const T* noise;
@@ -204,7 +242,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   }
   mbar_wait(s_mbar, 0);
 
-  const int* slice_off = reinterpret_cast<const int*>(s_tab + p.off_slice);
+  const int* blk_off = reinterpret_cast<const int*>(s_tab + p.off_slice);   // block b: slots [blk_off[b], blk_off[b+1])
   const int2* ovfidx = reinterpret_cast<const int2*>(s_tab + p.off_ovfidx);
   const int* wblk_ptr = reinterpret_cast<const int*>(s_tab + p.off_wblk_ptr);
   const int* wblk = reinterpret_cast<const int*>(s_tab + p.off_wblk);
@@ -261,6 +299,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       gid_lo[c] = static_cast<uint32_t>(gid);
       gid_hi[c] = static_cast<uint32_t>(gid >> 32);
     }
+    int smin = 0x7fffffff;    // steps every cell of the group takes (0 if a slot is empty)
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) smin = min(smin, it.steps[c]);
+    constexpr uint32_t full_mask = (1u << CPG) - 1u;
     uint32_t alive = 0;       // PROBE: bit c set while cell c is still iterating
     int iters[CPG];
     if (PROBE) {
@@ -296,20 +338,29 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       for (int c = 0; c < CPG; ++c) dsum[c] = T(0);
 
       // -------- phase B: tiles + element-wise update, one 128-gene block at a time --------
+      // all cells of the group active (the common case: groups are sorted by step count): no
+      // per-cell branches, so the four Philox chains and sixteen tanh's interleave freely
+      const bool all_active = PROBE ? (alive == full_mask) : (s < smin);
       for (int bi = my_b0; bi < my_b1; ++bi) {
         const int b = wblk[bi];
         const int gbase = b * 128 + lane;
         T acc[4][CPG];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          const T b0 = p.bias ? p.bias[gbase + j * 32] : T(0);
 #pragma unroll
-          for (int c = 0; c < CPG; ++c) acc[j][c] = T(0);
-          const int o0 = slice_off[b * 4 + j], o1 = slice_off[b * 4 + j + 1];
-          for (int o = o0 + lane; o < o1; o += 32) {
-            const WEnt e = wtile[o];
-            const RowT xv = *reinterpret_cast<const RowT*>(cur + e.off);
+          for (int c = 0; c < CPG; ++c) acc[j][c] = b0;
+        }
+        {
+          const int o1 = blk_off[b + 1];
+          for (int o = blk_off[b] + lane; o < o1; o += 128) {
 #pragma unroll
-            for (int c = 0; c < CPG; ++c) acc[j][c] = fma(e.v, xv.v[c], acc[j][c]);
+            for (int j = 0; j < 4; ++j) {
+              const WEnt e = wtile[o + j * 32];
+              const RowT xv = *reinterpret_cast<const RowT*>(cur + e.off);
+#pragma unroll
+              for (int c = 0; c < CPG; ++c) acc[j][c] = fma(e.v, xv.v[c], acc[j][c]);
+            }
           }
         }
         if (b < p.nlong_blocks) {
@@ -328,48 +379,73 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         unsigned char* dst = pp ? oth : bufA;
         RowT xo[4];
         PC pcv[4];
-        T bz[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int g = gbase + j * 32;
           xo[j] = *reinterpret_cast<const RowT*>(src + static_cast<size_t>(g) * 16);
           pcv[j] = pcs[g];
-          bz[j] = p.bias ? p.bias[g] : T(0);
         }
-        int og[4];
-        if (SUPPLIED) {
+        const uint32_t ctr0 = static_cast<uint32_t>(b * 32 + lane);
+        if (all_active && !SUPPLIED) {
+          uint32_t w[CPG][4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) og[j] = p.perm[gbase + j * 32];
-        }
+          for (int c = 0; c < CPG; ++c)
+            philox4x32_10_rk(ctr0, it.base[c] + static_cast<uint32_t>(s), gid_lo[c], gid_hi[c], p.rk, w[c]);
 #pragma unroll
-        for (int c = 0; c < CPG; ++c) {
-          const bool active = PROBE ? ((alive >> c) & 1u) : (s < it.steps[c]);
-          if (active) {   // uniform over the group's warps
-            T nz[4];
-            if (SUPPLIED) {
-              const int64_t nbase = (static_cast<int64_t>(it.row[c]) * p.noise_steps + s) * p.n;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) nz[j] = og[j] >= 0 ? p.noise[nbase + og[j]] : T(0);
-            } else {
-              uint32_t w[4];
-              philox4x32_10(static_cast<uint32_t>(b * 32 + lane), it.base[c] + static_cast<uint32_t>(s),
-                            gid_lo[c], gid_hi[c], p.k0, p.k1, w);
-              float a0, a1, a2, a3;
-              box_muller(w[0], w[1], p.rscale, a0, a1);
-              box_muller(w[2], w[3], p.rscale, a2, a3);
-              nz[0] = a0; nz[1] = a1; nz[2] = a2; nz[3] = a3;
-            }
+          for (int c = 0; c < CPG; ++c) {
+            float r0, c0, s0, r1, c1, s1;
+            box_muller_polar(w[c][0], w[c][1], p.rscale, r0, c0, s0);
+            box_muller_polar(w[c][2], w[c][3], p.rscale, r1, c1, s1);
+            const float rr[4] = {r0, r0, r1, r1};
+            const float uu[4] = {c0, s0, c1, s1};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const T x = xo[j].v[c];
               T drive = acc[j][c];
               if (PROBE) drive *= wscale;
-              const T z = drive + bz[j] + nz[j];
-              const T t = tanh_acc(z);
+              const T t = tanh_acc(add_noise(drive, rr[j], uu[j]));
               const T x1 = fma(p.dt, t - x, x);
               const T xn = fma(pcv[j].x, x1, pcv[j].y);
               if (PROBE) dsum[c] += fabs(xn - x);
               xo[j].v[c] = xn;
+            }
+          }
+        } else {
+          int og[4];
+          if (SUPPLIED) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) og[j] = p.perm[gbase + j * 32];
+          }
+#pragma unroll
+          for (int c = 0; c < CPG; ++c) {
+            const bool active = PROBE ? ((alive >> c) & 1u) : (s < it.steps[c]);
+            if (active) {   // uniform over the group's warps
+              T nz[4];
+              float rr[4] = {0.f, 0.f, 0.f, 0.f}, uu[4] = {0.f, 0.f, 0.f, 0.f};
+              if (SUPPLIED) {
+                const int64_t nbase = (static_cast<int64_t>(it.row[c]) * p.noise_steps + s) * p.n;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) nz[j] = og[j] >= 0 ? p.noise[nbase + og[j]] : T(0);
+              } else {
+                uint32_t w[4];
+                philox4x32_10_rk(ctr0, it.base[c] + static_cast<uint32_t>(s), gid_lo[c], gid_hi[c], p.rk, w);
+                box_muller_polar(w[0], w[1], p.rscale, rr[0], uu[0], uu[1]);
+                box_muller_polar(w[2], w[3], p.rscale, rr[2], uu[2], uu[3]);
+                rr[1] = rr[0];
+                rr[3] = rr[2];
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const T x = xo[j].v[c];
+                T drive = acc[j][c];
+                if (PROBE) drive *= wscale;
+                const T z = SUPPLIED ? drive + nz[j] : add_noise(drive, rr[j], uu[j]);
+                const T t = tanh_acc(z);
+                const T x1 = fma(p.dt, t - x, x);
+                const T xn = fma(pcv[j].x, x1, pcv[j].y);
+                if (PROBE) dsum[c] += fabs(xn - x);
+                xo[j].v[c] = xn;
+              }
             }
           }
         }
