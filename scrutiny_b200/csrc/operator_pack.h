@@ -66,7 +66,7 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
   cap = env_int("SCR_ROW_CAP", cap);
   if (cap < 1) cap = 1;
   op.cap = cap;
-  op.lv = std::max(1, env_int("SCR_CHUNK_LEN", std::min(cap, 16)));
+  op.lv = std::max(1, env_int("SCR_CHUNK_LEN", std::min(cap, 8)));
 
   // ---- gene order ----
   std::vector<int> order(n);

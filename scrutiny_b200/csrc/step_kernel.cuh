@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   volatile int* ctrl = reinterpret_cast<volatile int*>(red + 8);
 
   const int my_b0 = wblk_ptr[wq], my_b1 = wblk_ptr[wq + 1];
+  const bool has_bias = p.bias != nullptr;
 
   for (;;) {
     if (qtid == 0) ctrl[0] = atomicAdd(p.counter, 1);
@@ -341,15 +342,16 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       // all cells of the group active (the common case: groups are sorted by step count): no
       // per-cell branches, so the four Philox chains and sixteen tanh's interleave freely
       const bool all_active = PROBE ? (alive == full_mask) : (s < smin);
+      int bnext = (my_b0 < my_b1) ? wblk[my_b0] : 0;
       for (int bi = my_b0; bi < my_b1; ++bi) {
-        const int b = wblk[bi];
+        const int b = bnext;
+        bnext = (bi + 1 < my_b1) ? wblk[bi + 1] : 0;   // prefetched a block ahead: off the critical path
         const int gbase = b * 128 + lane;
         T acc[4][CPG];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const T b0 = p.bias ? p.bias[gbase + j * 32] : T(0);
 #pragma unroll
-          for (int c = 0; c < CPG; ++c) acc[j][c] = b0;
+          for (int c = 0; c < CPG; ++c) acc[j][c] = T(0);
         }
         {
           const int o1 = blk_off[b + 1];
@@ -361,6 +363,14 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
 #pragma unroll
               for (int c = 0; c < CPG; ++c) acc[j][c] = fma(e.v, xv.v[c], acc[j][c]);
             }
+          }
+        }
+        if (has_bias) {   // geneMeanLevels != 0 only: -mu * rowsum(W)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const T b0 = p.bias[gbase + j * 32];
+#pragma unroll
+            for (int c = 0; c < CPG; ++c) acc[j][c] += b0;
           }
         }
         if (b < p.nlong_blocks) {

@@ -1,0 +1,121 @@
+"""World-size-2 (gloo, CPU) test of the multi-rank scheduler: cells sharded by contiguous global id,
+the probe's iteration sum and the per-gene sums all-reduced, every per-cell draw keyed by the global
+cell id.  The CUDA engine is replaced by a test double built on the oracle (tests may use it), whose
+"device noise" is also a pure function of the global cell id -- so two ranks must reproduce the
+single-rank run exactly, which is the property the real engine is tested for on the GPU
+(test_results_do_not_depend_on_sharding)."""
+import os
+import socket
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleEngine:
+    """Stand-in for scrutiny_b200.engine.Engine over oracle/fast_oracle.py (float64)."""
+
+    def __init__(self, W, cells, offset):
+        from oracle import fast_oracle as fo
+        self.fo, self.W, self.n = fo, fo.as_operator(W), W.shape[0]
+        self.cells, self.offset = cells, offset
+        self.X = np.zeros((cells, self.n))
+
+    def _noise(self, gid, step, sigma, seed, salt):
+        rs = np.random.RandomState((int(gid) * 1000003 + int(step) * 7919 + int(seed) + salt) % (2 ** 32))
+        return sigma * rs.randn(self.n)
+
+    def set_states_broadcast(self, x0):
+        self.X[:] = x0
+
+    def run_phase(self, cell_ids, steps, proj, const, step_base=None, dt=0.01, sigma=0.05, mu=0.0, seed=0, noise=None):
+        for i, (c, k) in enumerate(zip(cell_ids, steps)):
+            for s in range(int(k)):
+                nz = self._noise(self.offset + c, step_base[i] + s, sigma, seed, 0)
+                self.X[c] = self.fo.step_batch(self.W, self.X[c][None], proj, const, dt, nz[None], mu)[0]
+
+    def probe(self, sample_ids, proj, const, dt=0.01, sigma=0.05, mu=0.0, thresh=0.1, max_iter=500, avg_num=20,
+              seed=0, stream=1, **kw):
+        noise = np.stack([[self._noise(self.offset + c, s, sigma, seed, 17) for s in range(max_iter)] for c in sample_ids])
+        it, _, _ = self.fo.probe(self.W, self.X[np.asarray(sample_ids)], proj, const, dt, noise, thresh, max_iter, avg_num, mu)
+        return it.astype(np.int32)
+
+    def gene_sums(self):
+        return self.X.sum(axis=0)
+
+    def counts(self, shift, size, exp_scale=1.0, seed=0, out=None, out_device_ptr=None):
+        self.lam = self.fo.poisson_lambda(self.X.T, shift, exp_scale, size).T
+        return self.lam
+
+
+def build_case():
+    from scrutiny_b200.lineage import Tree
+    np.random.seed(5)
+    n, cells = 24, 44
+    W = (np.random.rand(n, n) < 0.15) * np.random.randn(n, n) / 0.6
+    tree = Tree()
+    tree.add_head(-1, [], np.zeros(n), np.ones(n), 0)
+    members = [np.arange(0, 12), np.arange(12, 27), np.arange(27, 44)]
+    proj1 = np.ones(n)
+    proj1[3] = 0
+    const1 = np.zeros(n)
+    const1[3] = 1.0
+    tree.add_node(0, members[0], np.zeros(n), np.ones(n), 0, -1)
+    tree.add_node(1, members[1], const1, proj1, 0, 0)
+    tree.add_node(2, members[2], np.zeros(n), np.ones(n), 0, 0)
+    tree[0].setChildCellTypeMembers(np.concatenate([members[1], members[2]]))
+    tree[-1].setChildCellTypeMembers(np.arange(cells))
+    x0 = np.random.uniform(-1, 1, n)
+    return n, cells, W, tree, x0
+
+
+def run_rank(rank, world, port_no, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from scrutiny_b200.simulate import Comm, LineageSimulation, shard_bounds
+    if world > 1:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port_no, rank=rank, world_size=world)
+    n, cells, W, tree, x0 = build_case()
+    lo, hi = shard_bounds(cells, rank, world)
+    eng = OracleEngine(W, hi - lo, lo)
+    eng.set_states_broadcast(x0)
+    sim = LineageSimulation(eng, cells, lo, hi, comm=Comm(), seed=99)
+    res = sim.run_all(tree, seed=99, cellsToSample=6, maxNumIterations=60, convDistAvgNum=5, convergenceThreshold=0.6)
+    np.savez(out_path, lo=lo, hi=hi, X=eng.X, iters=res["iterations"], types=res["types"], size=res["size_factors"],
+             lam=eng.lam, glob=res["global_cell_steps"], T=np.array(sorted(sim.node_iterations.items())))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_ranks_reproduce_one_rank(tmp_path):
+    import torch.multiprocessing as mp
+    single = str(tmp_path / "single.npz")
+    run_rank(0, 1, 0, single)
+    port_no = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = []
+    for r in range(2):
+        p = ctx.Process(target=run_rank, args=(r, 2, port_no, str(tmp_path / ("rank%d.npz" % r))))
+        p.start()
+        procs.append(p)
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    one = np.load(single)
+    parts = [np.load(str(tmp_path / ("rank%d.npz" % r))) for r in range(2)]
+    assert int(parts[0]["lo"]) == 0 and int(parts[0]["hi"]) == int(parts[1]["lo"]) and int(parts[1]["hi"]) == 44
+    assert np.array_equal(parts[0]["T"], one["T"]) and np.array_equal(parts[1]["T"], one["T"])
+    for key in ("X", "iters", "types", "size", "lam"):
+        assert np.allclose(np.concatenate([parts[0][key], parts[1][key]]), one[key], rtol=1e-13, atol=1e-13), key
+    assert float(parts[0]["glob"]) == float(one["glob"]) == float(one["iters"].sum())
+    assert one["iters"].max() > 0 and len(np.unique(one["types"])) == 3
