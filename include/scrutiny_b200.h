@@ -54,7 +54,9 @@ int scr_sync(scr_ctx* ctx);
 
 /* ---- regulatory network: the `gc` argument of developCell (MS:503-504), already divided by
  * alpha (EX:49).  CSR over rows = regulated gene.  Builds the on-chip operator (gene
- * permutation, sliced-ELL tiles, long-row chunks).  Any density is accepted. */
+ * permutation, blocked-ELL tiles, long-row chunks).  Any density is accepted; float32 contexts
+ * switch scr_run_phase to the tcgen05 3xTF32 GEMM stepper when nnz >= 5 % of n^2 (the sparse
+ * operator is still built: the probe and float64 contexts use it). */
 int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* rowptr,
                         const int32_t* col, const double* val);
 /* same from a dense row-major (n, n) float64 matrix (what the reference passes around) */
@@ -66,7 +68,7 @@ int scr_debug_host_matvec(const scr_ctx* ctx, const double* x, double* y);
 /* Layout facts for DESIGN.md / tests: out[0]=n_pad, [1]=ping-pong genes, [2]=tile slots,
  * [3]=long-row chunks, [4]=chunk length, [5]=row cap, [6]=warps per cell group,
  * [7]=cell groups per CTA, [8]=dynamic smem bytes, [9]=operator resident in smem (0/1),
- * [10]=cells per group, [11]=CTAs per SM. */
+ * [10]=cells per group, [11]=dense (tcgen05 GEMM) stepper selected (0/1). */
 int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count);
 
 /* ---- cell states: `currentStates` of findAllNextStates (MS:540-554) --------------------------- */

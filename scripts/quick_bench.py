@@ -32,6 +32,8 @@ def main():
         gc, tf = network.generate_gene_correlation_matrix(0, "TRRUST")
     elif a.net == "dense500":
         gc, tf = network.generate_gene_correlation_matrix(500, "Random", networkSparsity=0.01)
+    elif a.net == "dense3000":
+        gc, tf = network.generate_gene_correlation_matrix(3000, "Random", networkSparsity=0.5)
     else:
         raise SystemExit("unknown net")
     n = gc.shape[0]
@@ -52,8 +54,9 @@ def main():
         wall = time.time() - t0
         ms, _ = e.step_kernel_stats()
         cs = float(steps.sum())
-        print("rep %d: kernel %.2f ms  wall %.2f ms  %.1f M cell-steps/s  algorithmic %.0f GB/s (%.1f%% of 6556)" % (
-            r, ms, wall * 1e3, cs / ms / 1e3, cs * 8 * n / ms / 1e6, cs * 8 * n / ms / 1e6 / 65.562), flush=True)
+        print("rep %d: kernel %.2f ms  wall %.2f ms  %.1f M cell-steps/s  algorithmic %.0f GB/s (%.1f%% of 6556)  "
+              "3xTF32-issued %.1f TFLOP/s" % (r, ms, wall * 1e3, cs / ms / 1e3, cs * 8 * n / ms / 1e6,
+                                            cs * 8 * n / ms / 1e6 / 65.562, cs * 6.0 * n * n / ms / 1e9), flush=True)
     s = e.get_states(0, 4)
     print("finite:", np.isfinite(s).all(), "range", s.min(), s.max())
 

@@ -42,8 +42,11 @@ inline int env_int(const char* name, int dflt) {
   return (v && *v) ? std::atoi(v) : dflt;
 }
 
+// identity_order: keep the caller's gene order and no row cap (dense networks: every row is long and
+// every gene is read, so sorting buys nothing and the GEMM path needs the natural order);
+// pad_to: n_pad is rounded up to a multiple of this (128 for the sparse path, 256 for the GEMM tiles)
 inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32_t* col, const double* val,
-                          PackedOperator& op, std::string& err) {
+                          PackedOperator& op, std::string& err, bool identity_order = false, int pad_to = 128) {
   if (n <= 0 || nnz < 0 || !rowptr || (nnz > 0 && (!col || !val))) { err = "bad CSR arguments"; return false; }
   if (rowptr[0] != 0 || rowptr[n] != nnz) { err = "rowptr does not span nnz"; return false; }
   for (int r = 0; r < n; ++r)
@@ -54,7 +57,7 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
   op = PackedOperator();
   op.n = n;
   op.nnz = nnz;
-  op.n_pad = (n + 127) / 128 * 128;
+  op.n_pad = (n + pad_to - 1) / pad_to * pad_to;
   op.nb = op.n_pad / 128;
 
   std::vector<int> indeg(n), outdeg(n, 0);
@@ -65,18 +68,23 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
   int cap = std::max(8, static_cast<int>(2.0 * mean_in + 0.999));
   cap = env_int("SCR_ROW_CAP", cap);
   if (cap < 1) cap = 1;
+  if (identity_order) {
+    cap = 1;
+    for (int r = 0; r < n; ++r) cap = std::max(cap, rowptr[r + 1] - rowptr[r]);
+  }
   op.cap = cap;
   op.lv = std::max(1, env_int("SCR_CHUNK_LEN", std::min(cap, 8)));
 
   // ---- gene order ----
   std::vector<int> order(n);
   std::iota(order.begin(), order.end(), 0);
-  auto cls = [&](int g) { return indeg[g] > cap ? 0 : (outdeg[g] > 0 ? 1 : 2); };
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-    const int ca = cls(a), cb = cls(b);
-    if (ca != cb) return ca < cb;
-    return indeg[a] > indeg[b];
-  });
+  auto cls = [&](int g) { return identity_order ? 1 : (indeg[g] > cap ? 0 : (outdeg[g] > 0 ? 1 : 2)); };
+  if (!identity_order)
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      const int ca = cls(a), cb = cls(b);
+      if (ca != cb) return ca < cb;
+      return indeg[a] > indeg[b];
+    });
   op.perm.assign(op.n_pad, -1);
   op.inv.assign(n, -1);
   int n_read = 0;

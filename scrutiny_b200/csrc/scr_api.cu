@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "dense_kernel.cuh"
 #include "operator_pack.h"
 #include "step_kernel.cuh"
 
@@ -41,6 +42,17 @@ struct scr_ctx {
   int q = 1;
   bool w_smem = false;
   size_t gbytes = 0, fixed_bytes = 0;
+
+  // dense (tcgen05 3xTF32) path
+  bool dense_mode = false;
+  float *d_whi = nullptr, *d_wlo = nullptr;      // [n_pad][n_pad] hi / lo splits of W
+  CUtensorMap tm_bhi, tm_blo;
+  float *d_x[2] = {nullptr, nullptr}, *d_xlo[2] = {nullptr, nullptr};   // working set [rows_cap][n_pad]
+  int64_t rows_cap = 0;
+  int *d_row_cell = nullptr, *d_row_steps = nullptr, *d_row_src = nullptr, *d_tile_steps = nullptr;
+  uint32_t* d_row_base = nullptr;
+  int64_t* d_row_gid = nullptr;
+  int64_t dense_launches = 0;
 
   // cells
   void* d_state = nullptr;
@@ -126,8 +138,48 @@ void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std:
 void free_network(scr_ctx* ctx) {
   if (ctx->host_only) return;
   cudaFree(ctx->d_tab); cudaFree(ctx->d_w); cudaFree(ctx->d_perm); cudaFree(ctx->d_inv);
-  cudaFree(ctx->d_pc); cudaFree(ctx->d_bias);
+  cudaFree(ctx->d_pc); cudaFree(ctx->d_bias); cudaFree(ctx->d_whi); cudaFree(ctx->d_wlo);
   ctx->d_tab = ctx->d_w = nullptr; ctx->d_perm = ctx->d_inv = nullptr; ctx->d_pc = ctx->d_bias = nullptr;
+  ctx->d_whi = ctx->d_wlo = nullptr;
+}
+
+void free_dense_work(scr_ctx* ctx) {
+  for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_x[i]); cudaFree(ctx->d_xlo[i]); ctx->d_x[i] = ctx->d_xlo[i] = nullptr; }
+  cudaFree(ctx->d_row_cell); cudaFree(ctx->d_row_steps); cudaFree(ctx->d_row_src); cudaFree(ctx->d_tile_steps);
+  cudaFree(ctx->d_row_base); cudaFree(ctx->d_row_gid);
+  ctx->d_row_cell = ctx->d_row_steps = ctx->d_row_src = ctx->d_tile_steps = nullptr;
+  ctx->d_row_base = nullptr; ctx->d_row_gid = nullptr;
+  ctx->rows_cap = 0;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+// fp32 matrix [rows][cols], row pitch ld elements, boxes of box_rows x 32 columns, 128-byte swizzle
+int make_tmap(scr_ctx* ctx, CUtensorMap* tm, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(ctx, SCR_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(scr::dense::BK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, SCR_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ")");
+  return SCR_OK;
 }
 
 int choose_config(scr_ctx* ctx) {
@@ -313,6 +365,122 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
   return rc;
 }
 
+
+// ---- dense path: one tcgen05 GEMM launch per timestep over the phase's working set ----
+int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t* steps, const int64_t* step_base,
+                    const double* proj, const double* cnst, double dt, double sigma, double mu, uint64_t seed,
+                    const double* noise, int64_t noise_steps) {
+  namespace D = scr::dense;
+  const PackedOperator& op = ctx->op;
+  const int n = op.n, ld = op.n_pad;
+  int smax = 0;
+  for (int64_t i = 0; i < m; ++i) {
+    if (cell_ids[i] < 0 || cell_ids[i] >= ctx->cells) return fail(ctx, SCR_E_ARG, "cell id out of range");
+    if (steps[i] < 0) return fail(ctx, SCR_E_ARG, "negative step count");
+    smax = std::max(smax, steps[i]);
+  }
+  if (noise && smax > noise_steps) return fail(ctx, SCR_E_ARG, "supplied noise shorter than the longest cell");
+  if (smax == 0) return SCR_OK;
+  // rows sorted by step count, longest first: tile t is finished after steps[t*128] launches
+  std::vector<int64_t> bucket(static_cast<size_t>(smax) + 2, 0);
+  for (int64_t i = 0; i < m; ++i) if (steps[i] > 0) bucket[smax - steps[i] + 1]++;
+  for (int s = 0; s <= smax; ++s) bucket[s + 1] += bucket[s];
+  const int64_t live = bucket[smax];
+  std::vector<int64_t> order(live);
+  {
+    std::vector<int64_t> pos(bucket.begin(), bucket.end() - 1);
+    for (int64_t i = 0; i < m; ++i) if (steps[i] > 0) order[pos[smax - steps[i]]++] = i;
+  }
+  const int64_t m_pad = (live + D::BM - 1) / D::BM * D::BM;
+  const int m_tiles = static_cast<int>(m_pad / D::BM);
+  std::vector<int> h_cell(m_pad, -1), h_steps(m_pad, 0), h_src(m_pad, 0), h_tile(m_tiles, 0);
+  std::vector<uint32_t> h_base(m_pad, 0);
+  std::vector<int64_t> h_gid(m_pad, 0);
+  for (int64_t r = 0; r < live; ++r) {
+    const int64_t i = order[r];
+    h_cell[r] = static_cast<int>(cell_ids[i]);
+    h_steps[r] = steps[i];
+    h_src[r] = static_cast<int>(i);
+    h_base[r] = static_cast<uint32_t>(step_base ? step_base[i] : 0);
+    h_gid[r] = ctx->cell_offset + cell_ids[i];
+  }
+  for (int t = 0; t < m_tiles; ++t) h_tile[t] = h_steps[static_cast<size_t>(t) * D::BM];
+  if (m_pad > ctx->rows_cap) {
+    free_dense_work(ctx);
+    const size_t bytes = static_cast<size_t>(m_pad) * ld * 4;
+    for (int i = 0; i < 2; ++i) { CK(cudaMalloc(&ctx->d_x[i], bytes)); CK(cudaMalloc(&ctx->d_xlo[i], bytes)); }
+    CK(cudaMalloc(&ctx->d_row_cell, m_pad * 4)); CK(cudaMalloc(&ctx->d_row_steps, m_pad * 4));
+    CK(cudaMalloc(&ctx->d_row_src, m_pad * 4)); CK(cudaMalloc(&ctx->d_tile_steps, (m_pad / D::BM) * 4));
+    CK(cudaMalloc(&ctx->d_row_base, m_pad * 4)); CK(cudaMalloc(&ctx->d_row_gid, m_pad * 8));
+    ctx->rows_cap = m_pad;
+  }
+  CK(cudaMemcpyAsync(ctx->d_row_cell, h_cell.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_row_steps, h_steps.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_row_src, h_src.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_tile_steps, h_tile.data(), m_tiles * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_row_base, h_base.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_row_gid, h_gid.data(), m_pad * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+  scr::StepParams<float> sp;           // reuse the node upload (proj/const/bias in identity order)
+  fill_common(ctx, sp);
+  int rc = upload_node<float>(ctx, proj, cnst, mu, sp);
+  if (rc) return rc;
+
+  CUtensorMap tm_a[2], tm_alo[2];
+  for (int i = 0; i < 2; ++i) {
+    if ((rc = make_tmap(ctx, &tm_a[i], ctx->d_x[i], m_pad, ld, ld, D::BM))) return rc;
+    if ((rc = make_tmap(ctx, &tm_alo[i], ctx->d_xlo[i], m_pad, ld, ld, D::BM))) return rc;
+  }
+  float* d_noise = nullptr;
+  if (noise) {
+    rc = upload_noise<float>(ctx, noise, static_cast<size_t>(m) * noise_steps * n, &d_noise);
+    if (rc) return rc;
+  }
+  D::Params p;
+  std::memset(&p, 0, sizeof(p));
+  p.ld = ld; p.n_tiles = ld / D::BN; p.k_blocks = ld / D::BK; p.n = n;
+  p.pc = static_cast<const float2*>(ctx->d_pc);
+  p.bias = sp.bias;
+  p.row_steps = ctx->d_row_steps; p.row_base = ctx->d_row_base; p.row_gid = ctx->d_row_gid; p.row_src = ctx->d_row_src;
+  p.dt = static_cast<float>(dt);
+  p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma);
+  scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_STEP), p.rk);
+  p.noise = d_noise; p.noise_steps = noise_steps;
+
+  CK(cudaFuncSetAttribute(D::dense_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM_BYTES));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  D::gather_rows_kernel<<<static_cast<unsigned>(m_pad), 256, 0, ctx->stream>>>(
+      static_cast<const float*>(ctx->d_state), ld, ctx->d_row_cell, static_cast<int>(live), ctx->d_x[0], ctx->d_xlo[0], ld);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  int active_tiles = m_tiles;
+  for (int s = 0; s < smax; ++s) {
+    while (active_tiles > 0 && h_tile[active_tiles - 1] <= s) --active_tiles;
+    const int cur = s & 1;
+    p.x_cur = ctx->d_x[cur]; p.x_next = ctx->d_x[cur ^ 1]; p.xlo_next = ctx->d_xlo[cur ^ 1];
+    p.m_tiles = active_tiles; p.s = s;
+    const int grid = std::min(active_tiles * p.n_tiles, ctx->sm_count);
+    D::dense_step_kernel<<<grid, D::NUM_THREADS, D::SMEM_BYTES, ctx->stream>>>(tm_a[cur], tm_alo[cur], ctx->tm_bhi, ctx->tm_blo, p);
+    ctx->launches++;
+    ctx->dense_launches++;
+  }
+  CK(cudaGetLastError());
+  D::scatter_rows_kernel<<<static_cast<unsigned>(m_pad), 256, 0, ctx->stream>>>(
+      static_cast<float*>(ctx->d_state), ld, ctx->d_row_cell, static_cast<int>(live), ctx->d_x[0], ctx->d_x[1], ctx->d_tile_steps, ld);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_noise);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "dense stepper");
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_ms = ms;
+  ctx->total_step_ms += ms;
+  ctx->total_step_launches += smax;
+  return SCR_OK;
+}
+
 template <typename T>
 int probe_t(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_div, const double* proj,
             const double* cnst, double dt, double sigma, double mu, double thresh, int32_t max_iter,
@@ -448,6 +616,7 @@ void scr_destroy(scr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     free_network(ctx);
+    free_dense_work(ctx);
     cudaFree(ctx->d_state); cudaFree(ctx->d_items); cudaFree(ctx->d_counter); cudaFree(ctx->d_err); cudaFree(ctx->d_stage);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -471,7 +640,13 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
   if (ctx->cells > 0 && ctx->has_net && n != ctx->op.n) return fail(ctx, SCR_E_STATE, "cells are allocated for a different n");
   PackedOperator op;
   std::string err;
-  if (!scr::pack_operator(n, nnz, rowptr, col, val, op, err)) return fail(ctx, SCR_E_ARG, err);
+  // density switch (north_star): sparse networks -> smem-resident SpMM stepper; dense ones -> tcgen05 GEMM
+  const double density = n > 0 ? static_cast<double>(nnz) / (static_cast<double>(n) * n) : 0.0;
+  const int dense_env = scr::env_int("SCR_DENSE", -1);
+  const bool dense = ctx->prec == SCR_F32 && n > 0 && (dense_env == 1 || (dense_env != 0 && density >= 0.05 && n >= 64));
+  if (!scr::pack_operator(n, nnz, rowptr, col, val, op, err, dense, dense ? scr::dense::BN : 128)) return fail(ctx, SCR_E_ARG, err);
+  if (ctx->cells > 0 && ctx->has_net && dense != ctx->dense_mode)
+    return fail(ctx, SCR_E_STATE, "network density class changed while cells are allocated");
   // the gene order must not change under allocated cells (alpha rescaling keeps the pattern, hence the order)
   if (ctx->cells > 0 && ctx->has_net && op.perm != ctx->op.perm)
     return fail(ctx, SCR_E_STATE, "network pattern changed while cells are allocated");
@@ -498,7 +673,31 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
     CK(cudaMemcpy(ctx->d_w, w.data(), w.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_perm, o.perm.data(), o.n_pad * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_inv, o.inv.data(), o.n * sizeof(int), cudaMemcpyHostToDevice));
+    if (dense) {
+      // B operands of the 3xTF32 GEMM: W (the tensor core truncates it to tf32) and its residual
+      const size_t ld = o.n_pad, cnt = ld * ld;
+      std::vector<float> whi(cnt, 0.f), wlo(cnt, 0.f);
+      for (int r = 0; r < n; ++r)
+        for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+          const float w = static_cast<float>(val[e]);
+          uint32_t bits;
+          std::memcpy(&bits, &w, 4);
+          bits &= 0xffffe000u;
+          float hi;
+          std::memcpy(&hi, &bits, 4);
+          whi[r * ld + col[e]] = w;
+          wlo[r * ld + col[e]] = w - hi;
+        }
+      CK(cudaMalloc(&ctx->d_whi, cnt * 4));
+      CK(cudaMalloc(&ctx->d_wlo, cnt * 4));
+      CK(cudaMemcpy(ctx->d_whi, whi.data(), cnt * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(ctx->d_wlo, wlo.data(), cnt * 4, cudaMemcpyHostToDevice));
+      int rc2 = make_tmap(ctx, &ctx->tm_bhi, ctx->d_whi, ld, ld, ld, scr::dense::BN);
+      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo, ctx->d_wlo, ld, ld, ld, scr::dense::BN);
+      if (rc2) return rc2;
+    }
   }
+  ctx->dense_mode = dense;
   ctx->has_net = true;
   return SCR_OK;
 }
@@ -530,7 +729,7 @@ int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count) {
   const PackedOperator& o = ctx->op;
   const int64_t v[12] = {o.n_pad, o.npp, static_cast<int64_t>(o.tile_val.size()), o.nv, o.lv, o.cap, o.wq, ctx->q,
                          static_cast<int64_t>(ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + ctx->q * ctx->gbytes),
-                         ctx->w_smem ? 1 : 0, ctx->cpg(), 1};
+                         ctx->w_smem ? 1 : 0, ctx->cpg(), ctx->dense_mode ? 1 : 0};
   for (int i = 0; i < count && i < 12; ++i) out[i] = v[i];
   return SCR_OK;
 }
@@ -625,6 +824,8 @@ int scr_run_phase(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (m < 0 || (m > 0 && (!cell_ids || !steps)) || !proj || !cnst) return fail(ctx, SCR_E_ARG, "bad arguments");
   if (m == 0) return SCR_OK;
+  if (ctx->dense_mode)
+    return run_phase_dense(ctx, m, cell_ids, steps, step_base, proj, cnst, dt, sigma, mu, seed, noise, noise_steps);
   if (ctx->prec == SCR_F64)
     return run_phase_t<double>(ctx, m, cell_ids, steps, step_base, proj, cnst, dt, sigma, mu, seed, noise, noise_steps);
   return run_phase_t<float>(ctx, m, cell_ids, steps, step_base, proj, cnst, dt, sigma, mu, seed, noise, noise_steps);
@@ -753,10 +954,17 @@ int scr_debug_noise(scr_ctx* ctx, int64_t global_cell, uint32_t step, double sig
   if (rc) return rc;
   CK(cudaMemsetAsync(ctx->d_stage, 0, n * sizeof(double), ctx->stream));
   const uint64_t gid = static_cast<uint64_t>(global_cell);
-  scr::debug_noise_kernel<<<(nb * 32 + 127) / 128, 128, 0, ctx->stream>>>(
-      nb, static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), step,
-      static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma), static_cast<uint32_t>(seed),
-      static_cast<uint32_t>(seed >> 32) ^ stream, ctx->d_perm, ctx->d_stage);
+  const float rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma);
+  if (ctx->dense_mode) {
+    scr::RoundKeys rk;
+    scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ stream, rk);
+    scr::dense::debug_noise_dense_kernel<<<(n / 4 + 128) / 128, 128, 0, ctx->stream>>>(
+        n, static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), step, rscale, rk, ctx->d_stage);
+  } else {
+    scr::debug_noise_kernel<<<(nb * 32 + 127) / 128, 128, 0, ctx->stream>>>(
+        nb, static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), step, rscale, static_cast<uint32_t>(seed),
+        static_cast<uint32_t>(seed >> 32) ^ stream, ctx->d_perm, ctx->d_stage);
+  }
   CK(cudaGetLastError());
   ctx->launches++;
   CK(cudaMemcpyAsync(out, ctx->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -86,7 +86,7 @@ class Engine:
         self._check(self._lib.scr_get_layout(self._ctx, _ptr(out, C.c_int64), 12))
         keys = ("n_pad", "pingpong_genes", "tile_slots", "chunks", "chunk_len", "row_cap",
                 "warps_per_group", "groups_per_cta", "smem_bytes", "operator_in_smem",
-                "cells_per_group", "ctas_per_sm")
+                "cells_per_group", "dense_stepper")
         return dict(zip(keys, (int(v) for v in out)))
 
     # -- states -----------------------------------------------------------------------------
