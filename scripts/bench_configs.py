@@ -1,0 +1,88 @@
+"""Runs BASELINE.json's other configurations end to end on ONE GPU (they are parity-test shapes, not the
+contract bench line) and prints one JSON line each: alpha search + lineage run + count read-out, all on the
+GPU through the same scheduler bench.py uses.
+    python scripts/bench_configs.py [c1 c2 c3 c4]
+c1 Random n=500 sparsity 0.01 (99 % dense), 1000 cells, one type          -> dense (tcgen05) path
+c2 TRRUST n=2895, 10000 cells, 7-type / 4-leaf tree                       -> sparse path
+c3 SimulatedPowerLaw n=3000 gamma=2.5, one GPU's shard (12500 cells) of 100k -> sparse path
+c4 Random n=3000 sparsity 0.5, 200000 cells, one type                     -> dense (tcgen05) path
+"""
+import json
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import scrutiny_b200.MatriSeq as ms  # noqa: E402
+from scrutiny_b200 import engine as eng_mod  # noqa: E402
+from scrutiny_b200.network import dense_to_csr  # noqa: E402
+from scrutiny_b200.simulate import LineageSimulation  # noqa: E402
+
+TREE7 = ([-1, 0, 0, 1, 1, 2, 2], [0.04, 0.08, 0.08, 0.2, 0.2, 0.2, 0.2])
+CONFIGS = {
+    "c1": dict(n=500, structure="Random", kw=dict(networkSparsity=0.01), cells=1000, tree=([-1], [1.0]), const=0.0),
+    "c2": dict(n=0, structure="TRRUST", kw={}, cells=10000, tree=TREE7, const=0.05),
+    "c3": dict(n=3000, structure="SimulatedPowerLaw", kw=dict(powerLawExponent=2.5), cells=12500, tree=TREE7, const=0.05),
+    "c4": dict(n=3000, structure="Random", kw=dict(networkSparsity=0.5), cells=200000, tree=([-1], [1.0]), const=0.0),
+}
+
+
+def run(name):
+    cfg = CONFIGS[name]
+    ms.init(outputDir=None, seed=1337, verbose=False)
+    t0 = time.time()
+    gc, tf = ms.generateGeneCorrelationMatrix(cfg["n"], cfg["structure"], **cfg["kw"])
+    n = gc.shape[0]
+    parents, shares = cfg["tree"]
+    cells = cfg["cells"]
+    counts = [int(round(s * cells)) for s in shares]
+    counts[-1] = cells - sum(counts[:-1])
+    tree, projM, constM = ms.formCellTypeTree(n, cells, parents, counts, [cfg["const"]] * len(parents), tf, [0] * len(parents))
+    x0 = 2.0 * np.random.rand(n) - 1.0
+    t_setup = time.time() - t0
+    t0 = time.time()
+    alpha = ms.findOptimalAlpha(n, gc, tree, np.repeat(x0[:, None], 64, axis=1), numToSample=50)
+    t_alpha = time.time() - t0
+    gc /= alpha
+    e = eng_mod.Engine(0, "f32")
+    e.set_network(csr=dense_to_csr(gc), n=n)
+    e.alloc_cells(cells)
+    lay = e.layout()
+    sim = LineageSimulation(e, cells, seed=1337)
+    for node in tree.walk():
+        node.cellTypeMembers = np.asarray(node.cellTypeMembers, dtype=np.int64)
+        node.childCellTypeMembers = np.asarray(node.childCellTypeMembers, dtype=np.int64)
+    sim.prepare(tree)
+    out = np.empty((cells, n), dtype=np.int32)
+    best = None
+    for rep in range(3):
+        e.set_states_broadcast(x0)
+        e.step_kernel_stats(reset=True)
+        t0 = time.time()
+        res = sim.run_all(tree, counts_out=out, seed=100 + rep)
+        wall = time.time() - t0
+        kms, launches = e.step_kernel_stats()
+        if best is None or wall < best["wall_s"]:
+            best = dict(wall_s=wall, kernel_ms=kms, kernel_launches=launches, cell_steps=res["global_cell_steps"])
+    cs = best["cell_steps"]
+    line = {"config": name, "genes": n, "nnz": int(np.count_nonzero(gc)), "cells": cells, "alpha": alpha,
+            "path": "dense tcgen05 3xTF32" if lay["dense_stepper"] else "sparse smem-resident",
+            "node_iterations": sim.node_iterations, "cell_steps": cs,
+            "cell_steps_per_s_whole_job": cs / best["wall_s"], "cell_steps_per_s_kernel": cs / (best["kernel_ms"] / 1e3),
+            "wall_s": best["wall_s"], "kernel_ms": best["kernel_ms"], "kernel_launches": best["kernel_launches"],
+            "alpha_search_s": t_alpha, "setup_s": t_setup, "counts_sum": int(out.sum()), "zero_fraction": float((out == 0).mean())}
+    if lay["dense_stepper"]:
+        line["tflops_3xtf32_issued"] = cs * 6.0 * n * n / (best["kernel_ms"] / 1e3) / 1e12
+    else:
+        line["algorithmic_GBps"] = cs * 8.0 * n / (best["kernel_ms"] / 1e3) / 1e9
+        line["frac_of_hbm_6556"] = line["algorithmic_GBps"] / 6556.2
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    for name in (sys.argv[1:] or ["c1", "c2", "c3", "c4"]):
+        run(name)

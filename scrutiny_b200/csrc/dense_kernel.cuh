@@ -48,6 +48,11 @@ struct Params {
   RoundKeys rk;
   const float* noise;        // supplied noise [row_src][noise_steps][n] or nullptr
   int64_t noise_steps;
+  // convergence probe (MatriSeq.py:650-669): per-row divisor of the drive (alpha ladder) and the
+  // per-(gene tile, row) partial sums of |x' - x| of this step, summed on the host in a fixed order
+  const float* row_scale;    // nullptr = 1
+  float* rowdiff;            // [n_tiles][m_pad] for THIS step, or nullptr
+  int m_pad;
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
@@ -199,6 +204,8 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_const
       float* orow = p.x_next + static_cast<int64_t>(row) * p.ld + nt * BN;
       float* lrow = p.xlo_next + static_cast<int64_t>(row) * p.ld + nt * BN;
       const float* nrow = p.noise ? p.noise + (static_cast<int64_t>(p.row_src[row]) * p.noise_steps + p.s) * p.n : nullptr;
+      const float scale = p.row_scale ? p.row_scale[row] : 1.f;
+      float dsum = 0.f;
 
       mbar_wait_parity(&tfull[ab], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -231,12 +238,14 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_const
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int i = 4 * v + e;
-              float z = __uint_as_float(acc[i]) + nz[e];
-              if (p.bias) z += p.bias[g0 + i];
+              float drive = __uint_as_float(acc[i]);
+              if (p.bias) drive += p.bias[g0 + i];
+              const float z = p.row_scale ? fmaf(drive, scale, nz[e]) : drive + nz[e];
               const float tt = tanh_acc(z);
               const float x1 = fmaf(p.dt, tt - xo[i], xo[i]);
               const float2 pcv = pc_tile[ch * 16 + i];
               xn[i] = fmaf(pcv.x, x1, pcv.y);
+              dsum += fabsf(xn[i] - xo[i]);
             }
           }
         } else {
@@ -255,6 +264,7 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_const
           *reinterpret_cast<float4*>(lrow + ch * 16 + v * 4) = l;
         }
       }
+      if (p.rowdiff) p.rowdiff[static_cast<int64_t>(nt) * p.m_pad + row] = dsum;
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&tempty[ab]);
       if (++ab == 2) { ab = 0; aph ^= 1u; }

@@ -438,7 +438,7 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
   }
   D::Params p;
   std::memset(&p, 0, sizeof(p));
-  p.ld = ld; p.n_tiles = ld / D::BN; p.k_blocks = ld / D::BK; p.n = n;
+  p.ld = ld; p.n_tiles = ld / D::BN; p.k_blocks = ld / D::BK; p.n = n; p.m_pad = static_cast<int>(m_pad);
   p.pc = static_cast<const float2*>(ctx->d_pc);
   p.bias = sp.bias;
   p.row_steps = ctx->d_row_steps; p.row_base = ctx->d_row_base; p.row_gid = ctx->d_row_gid; p.row_src = ctx->d_row_src;
@@ -478,6 +478,129 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
   ctx->last_ms = ms;
   ctx->total_step_ms += ms;
   ctx->total_step_launches += smax;
+  return SCR_OK;
+}
+
+
+// ---- dense probe: the sampled cells are stepped max_iter times through the GEMM stepper (copies, the
+// states are not written back); each step leaves per-row sums of |x' - x|; the stopping rule of
+// MatriSeq.py:657-668 is then applied per cell on the host (a converged cell's later steps are
+// simply ignored, which is what stopping it would have produced).  Steps run in chunks so that the
+// launch loop ends as soon as every cell has converged.
+int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_div, const double* proj,
+                const double* cnst, double dt, double sigma, double mu, double thresh, int32_t max_iter,
+                int32_t avg_num, uint64_t seed, uint32_t stream, const double* noise, int32_t* iters_out,
+                double* normdiff_out) {
+  namespace D = scr::dense;
+  const PackedOperator& op = ctx->op;
+  const int n = op.n, ld = op.n_pad;
+  const int64_t m_pad = (static_cast<int64_t>(k) + D::BM - 1) / D::BM * D::BM;
+  const int m_tiles = static_cast<int>(m_pad / D::BM), n_tiles = ld / D::BN;
+  std::vector<int> h_cell(m_pad, -1), h_steps(m_pad, 0), h_src(m_pad, 0);
+  std::vector<uint32_t> h_base(m_pad, 0);
+  std::vector<int64_t> h_gid(m_pad, 0);
+  std::vector<float> h_scale(m_pad, 1.f);
+  for (int i = 0; i < k; ++i) {
+    if (sample_ids[i] < 0 || sample_ids[i] >= ctx->cells) return fail(ctx, SCR_E_ARG, "sample id out of range");
+    h_cell[i] = static_cast<int>(sample_ids[i]);
+    h_steps[i] = max_iter;
+    h_src[i] = i;
+    h_gid[i] = ctx->cell_offset + sample_ids[i];
+    if (w_div) h_scale[i] = static_cast<float>(1.0 / w_div[i]);
+  }
+  // private working set (the phase working set of scr_run_phase is left alone)
+  float *x[2] = {nullptr, nullptr}, *xlo[2] = {nullptr, nullptr}, *d_scale = nullptr, *d_diff = nullptr, *d_noise = nullptr;
+  int *d_cell = nullptr, *d_steps = nullptr, *d_src = nullptr;
+  uint32_t* d_base = nullptr;
+  int64_t* d_gid = nullptr;
+  const int chunk = 64;
+  const size_t diff_per_step = static_cast<size_t>(n_tiles) * m_pad;
+  auto cleanup = [&]() {
+    for (int i = 0; i < 2; ++i) { cudaFree(x[i]); cudaFree(xlo[i]); }
+    cudaFree(d_scale); cudaFree(d_diff); cudaFree(d_noise); cudaFree(d_cell); cudaFree(d_steps); cudaFree(d_src);
+    cudaFree(d_base); cudaFree(d_gid);
+  };
+#define CKP(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
+  const size_t bytes = static_cast<size_t>(m_pad) * ld * 4;
+  for (int i = 0; i < 2; ++i) { CKP(cudaMalloc(&x[i], bytes)); CKP(cudaMalloc(&xlo[i], bytes)); }
+  CKP(cudaMalloc(&d_scale, m_pad * 4)); CKP(cudaMalloc(&d_diff, diff_per_step * chunk * 4));
+  CKP(cudaMalloc(&d_cell, m_pad * 4)); CKP(cudaMalloc(&d_steps, m_pad * 4)); CKP(cudaMalloc(&d_src, m_pad * 4));
+  CKP(cudaMalloc(&d_base, m_pad * 4)); CKP(cudaMalloc(&d_gid, m_pad * 8));
+  CKP(cudaMemcpyAsync(d_scale, h_scale.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_cell, h_cell.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_steps, h_steps.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_src, h_src.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_base, h_base.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_gid, h_gid.data(), m_pad * 8, cudaMemcpyHostToDevice, ctx->stream));
+  scr::StepParams<float> sp;
+  fill_common(ctx, sp);
+  int rc = upload_node<float>(ctx, proj, cnst, mu, sp);
+  if (rc) { cleanup(); return rc; }
+  CUtensorMap tm_a[2], tm_alo[2];
+  for (int i = 0; i < 2; ++i) {
+    if ((rc = make_tmap(ctx, &tm_a[i], x[i], m_pad, ld, ld, D::BM)) || (rc = make_tmap(ctx, &tm_alo[i], xlo[i], m_pad, ld, ld, D::BM))) {
+      cleanup();
+      return rc;
+    }
+  }
+  if (noise) {
+    rc = upload_noise<float>(ctx, noise, static_cast<size_t>(k) * max_iter * n, &d_noise);
+    if (rc) { cleanup(); return rc; }
+  }
+  D::Params p;
+  std::memset(&p, 0, sizeof(p));
+  p.ld = ld; p.n_tiles = n_tiles; p.k_blocks = ld / D::BK; p.n = n; p.m_tiles = m_tiles; p.m_pad = static_cast<int>(m_pad);
+  p.pc = static_cast<const float2*>(ctx->d_pc);
+  p.bias = sp.bias;
+  p.row_steps = d_steps; p.row_base = d_base; p.row_gid = d_gid; p.row_src = d_src; p.row_scale = d_scale;
+  p.dt = static_cast<float>(dt);
+  p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma);
+  scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ stream, p.rk);
+  p.noise = d_noise; p.noise_steps = max_iter;
+  CKP(cudaFuncSetAttribute(D::dense_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM_BYTES));
+  D::gather_rows_kernel<<<static_cast<unsigned>(m_pad), 256, 0, ctx->stream>>>(
+      static_cast<const float*>(ctx->d_state), ld, d_cell, k, x[0], xlo[0], ld);
+  CKP(cudaGetLastError());
+  ctx->launches++;
+  std::vector<double> nd(static_cast<size_t>(k) * max_iter, 0.0);
+  std::vector<int> iters(k, 0);
+  std::vector<char> done(k, 0);
+  std::vector<float> h_diff(diff_per_step * chunk);
+  const int grid = std::min(m_tiles * n_tiles, ctx->sm_count);
+  int ndone = 0;
+  for (int s0 = 0; s0 < max_iter && ndone < k; s0 += chunk) {
+    const int cnt = std::min(chunk, max_iter - s0);
+    for (int j = 0; j < cnt; ++j) {
+      const int s = s0 + j, cur = s & 1;
+      p.x_cur = x[cur]; p.x_next = x[cur ^ 1]; p.xlo_next = xlo[cur ^ 1]; p.s = s;
+      p.rowdiff = d_diff + diff_per_step * j;
+      D::dense_step_kernel<<<grid, D::NUM_THREADS, D::SMEM_BYTES, ctx->stream>>>(tm_a[cur], tm_alo[cur], ctx->tm_bhi, ctx->tm_blo, p);
+      ctx->launches++;
+    }
+    CKP(cudaGetLastError());
+    CKP(cudaMemcpyAsync(h_diff.data(), d_diff, diff_per_step * cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CKP(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < k; ++i) {
+      if (done[i]) continue;
+      double* trace = nd.data() + static_cast<size_t>(i) * max_iter;
+      for (int j = 0; j < cnt && !done[i]; ++j) {
+        const int s = s0 + j;
+        double tot = 0.0;
+        for (int t = 0; t < n_tiles; ++t) tot += static_cast<double>(h_diff[diff_per_step * j + static_cast<size_t>(t) * m_pad + i]);
+        trace[s] = tot / (static_cast<double>(n) * static_cast<double>(static_cast<float>(dt)));
+        iters[i] = s + 1;
+        if (s >= avg_num - 1) {
+          double acc = 0.0;
+          for (int q = s - avg_num + 1; q <= s; ++q) acc += trace[q];
+          if (acc / avg_num <= thresh) { done[i] = 1; ++ndone; }
+        }
+      }
+    }
+  }
+#undef CKP
+  for (int i = 0; i < k; ++i) iters_out[i] = iters[i];
+  if (normdiff_out) std::memcpy(normdiff_out, nd.data(), nd.size() * sizeof(double));
+  cleanup();
   return SCR_OK;
 }
 
@@ -838,6 +961,8 @@ int scr_probe(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* 
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (k <= 0 || !sample_ids || !proj || !cnst || !iters_out || max_iter <= 0 || avg_num <= 0)
     return fail(ctx, SCR_E_ARG, "bad arguments");
+  if (ctx->dense_mode && scr::env_int("SCR_DENSE_PROBE", 1))
+    return probe_dense(ctx, k, sample_ids, w_div, proj, cnst, dt, sigma, mu, thresh, max_iter, avg_num, seed, stream, noise, iters_out, normdiff_out);
   if (ctx->prec == SCR_F64)
     return probe_t<double>(ctx, k, sample_ids, w_div, proj, cnst, dt, sigma, mu, thresh, max_iter, avg_num, seed, stream, noise, iters_out, normdiff_out);
   return probe_t<float>(ctx, k, sample_ids, w_div, proj, cnst, dt, sigma, mu, thresh, max_iter, avg_num, seed, stream, noise, iters_out, normdiff_out);
