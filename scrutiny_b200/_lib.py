@@ -41,6 +41,7 @@ SIGNATURES = {
     "scr_debug_philox": (C.c_int, [c_ctx, C.c_int64, _u32p, C.c_uint32, C.c_uint32, _u32p]),
     "scr_debug_noise": (C.c_int, [c_ctx, C.c_int64, C.c_uint32, C.c_double, C.c_uint64, C.c_uint32, _f64p]),
     "scr_launch_count": (C.c_int64, [c_ctx]),
+    "scr_debug_path_launches": (C.c_int64, [c_ctx, C.c_int]),
     "scr_last_kernel_ms": (C.c_double, [c_ctx]),
     "scr_step_kernel_stats": (C.c_int, [c_ctx, _f64p, _i64p, C.c_int]),
 }

@@ -66,10 +66,10 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity)
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra LAB_DONE;\n\t"
       "bra LAB_WAIT;\n\t"
-      "LAB_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "LAB_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {

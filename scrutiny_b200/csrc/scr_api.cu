@@ -14,6 +14,7 @@
 #include "dense_kernel.cuh"
 #include "operator_pack.h"
 #include "step_kernel.cuh"
+#include "step_kernel_ws.cuh"
 
 using scr::Item;
 using scr::PackedOperator;
@@ -52,7 +53,7 @@ struct scr_ctx {
   int *d_row_cell = nullptr, *d_row_steps = nullptr, *d_row_src = nullptr, *d_tile_steps = nullptr;
   uint32_t* d_row_base = nullptr;
   int64_t* d_row_gid = nullptr;
-  int64_t dense_launches = 0;
+  int64_t dense_launches = 0, ws_launches = 0;
 
   // cells
   void* d_state = nullptr;
@@ -232,8 +233,54 @@ int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
   return SCR_OK;
 }
 
+// warp-specialised float32 stepper (step_kernel_ws.cuh): EXPERIMENT, opt-in with SCR_WS=1.  Measured
+// slower than the single-role kernel on B200 (131 vs 180 M cell-steps/s, power law n=3000): the update
+// warps are latency-bound per warp and the noise tiles squeeze L1 (operator hit rate 96 % -> 43 %);
+// see DESIGN.md 3.1 and profiles/r1_ws_experiment.txt
+int launch_step_ws(scr_ctx* ctx, scr::StepParams<float>& p, int nitems, bool* used) {
+  *used = false;
+  const int q = std::min(ctx->q, std::max(1, (nitems + ctx->sm_count - 1) / ctx->sm_count));
+  const int uwarps = q * ctx->op.wq;
+  const size_t smem = ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * ctx->gbytes +
+                      scr::ws_extra_smem(uwarps);
+  // setmaxnreg works on warp groups of 4: the update warps must be a multiple of 4 (noise warps mirror them)
+  if (uwarps % 4 != 0 || uwarps > 16 || smem > static_cast<size_t>(ctx->smem_optin) || scr::env_int("SCR_WS", 0) == 0) return SCR_OK;
+  p.q = q;
+  p.dbg = scr::env_int("SCR_WS_DEBUG", 0);
+  auto kern = ctx->w_smem ? scr::step_kernel_ws<true> : scr::step_kernel_ws<false>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int grid = std::max(1, std::min((nitems + q - 1) / q, ctx->sm_count));
+  CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  kern<<<grid, 2 * uwarps * 32, smem, ctx->stream>>>(p);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->launches++;
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_ms = ms;
+  ctx->total_step_ms += ms;
+  ctx->total_step_launches++;
+  ctx->ws_launches++;
+  *used = true;
+  return SCR_OK;
+}
+
+template <typename T>
+int launch_step_ws_if(scr_ctx*, scr::StepParams<T>&, int, bool* used) { *used = false; return SCR_OK; }
+template <>
+int launch_step_ws_if<float>(scr_ctx* ctx, scr::StepParams<float>& p, int nitems, bool* used) {
+  return launch_step_ws(ctx, p, nitems, used);
+}
+
 template <typename T>
 int launch_step(scr_ctx* ctx, scr::StepParams<T>& p, int nitems, bool probe, bool supplied) {
+  if (!probe && !supplied) {
+    bool used = false;
+    const int rc = launch_step_ws_if<T>(ctx, p, nitems, &used);
+    if (rc || used) return rc;
+  }
   if (probe) return supplied ? launch_step_t<T, true, true>(ctx, p, nitems) : launch_step_t<T, true, false>(ctx, p, nitems);
   return supplied ? launch_step_t<T, false, true>(ctx, p, nitems) : launch_step_t<T, false, false>(ctx, p, nitems);
 }
@@ -1098,6 +1145,10 @@ int scr_debug_noise(scr_ctx* ctx, int64_t global_cell, uint32_t step, double sig
 }
 
 int64_t scr_launch_count(const scr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t scr_debug_path_launches(const scr_ctx* ctx, int which) {
+  if (!ctx) return 0;
+  return which == 0 ? ctx->ws_launches : ctx->dense_launches;
+}
 double scr_last_kernel_ms(const scr_ctx* ctx) { return ctx ? ctx->last_ms : -1.0; }
 int scr_step_kernel_stats(scr_ctx* ctx, double* total_ms, int64_t* launches, int reset) {
   if (!ctx) return SCR_E_ARG;

@@ -47,14 +47,16 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the hint (ns) elapses; without
+// the hint the default limit is short and the loop below spins, stealing issue slots from other warps
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -198,6 +200,7 @@ template <typename T> struct StepParams {
   int max_iter, avg_num;
   int* iters_out;
   double* nd;                 // [k][max_iter]
+  int dbg;                    // developer timing experiments only (SCR_WS_DEBUG): 1 = skip noise generation, 2 = skip update
 };
 
 __host__ __device__ inline size_t group_smem_bytes(int n_pad, int npp, int nv_pad) {
