@@ -1,0 +1,40 @@
+"""Wall-time breakdown of one bench pass by API call (developer tool)."""
+import os, sys, time, random
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from scrutiny_b200 import engine as eng_mod
+from scrutiny_b200.network import dense_to_csr
+from scrutiny_b200.simulate import LineageSimulation
+
+cells = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+n = 3000
+gc, tf = bench.build_network(n)
+tree = bench.build_tree(n, cells, tf)
+x0 = 2.0 * np.random.rand(n) - 1.0
+gcs = gc / 0.4
+eng = eng_mod.Engine(0, "f32")
+eng.set_network(csr=dense_to_csr(gcs), n=n)
+eng.alloc_cells(cells)
+sim = LineageSimulation(eng, cells, seed=1)
+sim.prepare(tree)
+import torch
+dev = torch.empty((cells, n), dtype=torch.int32, device="cuda:0")
+acc = {}
+def wrap(obj, name):
+    f = getattr(obj, name)
+    def g(*a, **k):
+        t0 = time.perf_counter(); r = f(*a, **k); acc[name] = acc.get(name, 0.0) + time.perf_counter() - t0; return r
+    setattr(obj, name, g)
+for name in ("probe", "run_phase", "gene_sums", "counts"):
+    wrap(eng, name)
+for rep in range(3):
+    acc.clear()
+    eng.set_states_broadcast(x0)
+    eng.step_kernel_stats(reset=True)
+    t0 = time.perf_counter()
+    res = sim.run_all(tree, counts_dev_ptr=dev.data_ptr(), seed=5 + rep)
+    wall = time.perf_counter() - t0
+    kms, _ = eng.step_kernel_stats()
+    print("rep %d wall %.1f ms | stepper kernel %.1f ms | " % (rep, wall * 1e3, kms) +
+          " ".join("%s %.1f" % (k, v * 1e3) for k, v in acc.items()) + " | other host %.1f ms" % ((wall - sum(acc.values())) * 1e3))

@@ -115,18 +115,23 @@ __device__ inline int poisson_draw(double lam, UniformSource& u) {
   return static_cast<int>(lam);
 }
 
-// one CTA per cell of the chunk; threads stride over ORIGINAL genes so the output row is coalesced
+// one CTA per cell of the chunk.  Thread t handles gene `order[t]`, where `order` sorts the genes by
+// their shift (the dominant term of log lambda): the 32 lanes of a warp then see similar lambda and leave
+// the sampler's loops together instead of waiting for the largest one.  Counts are staged in shared
+// memory and written as one coalesced int32 row in the caller's gene order.
 template <typename T>
-__global__ void counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ inv, int n,
-                              int64_t cell0, const double* __restrict__ shift, double exp_scale,
-                              const double* __restrict__ sizef, uint32_t k0, uint32_t k1, int64_t cell_offset,
-                              const double* __restrict__ uniforms, int draws, int32_t* __restrict__ out,
-                              double* __restrict__ lam_out, int* err) {
+__global__ void counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ inv,
+                              const int* __restrict__ order, int n, int64_t cell0, const double* __restrict__ shift,
+                              double exp_scale, const double* __restrict__ sizef, uint32_t k0, uint32_t k1,
+                              int64_t cell_offset, const double* __restrict__ uniforms, int draws,
+                              int32_t* __restrict__ out, double* __restrict__ lam_out, int* err) {
+  extern __shared__ int32_t s_counts[];
   const int64_t c = cell0 + blockIdx.x;   // local slot
   const uint64_t gid = static_cast<uint64_t>(cell_offset + c);
   const double sf = sizef[c];
   const T* row = state + c * ld;
-  for (int o = threadIdx.x; o < n; o += blockDim.x) {
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const int o = order[t];
     const double x = static_cast<double>(row[inv[o]]);
     double lam = exp(exp_scale * (x + shift[o])) * sf;
     if (lam < 0.0) lam = 0.0;
@@ -139,10 +144,12 @@ __global__ void counts_kernel(const T* __restrict__ state, int64_t ld, const int
     u.c2 = static_cast<uint32_t>(gid);
     u.c3 = static_cast<uint32_t>(gid >> 32);
     u.k0 = k0; u.k1 = k1; u.call = 0; u.have = 0; u.err = err;
-    const int64_t oi = static_cast<int64_t>(blockIdx.x) * n + o;
-    out[oi] = poisson_draw(lam, u);
-    if (lam_out) lam_out[oi] = lam;
+    s_counts[o] = poisson_draw(lam, u);
+    if (lam_out) lam_out[static_cast<int64_t>(blockIdx.x) * n + o] = lam;
   }
+  __syncthreads();
+  int32_t* orow = out + static_cast<int64_t>(blockIdx.x) * n;
+  for (int o = threadIdx.x; o < n; o += blockDim.x) orow[o] = s_counts[o];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1045,12 +1045,19 @@ int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double
   const int n = ctx->op.n;
   const int64_t cells = ctx->cells;
   double *d_shift = nullptr, *d_size = nullptr, *d_uni = nullptr, *d_lam = nullptr;
+  int* d_order = nullptr;
   int32_t* d_buf[2] = {nullptr, nullptr};
   int rc = SCR_OK;
-  auto cleanup = [&]() { cudaFree(d_shift); cudaFree(d_size); cudaFree(d_uni); cudaFree(d_lam); cudaFree(d_buf[0]); cudaFree(d_buf[1]); };
+  auto cleanup = [&]() { cudaFree(d_shift); cudaFree(d_size); cudaFree(d_uni); cudaFree(d_lam); cudaFree(d_order); cudaFree(d_buf[0]); cudaFree(d_buf[1]); };
+  // genes sorted by shift: neighbouring lanes get similar lambda (see counts_kernel)
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return shift[a] < shift[b]; });
 #define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
   CKC(cudaMalloc(&d_shift, n * sizeof(double)));
   CKC(cudaMalloc(&d_size, cells * sizeof(double)));
+  CKC(cudaMalloc(&d_order, n * sizeof(int)));
+  CKC(cudaMemcpyAsync(d_order, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemcpyAsync(d_shift, shift, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemcpyAsync(d_size, size_factors, cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
@@ -1063,9 +1070,9 @@ int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double
   const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_COUNTS);
   auto launch = [&](int64_t c0, int64_t cnt, int32_t* out, double* lam) -> cudaError_t {
     if (ctx->prec == SCR_F64)
-      scr::counts_kernel<double><<<static_cast<unsigned>(cnt), 256, 0, ctx->stream>>>(static_cast<const double*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, n, c0, d_shift, exp_scale, d_size, k0, k1, ctx->cell_offset, d_uni, draws_per_entry, out, lam, ctx->d_err);
+      scr::counts_kernel<double><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const double*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, c0, d_shift, exp_scale, d_size, k0, k1, ctx->cell_offset, d_uni, draws_per_entry, out, lam, ctx->d_err);
     else
-      scr::counts_kernel<float><<<static_cast<unsigned>(cnt), 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, n, c0, d_shift, exp_scale, d_size, k0, k1, ctx->cell_offset, d_uni, draws_per_entry, out, lam, ctx->d_err);
+      scr::counts_kernel<float><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const float*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, c0, d_shift, exp_scale, d_size, k0, k1, ctx->cell_offset, d_uni, draws_per_entry, out, lam, ctx->d_err);
     ctx->launches++;
     return cudaGetLastError();
   };
