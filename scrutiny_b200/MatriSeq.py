@@ -297,10 +297,13 @@ ARTEFACTS = ("synthscRNAseq", "cellTypesRecord", "gc", "projMatrix", "constMatri
 
 def saveData(synthscRNAseq, cellTypesRecord, gc, projMatrix, constMatrix, cellSizeFactors, synthPseudotimes):
     """MS:1035-1065: the seven ``<name>.npy`` artefacts RegNetInference.readCellStates loads
-    (RegNetInference.py:49-66).  The R ``.gzip`` copies need rpy2 + R and are not written."""
+    (RegNetInference.py:49-66) and their R twins ``<name>.gzip`` (what ``save(..., compress=TRUE)``
+    writes through rpy2 at MS:1062-1065), produced here without R by ``rdata.write_rdata``."""
+    from .rdata import write_rdata
     for name, value in zip(ARTEFACTS, (synthscRNAseq, cellTypesRecord, gc, projMatrix, constMatrix,
                                        cellSizeFactors, synthPseudotimes)):
         np.save(os.path.join(__outputDir, name), value)
+        write_rdata(os.path.join(__outputDir, name + ".gzip"), name, np.asarray(value))
 
 
 def analyzeDataBeforeTransformation(*args, **kwargs):

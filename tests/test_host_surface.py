@@ -63,4 +63,27 @@ def test_save_data_writes_the_seven_artefacts(tmp_path):
     for name in ("synthscRNAseq", "cellTypesRecord", "gc", "projMatrix", "constMatrix", "cellSizeFactors",
                  "synthPseudotimes"):
         assert (tmp_path / "out" / (name + ".npy")).exists()
+        assert (tmp_path / "out" / (name + ".gzip")).exists()
     assert np.load(tmp_path / "out" / "synthscRNAseq.npy").shape == (n, cells)
+    from scrutiny_b200.rdata import read_rdata
+    name, back = read_rdata(str(tmp_path / "out" / "projMatrix.gzip"))
+    assert name == "projMatrix" and np.array_equal(back, np.ones((2, n)))
+    name, back = read_rdata(str(tmp_path / "out" / "cellTypesRecord.gzip"))
+    assert back.dtype == np.int64 and back.shape == (cells,)
+
+
+def test_r_workspace_writer_reproduces_files_written_by_r():
+    """tests/golden/r_*.gzip were written by R itself (shipped by the reference under R_files/):
+    reading them and re-serialising must give the same bytes."""
+    import gzip
+    import os
+    from scrutiny_b200 import rdata
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name, shape, dtype in (("cellTypesRecord", (100,), np.int64), ("cellSizeFactors", (100,), np.float64),
+                               ("projMatrix", (3, 500), np.float64)):
+        path = os.path.join(here, "r_%s.gzip" % name)
+        got_name, value = rdata.read_rdata(path)
+        assert got_name == name and value.shape == shape and value.dtype == dtype
+        assert rdata.serialize(name, value) == gzip.open(path).read()
+    _, proj = rdata.read_rdata(os.path.join(here, "r_projMatrix.gzip"))
+    assert set(np.unique(proj)) <= {0.0, 1.0} and (proj == 0).sum(axis=1).tolist() == sorted((proj == 0).sum(axis=1).tolist())
