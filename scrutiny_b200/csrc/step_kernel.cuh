@@ -143,6 +143,49 @@ __device__ __forceinline__ double tanh_acc(double z) { return tanh(z); }
 __device__ __forceinline__ float add_noise(float drive, float r, float u) { return fmaf(r, u, drive); }
 __device__ __forceinline__ double add_noise(double drive, float r, float u) { return drive + static_cast<double>(r * u); }
 
+
+// ------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2): one issue slot, two IEEE fp32 results,
+// bit-identical to the scalar instructions.  Pairs are (cell c, cell c+1) of one gene row, which sit
+// in adjacent registers after the LDS.128 of the state row.
+// ------------------------------------------------------------------------------------------
+#ifndef SCR_PACKED_F32X2
+#define SCR_PACKED_F32X2 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// Box-Muller for the same word pair of two cells at once: radius pair and (cos, sin) pairs
+__device__ __forceinline__ void box_muller_polar2(uint32_t wa0, uint32_t wb0, uint32_t wa1, uint32_t wb1, f32x2 rscale2,
+                                                  f32x2& r, f32x2& c, f32x2& sn) {
+  const f32x2 f1 = pk2(__uint_as_float(0x3f800000u | (wa0 >> 9)), __uint_as_float(0x3f800000u | (wa1 >> 9)));
+  const f32x2 f2 = pk2(__uint_as_float(0x3f800000u | (wb0 >> 9)), __uint_as_float(0x3f800000u | (wb1 >> 9)));
+  float u0, u1;
+  upk2(fma2(f1, pk2(-1.0f, -1.0f), pk2(2.0f, 2.0f)), u0, u1);                       // 2 - f1 in (0, 1]
+  float t0, t1;
+  upk2(mul2(pk2(ptx_lg2(u0), ptx_lg2(u1)), rscale2), t0, t1);
+  r = pk2(ptx_sqrt(fabsf(t0)), ptx_sqrt(fabsf(t1)));
+  float h0, h1;
+  upk2(fma2(f2, pk2(6.28318530717958647692f, 6.28318530717958647692f), pk2(-9.42477796076937971538f, -9.42477796076937971538f)), h0, h1);
+  c = pk2(ptx_cos(h0), ptx_cos(h1));
+  sn = pk2(ptx_sin(h0), ptx_sin(h1));
+}
+// tanh of a pair (same formula as tanh_acc(float))
+__device__ __forceinline__ f32x2 tanh_acc2(f32x2 z) {
+  float m0, m1, z0, z1;
+  upk2(mul2(z, pk2(2.88539008177792681472f, 2.88539008177792681472f)), m0, m1);
+  upk2(z, z0, z1);
+  float s0, s1;
+  upk2(add2(pk2(ptx_ex2(fabsf(m0)), ptx_ex2(fabsf(m1))), pk2(1.0f, 1.0f)), s0, s1);
+  float t0, t1;
+  upk2(fma2(pk2(ptx_rcp(s0), ptx_rcp(s1)), pk2(-2.0f, -2.0f), pk2(1.0f, 1.0f)), t0, t1);
+  return pk2(copysignf(t0, z0), copysignf(t1, z1));
+}
+
 // ------------------------------------------------------------------------------------------
 // types
 // ------------------------------------------------------------------------------------------
@@ -202,6 +245,37 @@ template <typename T> struct StepParams {
   double* nd;                 // [k][max_iter]
   int dbg;                    // developer timing experiments only (SCR_WS_DEBUG): 1 = skip noise generation, 2 = skip update
 };
+
+
+// element-wise update of one 128-gene block for a fully active group of 4 float cells, packed fp32x2
+__device__ __forceinline__ void fast_update_f32x2(const uint32_t (&w)[4][4], float rscale, float dt, const float (&acc)[4][4],
+                                                  Row<float> (&xo)[4], const float2 (&pcv)[4]) {
+  const f32x2 rscale2 = pk2(rscale, rscale), dt2 = pk2(dt, dt), neg1 = pk2(-1.0f, -1.0f);
+#pragma unroll
+  for (int pr = 0; pr < 2; ++pr) {          // cell pairs (0,1) and (2,3)
+    const int c0 = 2 * pr, c1 = 2 * pr + 1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {           // word pairs -> genes (2h, 2h+1)
+      f32x2 r, cs, sn;
+      box_muller_polar2(w[c0][2 * h], w[c0][2 * h + 1], w[c1][2 * h], w[c1][2 * h + 1], rscale2, r, cs, sn);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 2 * h + e;
+        const f32x2 z = fma2(r, e == 0 ? cs : sn, pk2(acc[j][c0], acc[j][c1]));
+        const f32x2 t = tanh_acc2(z);
+        const f32x2 x = pk2(xo[j].v[c0], xo[j].v[c1]);
+        const f32x2 x1 = fma2(dt2, fma2(x, neg1, t), x);                       // x + dt (t - x)
+        float a, b;
+        upk2(fma2(pk2(pcv[j].x, pcv[j].x), x1, pk2(pcv[j].y, pcv[j].y)), a, b);
+        xo[j].v[c0] = a;
+        xo[j].v[c1] = b;
+      }
+    }
+  }
+}
+// (double contexts never take this path; the overload only keeps the template well-formed)
+__device__ __forceinline__ void fast_update_f32x2(const uint32_t (&)[2][4], float, double, const double (&)[4][2],
+                                                  Row<double> (&)[4], const double2 (&)[4]) {}
 
 __host__ __device__ inline size_t group_smem_bytes(int n_pad, int npp, int nv_pad) {
   return static_cast<size_t>(n_pad + npp + nv_pad) * 16 + 8 * 16 + 64;
@@ -399,7 +473,13 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           pcv[j] = pcs[g];
         }
         const uint32_t ctr0 = static_cast<uint32_t>(b * 32 + lane);
-        if (all_active && !SUPPLIED) {
+        if (all_active && !SUPPLIED && !PROBE && SCR_PACKED_F32X2 && sizeof(T) == 4) {
+          uint32_t w[CPG][4];
+#pragma unroll
+          for (int c = 0; c < CPG; ++c)
+            philox4x32_10_rk(ctr0, it.base[c] + static_cast<uint32_t>(s), gid_lo[c], gid_hi[c], p.rk, w[c]);
+          fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
+        } else if (all_active && !SUPPLIED) {
           uint32_t w[CPG][4];
 #pragma unroll
           for (int c = 0; c < CPG; ++c)
