@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscrutiny_b200.so")
+# SCRUTINY_B200_LIB: developer override used by A/B kernel experiments (scripts/ab_build.sh)
+LIB_PATH = os.environ.get("SCRUTINY_B200_LIB") or os.path.join(_HERE, "libscrutiny_b200.so")
 
 c_ctx = C.c_void_p
 _i32p = C.POINTER(C.c_int32)

@@ -188,7 +188,10 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
   op.wblk_ptr.assign(wq + 1, 0);
   op.wblk.clear();
   for (int w = 0; w < wq; ++w) {
-    std::sort(lists[w].begin(), lists[w].end());
+    // order the stepper's split barriers rely on: regulator blocks without long rows, blocks with long
+    // rows (their chunk partials arrive late), then blocks nobody reads (step_kernel.cuh)
+    auto kls = [&](int b) { return b < op.nlong_blocks ? 1 : (b < op.npp_blocks ? 0 : 2); };
+    std::sort(lists[w].begin(), lists[w].end(), [&](int a, int b) { return kls(a) != kls(b) ? kls(a) < kls(b) : a < b; });
     for (int b : lists[w]) op.wblk.push_back(b);
     op.wblk_ptr[w + 1] = static_cast<int>(op.wblk.size());
   }

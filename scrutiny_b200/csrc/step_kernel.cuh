@@ -49,14 +49,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 // try_wait suspends the thread in hardware until the phase completes or the hint (ns) elapses; without
 // the hint the default limit is short and the loop below spins, stealing issue slots from other warps
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+// one arrival (release at CTA scope); the waiters' try_wait is the matching acquire
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -151,6 +157,15 @@ __device__ __forceinline__ double add_noise(double drive, float r, float u) { re
 // ------------------------------------------------------------------------------------------
 #ifndef SCR_PACKED_F32X2
 #define SCR_PACKED_F32X2 1
+#endif
+#ifndef SCR_SPLIT_BARRIER
+#define SCR_SPLIT_BARRIER 1
+#endif
+#ifndef SCR_PACKED_GATHER
+#define SCR_PACKED_GATHER 0
+#endif
+#ifndef SCR_PIPE_PHILOX
+#define SCR_PIPE_PHILOX 0
 #endif
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
@@ -305,10 +320,15 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   const int qthreads = p.wq * 32, qtid = wq * 32 + lane, bar_id = 1 + grp;
 
   // ---- stage operator tables and the node's proj/const with the bulk-copy engine ----
-  if (threadIdx.x == 0) {
-    mbar_init(s_mbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (threadIdx.x == 0) mbar_init(s_mbar, 1);
+  if (SCR_SPLIT_BARRIER && !PROBE && qtid == 0) {
+    unsigned char* g0 = s_groups + static_cast<size_t>(grp) * gbytes;
+    uint64_t* b0 = reinterpret_cast<uint64_t*>(g0 + static_cast<size_t>(p.n_pad + p.npp + p.nv_pad + 8) * 16 + 16);
+    mbar_init(b0, p.wq);
+    mbar_init(b0 + 1, p.wq);
+    mbar_init(b0 + 2, p.wq);
   }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t pc_bytes = static_cast<uint32_t>(p.n_pad * sizeof(PC));
@@ -333,8 +353,23 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   RowT* ovf = reinterpret_cast<RowT*>(bufB + static_cast<size_t>(p.npp) * 16);
   RowT* red = ovf + p.nv_pad;
   volatile int* ctrl = reinterpret_cast<volatile int*>(red + 8);
+  // split step barriers (non-probe runs): three mbarriers per group, one arrival per warp
+  //   bar_w: this step's new regulator values are all written     (waited at the start of the next step)
+  //   bar_r: every read of this step's `cur` buffer has finished   (waited before the next step's first regulator store)
+  //   bar_a: the long-row chunk partials of this step are in place (waited by the owners of long rows)
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(const_cast<int*>(ctrl) + 4);
+  uint64_t* bar_r = bar_w + 1;
+  uint64_t* bar_a = bar_w + 2;
 
   const int my_b0 = wblk_ptr[wq], my_b1 = wblk_ptr[wq + 1];
+  const int first_blk = (my_b0 < my_b1) ? wblk[my_b0] : 0;
+  // the warp's list is ordered [regulator blocks without long rows | blocks with long rows | the rest]
+  // (operator_pack.h); reg_end = end of the ping-ponged (regulator) part
+  constexpr bool kSplit = SCR_SPLIT_BARRIER && !PROBE;
+  int reg_end = my_b0;
+  while (reg_end < my_b1 && wblk[reg_end] < p.npp_blocks) ++reg_end;
+  uint32_t tg = 0;            // steps this group has completed so far (mbarrier phase counter)
+  const bool flip = (wq >> 2) & 1;
   const bool has_bias = p.bias != nullptr;
 
   for (;;) {
@@ -390,7 +425,21 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
     }
     const T wscale = PROBE ? static_cast<T>(it.scale) : T(1);
 
+    // software pipeline of the noise generator (float32 free-running runs): the Philox words of the NEXT
+    // block are produced while the current block sits in its MUFU-bound Box-Muller / tanh section, so
+    // the integer pipe and the MUFU pipe of a warp overlap instead of alternating
+    constexpr bool kPacked = !PROBE && !SUPPLIED && SCR_PACKED_F32X2 && sizeof(T) == 4;
+    constexpr bool kPipe = kPacked && SCR_PIPE_PHILOX;
+    uint32_t wn[CPG][4];
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) { wn[c][0] = wn[c][1] = wn[c][2] = wn[c][3] = 0u; }
+    if (kPipe && smin > 0 && my_b0 < my_b1) {
+      const uint32_t c0n = static_cast<uint32_t>(first_blk * 32 + lane);
+#pragma unroll
+      for (int c = 0; c < CPG; ++c) philox4x32_10_rk(c0n, it.base[c], gid_lo[c], gid_hi[c], p.rk, wn[c]);
+    }
     for (int s = 0; s < smax; ++s) {
+      if (kSplit && s > 0) mbar_wait(bar_w, (tg - 1u) & 1u);   // all of cur is in place
       // -------- phase A: chunks of rows longer than the cap --------
       if (p.nv > 0) {
         for (int v = qtid; v < p.nv_pad; v += qthreads) {
@@ -408,7 +457,16 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           for (int c = 0; c < CPG; ++c) o.v[c] = acc[c];
           ovf[v] = o;
         }
-        named_bar_sync(bar_id, qthreads);
+        if (kSplit) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_a);
+        } else {
+          named_bar_sync(bar_id, qthreads);
+        }
+      }
+      if (kSplit && reg_end == my_b0) {   // a warp without regulator blocks has nothing to publish
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_w);
       }
 
       T dsum[CPG];
@@ -430,7 +488,30 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
 #pragma unroll
           for (int c = 0; c < CPG; ++c) acc[j][c] = T(0);
         }
-        {
+        if constexpr (kPacked && SCR_PACKED_GATHER) {
+          // packed accumulation (FFMA2 with the W value broadcast): two issue slots per entry instead of four
+          f32x2 a2[4][2];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { a2[j][0] = 0ull; a2[j][1] = 0ull; }
+          const int o1 = blk_off[b + 1];
+          for (int o = blk_off[b] + lane; o < o1; o += 128) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const WEnt e = wtile[o + j * 32];
+              const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(cur + e.off);
+              const f32x2 ev = pk2(e.v, e.v);
+              a2[j][0] = fma2(ev, xv.x, a2[j][0]);
+              a2[j][1] = fma2(ev, xv.y, a2[j][1]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float t0, t1, t2, t3;
+            upk2(a2[j][0], t0, t1);
+            upk2(a2[j][1], t2, t3);
+            acc[j][0] = t0; acc[j][1] = t1; acc[j][CPG - 2] = t2; acc[j][CPG - 1] = t3;
+          }
+        } else {
           const int o1 = blk_off[b + 1];
           for (int o = blk_off[b] + lane; o < o1; o += 128) {
 #pragma unroll
@@ -451,6 +532,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           }
         }
         if (b < p.nlong_blocks) {
+          if (kSplit) mbar_wait(bar_a, tg & 1u);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int2 oi = ovfidx[gbase + j * 32];
@@ -473,12 +555,44 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           pcv[j] = pcs[g];
         }
         const uint32_t ctr0 = static_cast<uint32_t>(b * 32 + lane);
-        if (all_active && !SUPPLIED && !PROBE && SCR_PACKED_F32X2 && sizeof(T) == 4) {
+        if (kPacked && all_active) {
           uint32_t w[CPG][4];
+          if (kPipe) {
 #pragma unroll
-          for (int c = 0; c < CPG; ++c)
-            philox4x32_10_rk(ctr0, it.base[c] + static_cast<uint32_t>(s), gid_lo[c], gid_hi[c], p.rk, w[c]);
-          fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
+            for (int c = 0; c < CPG; ++c) { w[c][0] = wn[c][0]; w[c][1] = wn[c][1]; w[c][2] = wn[c][2]; w[c][3] = wn[c][3]; }
+            // coordinates of the block this warp handles next: the following block of this step, or its
+            // first block of the next step (one wasted batch at the very end of the group's run)
+            const bool last = bi + 1 >= my_b1;
+            const uint32_t sn = static_cast<uint32_t>(last ? s + 1 : s);
+            const uint32_t c0n = static_cast<uint32_t>((last ? first_blk : bnext) * 32 + lane);
+            if (SCR_PIPE_PHILOX == 2) {
+              // staggered: the two warps of a group that share a scheduler (wq, wq + 4) run the integer
+              // generator and the MUFU-bound update in opposite order, so one feeds the issue slots the
+              // other leaves idle while it waits on the MUFU pipe
+              if (flip) {
+#pragma unroll
+                for (int c = 0; c < CPG; ++c)
+                  philox4x32_10_rk(c0n, it.base[c] + sn, gid_lo[c], gid_hi[c], p.rk, wn[c]);
+              }
+              fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
+              if (!flip) {
+#pragma unroll
+                for (int c = 0; c < CPG; ++c)
+                  philox4x32_10_rk(c0n, it.base[c] + sn, gid_lo[c], gid_hi[c], p.rk, wn[c]);
+              }
+            } else {
+              // same basic block as the update: ptxas interleaves IMAD with MUFU
+#pragma unroll
+              for (int c = 0; c < CPG; ++c)
+                philox4x32_10_rk(c0n, it.base[c] + sn, gid_lo[c], gid_hi[c], p.rk, wn[c]);
+              fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CPG; ++c)
+              philox4x32_10_rk(ctr0, it.base[c] + static_cast<uint32_t>(s), gid_lo[c], gid_hi[c], p.rk, w[c]);
+            fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
+          }
         } else if (all_active && !SUPPLIED) {
           uint32_t w[CPG][4];
 #pragma unroll
@@ -542,9 +656,15 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
             }
           }
         }
+        // the first regulator store of a step overwrites the buffer the previous step read from
+        if (kSplit && s > 0 && bi == my_b0 && pp) mbar_wait(bar_r, (tg - 1u) & 1u);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<RowT*>(dst + static_cast<size_t>(gbase + j * 32) * 16) = xo[j];
+        if (kSplit && bi == reg_end - 1) {   // this warp's share of the next step's inputs is published
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_w);
+        }
       }
 
       if (PROBE) {
@@ -560,7 +680,13 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           red[wq] = o;
         }
       }
-      named_bar_sync(bar_id, qthreads);   // end of step: every new value is in place
+      if (kSplit) {   // this warp no longer reads cur
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_r);
+        ++tg;
+      } else {
+        named_bar_sync(bar_id, qthreads);   // end of step: every new value is in place
+      }
       { unsigned char* t = cur; cur = oth; oth = t; }
 
       if (PROBE) {
@@ -588,6 +714,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       }
     }
 
+    if (kSplit && smax > 0) {   // both complete = full barrier: every value of the last step is visible
+      mbar_wait(bar_w, (tg - 1u) & 1u);
+      mbar_wait(bar_r, (tg - 1u) & 1u);
+    }
     if (PROBE) {
       if (qtid == 0) {
 #pragma unroll
