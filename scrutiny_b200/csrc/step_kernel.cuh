@@ -161,12 +161,6 @@ __device__ __forceinline__ double add_noise(double drive, float r, float u) { re
 #ifndef SCR_SPLIT_BARRIER
 #define SCR_SPLIT_BARRIER 1
 #endif
-#ifndef SCR_PACKED_GATHER
-#define SCR_PACKED_GATHER 0
-#endif
-#ifndef SCR_PIPE_PHILOX
-#define SCR_PIPE_PHILOX 0
-#endif
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
@@ -362,14 +356,12 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   uint64_t* bar_a = bar_w + 2;
 
   const int my_b0 = wblk_ptr[wq], my_b1 = wblk_ptr[wq + 1];
-  const int first_blk = (my_b0 < my_b1) ? wblk[my_b0] : 0;
   // the warp's list is ordered [regulator blocks without long rows | blocks with long rows | the rest]
   // (operator_pack.h); reg_end = end of the ping-ponged (regulator) part
   constexpr bool kSplit = SCR_SPLIT_BARRIER && !PROBE;
   int reg_end = my_b0;
   while (reg_end < my_b1 && wblk[reg_end] < p.npp_blocks) ++reg_end;
   uint32_t tg = 0;            // steps this group has completed so far (mbarrier phase counter)
-  const bool flip = (wq >> 2) & 1;
   const bool has_bias = p.bias != nullptr;
 
   for (;;) {
@@ -425,19 +417,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
     }
     const T wscale = PROBE ? static_cast<T>(it.scale) : T(1);
 
-    // software pipeline of the noise generator (float32 free-running runs): the Philox words of the NEXT
-    // block are produced while the current block sits in its MUFU-bound Box-Muller / tanh section, so
-    // the integer pipe and the MUFU pipe of a warp overlap instead of alternating
     constexpr bool kPacked = !PROBE && !SUPPLIED && SCR_PACKED_F32X2 && sizeof(T) == 4;
-    constexpr bool kPipe = kPacked && SCR_PIPE_PHILOX;
-    uint32_t wn[CPG][4];
-#pragma unroll
-    for (int c = 0; c < CPG; ++c) { wn[c][0] = wn[c][1] = wn[c][2] = wn[c][3] = 0u; }
-    if (kPipe && smin > 0 && my_b0 < my_b1) {
-      const uint32_t c0n = static_cast<uint32_t>(first_blk * 32 + lane);
-#pragma unroll
-      for (int c = 0; c < CPG; ++c) philox4x32_10_rk(c0n, it.base[c], gid_lo[c], gid_hi[c], p.rk, wn[c]);
-    }
     for (int s = 0; s < smax; ++s) {
       if (kSplit && s > 0) mbar_wait(bar_w, (tg - 1u) & 1u);   // all of cur is in place
       // -------- phase A: chunks of rows longer than the cap --------
@@ -488,30 +468,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
 #pragma unroll
           for (int c = 0; c < CPG; ++c) acc[j][c] = T(0);
         }
-        if constexpr (kPacked && SCR_PACKED_GATHER) {
-          // packed accumulation (FFMA2 with the W value broadcast): two issue slots per entry instead of four
-          f32x2 a2[4][2];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { a2[j][0] = 0ull; a2[j][1] = 0ull; }
-          const int o1 = blk_off[b + 1];
-          for (int o = blk_off[b] + lane; o < o1; o += 128) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const WEnt e = wtile[o + j * 32];
-              const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(cur + e.off);
-              const f32x2 ev = pk2(e.v, e.v);
-              a2[j][0] = fma2(ev, xv.x, a2[j][0]);
-              a2[j][1] = fma2(ev, xv.y, a2[j][1]);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float t0, t1, t2, t3;
-            upk2(a2[j][0], t0, t1);
-            upk2(a2[j][1], t2, t3);
-            acc[j][0] = t0; acc[j][1] = t1; acc[j][CPG - 2] = t2; acc[j][CPG - 1] = t3;
-          }
-        } else {
+        {
           const int o1 = blk_off[b + 1];
           for (int o = blk_off[b] + lane; o < o1; o += 128) {
 #pragma unroll
@@ -557,42 +514,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         const uint32_t ctr0 = static_cast<uint32_t>(b * 32 + lane);
         if (kPacked && all_active) {
           uint32_t w[CPG][4];
-          if (kPipe) {
 #pragma unroll
-            for (int c = 0; c < CPG; ++c) { w[c][0] = wn[c][0]; w[c][1] = wn[c][1]; w[c][2] = wn[c][2]; w[c][3] = wn[c][3]; }
-            // coordinates of the block this warp handles next: the following block of this step, or its
-            // first block of the next step (one wasted batch at the very end of the group's run)
-            const bool last = bi + 1 >= my_b1;
-            const uint32_t sn = static_cast<uint32_t>(last ? s + 1 : s);
-            const uint32_t c0n = static_cast<uint32_t>((last ? first_blk : bnext) * 32 + lane);
-            if (SCR_PIPE_PHILOX == 2) {
-              // staggered: the two warps of a group that share a scheduler (wq, wq + 4) run the integer
-              // generator and the MUFU-bound update in opposite order, so one feeds the issue slots the
-              // other leaves idle while it waits on the MUFU pipe
-              if (flip) {
-#pragma unroll
-                for (int c = 0; c < CPG; ++c)
-                  philox4x32_10_rk(c0n, it.base[c] + sn, gid_lo[c], gid_hi[c], p.rk, wn[c]);
-              }
-              fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
-              if (!flip) {
-#pragma unroll
-                for (int c = 0; c < CPG; ++c)
-                  philox4x32_10_rk(c0n, it.base[c] + sn, gid_lo[c], gid_hi[c], p.rk, wn[c]);
-              }
-            } else {
-              // same basic block as the update: ptxas interleaves IMAD with MUFU
-#pragma unroll
-              for (int c = 0; c < CPG; ++c)
-                philox4x32_10_rk(c0n, it.base[c] + sn, gid_lo[c], gid_hi[c], p.rk, wn[c]);
-              fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < CPG; ++c)
-              philox4x32_10_rk(ctr0, it.base[c] + static_cast<uint32_t>(s), gid_lo[c], gid_hi[c], p.rk, w[c]);
-            fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
-          }
+          for (int c = 0; c < CPG; ++c)
+            philox4x32_10_rk(ctr0, it.base[c] + static_cast<uint32_t>(s), gid_lo[c], gid_hi[c], p.rk, w[c]);
+          fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
         } else if (all_active && !SUPPLIED) {
           uint32_t w[CPG][4];
 #pragma unroll
