@@ -134,6 +134,29 @@ double scr_last_kernel_ms(const scr_ctx* ctx);
  * last reset; bench.py derives roofline.achieved from these */
 int scr_step_kernel_stats(scr_ctx* ctx, double* total_ms, int64_t* launches, int reset);
 
+
+/* ---- RegNetInference front end ("RNI" = RNAscrutiny/RNAscrutiny/RegNetInference.py).
+ * These two calls need only a context (no network / cells): they work on the matrices the caller passes. */
+
+/* RNI:69-78 convertToS(n, cells, cellStates): in place.  Every cell's genes are replaced by
+ * 2*((r+1)/n)-1 with r = scipy.stats.rankdata 'average' ranks, then every gene's cells likewise with `cells`.
+ * S is (n, cells) float64, row stride ld.  Results are bit-identical to the reference (integer rank work;
+ * the final float64 expression is evaluated in the reference's operation order).  n <= 8192; finite inputs. */
+int scr_rank_transform(scr_ctx* ctx, int64_t n, int64_t cells, double* S_genes_by_cells, int64_t ld);
+
+/* RNI:397-416 (and RNI:764-777 inside getCVCost): all [cell1, cell2] of the same type with
+ * 0 < pt[cell1] - pt[cell2] <= thresh whose state columns differ, ordered by type, cell1, cell2 ascending.
+ * count_out receives the number of pairs; rows are written to pairs_out (int64 [count][2]) only when
+ * pairs_out != NULL and capacity >= count (call once with NULL to size the buffer).  Negative types match
+ * nothing, like the reference's range(max(types)+1) loop. */
+int scr_cell_pairs(scr_ctx* ctx, int64_t n, int64_t cells, const double* S_genes_by_cells, int64_t ld,
+                   const double* pseudotimes /* cells */, const int64_t* cell_types /* cells */, double thresh,
+                   int64_t* pairs_out, int64_t capacity, int64_t* count_out);
+
+/* kernels of the last scr_rank_transform: device milliseconds (CUDA events, both passes), cells ranked by the
+ * counting path and by the sorting path */
+int scr_rank_transform_stats(const scr_ctx* ctx, double* kernel_ms, int64_t* counting_cells, int64_t* sorted_cells);
+
 #ifdef __cplusplus
 }
 #endif

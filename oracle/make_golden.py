@@ -153,6 +153,35 @@ def case_poisson_mode(ms):
                         types=types, iters=iters)
 
 
+def case_regnet():
+    """RegNetInference.convertToS (RNI:69-78) on count-like, continuous and heavily tied matrices, and
+    getCVCost (RNI:755-797) -- its value pins the pair set of RNI:764-777 -- from the unmodified reference."""
+    rni = rh.load_reference_rni()
+    out = {}
+    rs = np.random.RandomState(71)
+    a = rs.poisson(1.5, size=(37, 53)).astype(np.float64)           # counts: many ties
+    b = rs.standard_normal(size=(20, 31))                           # continuous: no ties
+    c = rs.randint(0, 3, size=(16, 64)).astype(np.float64)          # three distinct values
+    c[:, 5] = c[:, 9]                                               # two identical cells
+    d = np.exp(rs.normal(2.0, 2.5, size=(45, 12))).round()         # large integer counts
+    for name, m in (("a", a), ("b", b), ("c", c), ("d", d)):
+        out["in_" + name] = m
+        out["s_" + name] = rni.convertToS(m.shape[0], m.shape[1], m.copy())
+    # pair search through getCVCost on the transformed matrix `c` (identical cells 5 and 9 present)
+    S = out["s_c"]
+    n, cells = S.shape
+    pt = np.round(rs.rand(cells), 2)                                # rounded: equal pseudotimes occur
+    pt[9] = pt[5] + 0.01
+    types = rs.randint(0, 3, size=cells).astype(np.int64)
+    types[9] = types[5]
+    W = 0.3 * rs.standard_normal(size=(n, n))
+    out["pt"], out["types"], out["W"] = pt, types, W
+    th = np.array([0.05, 0.2, 0.61])
+    out["thresh"] = th
+    out["cv_cost"] = np.array([rni.getCVCost(t, W, S, pt, types) for t in th])
+    np.savez_compressed(os.path.join(OUT, "regnet.npz"), **out)
+
+
 def main():
     if not rh.available():
         sys.exit("reference not available; fixtures can only be regenerated in the build container")
@@ -162,6 +191,8 @@ def main():
                case_transform_alt, case_poisson_mode):
         fn(ms)
         print("wrote", fn.__name__)
+    case_regnet()
+    print("wrote case_regnet")
 
 
 if __name__ == "__main__":

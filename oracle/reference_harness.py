@@ -78,3 +78,25 @@ def load_reference():
     ms.np.load = patched_load  # ms.np is numpy itself: patch is global but harmless
     _cached = ms
     return ms
+
+
+_cached_rni = None
+
+
+def load_reference_rni():
+    """Return the reference ``RegNetInference`` module (stub plotting modules; scipy / sklearn / networkx are
+    present in the build container)."""
+    global _cached_rni
+    if _cached_rni is not None:
+        return _cached_rni
+    if not available():
+        raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "seaborn"):
+        if name not in sys.modules:
+            _stub(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].patches = sys.modules["matplotlib.patches"]
+    if _PKG_DIR not in sys.path:
+        sys.path.insert(0, _PKG_DIR)
+    _cached_rni = importlib.import_module("RegNetInference")
+    return _cached_rni

@@ -13,6 +13,7 @@
 #include "aux_kernels.cuh"
 #include "dense_kernel.cuh"
 #include "operator_pack.h"
+#include "regnet_kernels.cuh"
 #include "step_kernel.cuh"
 #include "step_kernel_ws.cuh"
 
@@ -66,6 +67,16 @@ struct scr_ctx {
   int* d_err = nullptr;
   double* d_stage = nullptr;
   size_t stage_elems = 0;
+  // read-out scratch, kept between scr_counts calls (cudaMalloc / cudaFree of the 256 MB staging buffers
+  // synchronise the device and cost more than the kernel itself)
+  double *d_cshift = nullptr, *d_csize = nullptr;
+  int* d_corder = nullptr;
+  int32_t* d_cbuf[2] = {nullptr, nullptr};
+  size_t cshift_cap = 0, csize_cap = 0, corder_cap = 0, cbuf_cap[2] = {0, 0};
+
+  // RegNetInference front end
+  double rank_kernel_ms = 0.0;
+  int64_t rank_counting = 0, rank_sorted = 0;
 
   // stats
   int64_t launches = 0;
@@ -720,6 +731,22 @@ int probe_t(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_
   return rc;
 }
 
+template <typename P>
+int ensure_buf(scr_ctx* ctx, P*& ptr, size_t& cap, size_t elems) {
+  if (elems <= cap) return SCR_OK;
+  cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+  CK(cudaMalloc(&ptr, elems * sizeof(P)));
+  cap = elems;
+  return SCR_OK;
+}
+void free_counts_scratch(scr_ctx* ctx) {
+  cudaFree(ctx->d_cshift); cudaFree(ctx->d_csize); cudaFree(ctx->d_corder); cudaFree(ctx->d_cbuf[0]); cudaFree(ctx->d_cbuf[1]);
+  ctx->d_cshift = ctx->d_csize = nullptr; ctx->d_corder = nullptr; ctx->d_cbuf[0] = ctx->d_cbuf[1] = nullptr;
+  ctx->cshift_cap = ctx->csize_cap = ctx->corder_cap = ctx->cbuf_cap[0] = ctx->cbuf_cap[1] = 0;
+}
+
 int ensure_stage(scr_ctx* ctx, size_t elems) {
   if (elems <= ctx->stage_elems) return SCR_OK;
   cudaFree(ctx->d_stage);
@@ -788,6 +815,7 @@ void scr_destroy(scr_ctx* ctx) {
     free_network(ctx);
     free_dense_work(ctx);
     cudaFree(ctx->d_state); cudaFree(ctx->d_items); cudaFree(ctx->d_counter); cudaFree(ctx->d_err); cudaFree(ctx->d_stage);
+    free_counts_scratch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]); if (ctx->ev_c[i]) cudaEventDestroy(ctx->ev_c[i]); }
@@ -1044,19 +1072,20 @@ int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double
   if (!shift || !size_factors || !counts_out) return fail(ctx, SCR_E_ARG, "bad arguments");
   const int n = ctx->op.n;
   const int64_t cells = ctx->cells;
-  double *d_shift = nullptr, *d_size = nullptr, *d_uni = nullptr, *d_lam = nullptr;
-  int* d_order = nullptr;
-  int32_t* d_buf[2] = {nullptr, nullptr};
+  double *d_uni = nullptr, *d_lam = nullptr;   // parity / debug inputs only: allocated per call
   int rc = SCR_OK;
-  auto cleanup = [&]() { cudaFree(d_shift); cudaFree(d_size); cudaFree(d_uni); cudaFree(d_lam); cudaFree(d_order); cudaFree(d_buf[0]); cudaFree(d_buf[1]); };
+  auto cleanup = [&]() { cudaFree(d_uni); cudaFree(d_lam); };
   // genes sorted by shift: neighbouring lanes get similar lambda (see counts_kernel)
   std::vector<int> order(n);
   for (int i = 0; i < n; ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return shift[a] < shift[b]; });
+  if ((rc = ensure_buf(ctx, ctx->d_corder, ctx->corder_cap, static_cast<size_t>(n)))) return rc;
+  if ((rc = ensure_buf(ctx, ctx->d_cshift, ctx->cshift_cap, static_cast<size_t>(n)))) return rc;
+  if ((rc = ensure_buf(ctx, ctx->d_csize, ctx->csize_cap, static_cast<size_t>(cells)))) return rc;
+  double *d_shift = ctx->d_cshift, *d_size = ctx->d_csize;
+  int* d_order = ctx->d_corder;
+  int32_t** d_buf = ctx->d_cbuf;
 #define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
-  CKC(cudaMalloc(&d_shift, n * sizeof(double)));
-  CKC(cudaMalloc(&d_size, cells * sizeof(double)));
-  CKC(cudaMalloc(&d_order, n * sizeof(int)));
   CKC(cudaMemcpyAsync(d_order, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemcpyAsync(d_shift, shift, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemcpyAsync(d_size, size_factors, cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -1081,8 +1110,8 @@ int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double
   } else {
     // double-buffered: the Poisson kernel of chunk i+1 overlaps the D2H copy of chunk i
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(cells, (256LL << 20) / (static_cast<int64_t>(n) * 4)));
-    CKC(cudaMalloc(&d_buf[0], static_cast<size_t>(chunk) * n * 4));
-    if (cells > chunk) CKC(cudaMalloc(&d_buf[1], static_cast<size_t>(chunk) * n * 4));
+    if ((rc = ensure_buf(ctx, ctx->d_cbuf[0], ctx->cbuf_cap[0], static_cast<size_t>(chunk) * n))) { cleanup(); return rc; }
+    if (cells > chunk && (rc = ensure_buf(ctx, ctx->d_cbuf[1], ctx->cbuf_cap[1], static_cast<size_t>(chunk) * n))) { cleanup(); return rc; }
     int used[2] = {0, 0};
     int64_t ci = 0;
     for (int64_t c0 = 0; c0 < cells; c0 += chunk, ++ci) {
@@ -1162,6 +1191,172 @@ int scr_step_kernel_stats(scr_ctx* ctx, double* total_ms, int64_t* launches, int
   if (total_ms) *total_ms = ctx->total_step_ms;
   if (launches) *launches = ctx->total_step_launches;
   if (reset) { ctx->total_step_ms = 0.0; ctx->total_step_launches = 0; }
+  return SCR_OK;
+}
+
+// ---- RegNetInference front end -------------------------------------------------------------------------
+
+int scr_rank_transform(scr_ctx* ctx, int64_t n, int64_t cells, double* S, int64_t ld) {
+  NEED_GPU();
+  if (n <= 0 || cells <= 0 || !S || ld < cells) return fail(ctx, SCR_E_ARG, "bad arguments");
+  if (n > 8192) return fail(ctx, SCR_E_RESOURCE, "rank transform: n > 8192 does not fit the per-cell shared-memory sort");
+  if (cells > (1LL << 31) - 2) return fail(ctx, SCR_E_RESOURCE, "rank transform: too many cells");
+  int n_pad = 2;
+  while (n_pad < n) n_pad <<= 1;
+  const int nbins = static_cast<int>(2 * n + 2);
+  const size_t smem1 = static_cast<size_t>(n_pad) * 10 + (scr::regnet::kHistBins + 1 + 32) * 4;
+  const size_t smem2 = static_cast<size_t>(nbins + 1 + 32) * 4;
+  CK(cudaFuncSetAttribute(scr::regnet::rank_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
+  CK(cudaFuncSetAttribute(scr::regnet::rank_genes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+
+  // slabs of ~256 MB (two: the copy of one overlaps the kernel of the other); a slab holds whole columns in
+  // pass 1 (n x cw) and whole rows in pass 2 (gw x cells)
+  const int64_t slab_elems = std::max<int64_t>({(256LL << 20) / 8, n, cells});
+  const int64_t cw = std::max<int64_t>(1, std::min<int64_t>(cells, slab_elems / n));
+  const int64_t gw = std::max<int64_t>(1, std::min<int64_t>(n, slab_elems / cells));
+  uint16_t* d_keys = nullptr;
+  double* d_slab[2] = {nullptr, nullptr};
+  int* d_paths = nullptr;
+  auto cleanup = [&]() { cudaFree(d_keys); cudaFree(d_slab[0]); cudaFree(d_slab[1]); cudaFree(d_paths); };
+#define CKR(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
+  CKR(cudaMalloc(&d_keys, static_cast<size_t>(n) * cells * sizeof(uint16_t)));
+  CKR(cudaMalloc(&d_slab[0], static_cast<size_t>(slab_elems) * 8));
+  CKR(cudaMalloc(&d_slab[1], static_cast<size_t>(slab_elems) * 8));
+  CKR(cudaMalloc(&d_paths, 2 * sizeof(int)));
+  CKR(cudaMemsetAsync(d_paths, 0, 2 * sizeof(int), ctx->stream));
+  CKR(cudaStreamSynchronize(ctx->stream));
+  cudaEvent_t k0[2], k1[2];
+  for (int b = 0; b < 2; ++b) { CKR(cudaEventCreate(&k0[b])); CKR(cudaEventCreate(&k1[b])); }
+  double kernel_ms = 0.0;
+  auto reap = [&](int b) {   // the kernel that last used slab b has been waited for: add its time
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, k0[b], k1[b]) == cudaSuccess) kernel_ms += ms;
+  };
+
+  // pass 1: H2D column slab on the copy stream -> per-cell ranks on the compute stream
+  int used[2] = {0, 0};
+  int64_t ci = 0;
+  for (int64_t c0 = 0; c0 < cells; c0 += cw, ++ci) {
+    const int b = static_cast<int>(ci & 1);
+    const int64_t cnt = std::min(cw, cells - c0);
+    if (used[b]) { CKR(cudaEventSynchronize(k1[b])); reap(b); }
+    CKR(cudaMemcpy2DAsync(d_slab[b], cnt * 8, S + c0, ld * 8, cnt * 8, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CKR(cudaEventRecord(ctx->ev_c[b], ctx->copy_stream));
+    CKR(cudaStreamWaitEvent(ctx->stream, ctx->ev_c[b], 0));
+    CKR(cudaEventRecord(k0[b], ctx->stream));
+    scr::regnet::rank_cells_kernel<<<static_cast<unsigned>(cnt), 256, smem1, ctx->stream>>>(
+        d_slab[b], cnt, static_cast<int>(n), n_pad, d_keys, cells, c0, d_paths);
+    CKR(cudaGetLastError());
+    CKR(cudaEventRecord(k1[b], ctx->stream));
+    ctx->launches++;
+    used[b] = 1;
+  }
+  CKR(cudaStreamSynchronize(ctx->stream));
+  for (int b = 0; b < 2; ++b) if (used[b]) reap(b);
+
+  // pass 2: per-gene ranks into a row slab -> D2H on the copy stream
+  used[0] = used[1] = 0;
+  ci = 0;
+  for (int64_t g0 = 0; g0 < n; g0 += gw, ++ci) {
+    const int b = static_cast<int>(ci & 1);
+    const int64_t cnt = std::min(gw, n - g0);
+    if (used[b]) { CKR(cudaStreamWaitEvent(ctx->stream, ctx->ev_c[b], 0)); CKR(cudaEventSynchronize(k1[b])); reap(b); }
+    CKR(cudaEventRecord(k0[b], ctx->stream));
+    scr::regnet::rank_genes_kernel<<<static_cast<unsigned>(cnt), 512, smem2, ctx->stream>>>(d_keys, cells, nbins, g0, d_slab[b]);
+    CKR(cudaGetLastError());
+    CKR(cudaEventRecord(k1[b], ctx->stream));
+    ctx->launches++;
+    CKR(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+    CKR(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[b], 0));
+    CKR(cudaMemcpy2DAsync(S + g0 * ld, ld * 8, d_slab[b], cells * 8, cells * 8, cnt, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CKR(cudaEventRecord(ctx->ev_c[b], ctx->copy_stream));
+    used[b] = 1;
+  }
+  CKR(cudaStreamSynchronize(ctx->stream));
+  CKR(cudaStreamSynchronize(ctx->copy_stream));
+  for (int b = 0; b < 2; ++b) if (used[b]) reap(b);
+  int paths[2] = {0, 0};
+  CKR(cudaMemcpy(paths, d_paths, sizeof(paths), cudaMemcpyDeviceToHost));
+#undef CKR
+  for (int b = 0; b < 2; ++b) { cudaEventDestroy(k0[b]); cudaEventDestroy(k1[b]); }
+  cleanup();
+  ctx->rank_kernel_ms = kernel_ms;
+  ctx->rank_counting = paths[0];
+  ctx->rank_sorted = paths[1];
+  return SCR_OK;
+}
+
+int scr_rank_transform_stats(const scr_ctx* ctx, double* kernel_ms, int64_t* counting_cells, int64_t* sorted_cells) {
+  if (!ctx) return SCR_E_ARG;
+  if (kernel_ms) *kernel_ms = ctx->rank_kernel_ms;
+  if (counting_cells) *counting_cells = ctx->rank_counting;
+  if (sorted_cells) *sorted_cells = ctx->rank_sorted;
+  return SCR_OK;
+}
+
+int scr_cell_pairs(scr_ctx* ctx, int64_t n, int64_t cells, const double* S, int64_t ld, const double* pseudotimes,
+                   const int64_t* cell_types, double thresh, int64_t* pairs_out, int64_t capacity, int64_t* count_out) {
+  NEED_GPU();
+  if (n <= 0 || cells <= 0 || !S || ld < cells || !pseudotimes || !cell_types || !count_out)
+    return fail(ctx, SCR_E_ARG, "bad arguments");
+  // positions grouped by type (ascending), cells ascending inside a type: the reference's loop order
+  int64_t tmax = -1;
+  for (int64_t c = 0; c < cells; ++c) tmax = std::max(tmax, cell_types[c]);
+  *count_out = 0;
+  if (tmax < 0) return SCR_OK;
+  std::vector<int64_t> start(static_cast<size_t>(tmax) + 2, 0);
+  for (int64_t c = 0; c < cells; ++c)
+    if (cell_types[c] >= 0) start[cell_types[c] + 1]++;
+  for (int64_t t = 0; t <= tmax; ++t) start[t + 1] += start[t];
+  const int64_t m = start[tmax + 1];
+  std::vector<int64_t> order(m), seg_b(m), seg_e(m), fillp(start.begin(), start.end() - 1);
+  std::vector<double> pt(m);
+  for (int64_t c = 0; c < cells; ++c) {
+    const int64_t t = cell_types[c];
+    if (t < 0) continue;
+    const int64_t pos = fillp[t]++;
+    order[pos] = c;
+    pt[pos] = pseudotimes[c];
+    seg_b[pos] = start[t];
+    seg_e[pos] = start[t + 1];
+  }
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t need = static_cast<size_t>(n) * cells * 8 + static_cast<size_t>(m) * 48;
+  if (need + (1ULL << 30) > free_b) return fail(ctx, SCR_E_RESOURCE, "cell pairs: state matrix does not fit in device memory");
+  double *d_S = nullptr, *d_pt = nullptr;
+  int64_t *d_order = nullptr, *d_sb = nullptr, *d_se = nullptr, *d_cnt = nullptr, *d_off = nullptr, *d_pairs = nullptr;
+  auto cleanup = [&]() { cudaFree(d_S); cudaFree(d_pt); cudaFree(d_order); cudaFree(d_sb); cudaFree(d_se); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_pairs); };
+#define CKP(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
+  CKP(cudaMalloc(&d_S, static_cast<size_t>(n) * cells * 8));
+  CKP(cudaMalloc(&d_pt, m * 8)); CKP(cudaMalloc(&d_order, m * 8)); CKP(cudaMalloc(&d_sb, m * 8));
+  CKP(cudaMalloc(&d_se, m * 8)); CKP(cudaMalloc(&d_cnt, m * 8)); CKP(cudaMalloc(&d_off, m * 8));
+  CKP(cudaMemcpy2DAsync(d_S, cells * 8, S, ld * 8, cells * 8, n, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_pt, pt.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_order, order.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_sb, seg_b.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_se, seg_e.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned grid = static_cast<unsigned>((m + 255) / 256);
+  scr::regnet::pairs_kernel<false><<<grid, 256, 0, ctx->stream>>>(m, d_pt, d_order, d_sb, d_se, thresh, d_S, cells, static_cast<int>(n), d_cnt, nullptr, nullptr);
+  CKP(cudaGetLastError());
+  ctx->launches++;
+  std::vector<int64_t> cnt(m), off(m);
+  CKP(cudaMemcpyAsync(cnt.data(), d_cnt, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CKP(cudaStreamSynchronize(ctx->stream));
+  int64_t total = 0;
+  for (int64_t i = 0; i < m; ++i) { off[i] = total; total += cnt[i]; }
+  *count_out = total;
+  if (pairs_out && capacity >= total && total > 0) {
+    CKP(cudaMalloc(&d_pairs, static_cast<size_t>(total) * 16));
+    CKP(cudaMemcpyAsync(d_off, off.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    scr::regnet::pairs_kernel<true><<<grid, 256, 0, ctx->stream>>>(m, d_pt, d_order, d_sb, d_se, thresh, d_S, cells, static_cast<int>(n), nullptr, d_off, d_pairs);
+    CKP(cudaGetLastError());
+    ctx->launches++;
+    CKP(cudaMemcpyAsync(pairs_out, d_pairs, static_cast<size_t>(total) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CKP(cudaStreamSynchronize(ctx->stream));
+  }
+#undef CKP
+  cleanup();
   return SCR_OK;
 }
 

@@ -178,6 +178,37 @@ class Engine:
                                          _ptr(uni, C.c_double), int(draws), ptr, on_dev, _ptr(lam, C.c_double)))
         return (out, lam) if want_lambda else out
 
+    # -- RegNetInference front end ------------------------------------------------------------
+    def rank_transform(self, S):
+        """In-place convertToS (RegNetInference.py:69-78) of a (genes, cells) float64 array whose rows may be
+        strided (ld = row stride)."""
+        assert S.dtype == np.float64 and S.ndim == 2 and S.strides[1] == 8 and S.strides[0] % 8 == 0
+        n, cells = S.shape
+        self._check(self._lib.scr_rank_transform(self._ctx, n, cells, _ptr(S, C.c_double), S.strides[0] // 8))
+        return S
+
+    def rank_transform_stats(self):
+        ms, a, b = C.c_double(0.0), C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.scr_rank_transform_stats(self._ctx, C.byref(ms), C.byref(a), C.byref(b)))
+        return {"kernel_ms": ms.value, "counting_cells": a.value, "sorted_cells": b.value}
+
+    def cell_pairs(self, S, pseudotimes, cell_types, thresh):
+        """(pairs, 2) int64 array in the reference's order (RegNetInference.py:397-416)."""
+        assert S.dtype == np.float64 and S.ndim == 2 and S.strides[1] == 8 and S.strides[0] % 8 == 0
+        n, cells = S.shape
+        pt = _f64(pseudotimes)
+        ty = np.ascontiguousarray(cell_types, dtype=np.int64)
+        assert pt.shape == (cells,) and ty.shape == (cells,)
+        count = C.c_int64(0)
+        args = (self._ctx, n, cells, _ptr(S, C.c_double), S.strides[0] // 8, _ptr(pt, C.c_double),
+                _ptr(ty, C.c_int64), float(thresh))
+        self._check(self._lib.scr_cell_pairs(*args, None, 0, C.byref(count)))
+        pairs = np.empty((count.value, 2), dtype=np.int64)
+        if count.value:
+            self._check(self._lib.scr_cell_pairs(*args, _ptr(pairs, C.c_int64), count.value, C.byref(count)))
+            assert count.value == len(pairs)
+        return pairs
+
     # -- debug ------------------------------------------------------------------------------
     def debug_philox(self, ctr4, k0, k1):
         ctr = np.ascontiguousarray(ctr4, dtype=np.uint32).reshape(-1, 4)
