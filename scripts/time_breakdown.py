@@ -8,6 +8,7 @@ from scrutiny_b200.network import dense_to_csr
 from scrutiny_b200.simulate import LineageSimulation
 
 cells = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+host = len(sys.argv) > 2 and sys.argv[2] == "host"      # e2e variant: counts to a pinned host matrix
 n = 3000
 gc, tf = bench.build_network(n)
 tree = bench.build_tree(n, cells, tf)
@@ -19,7 +20,8 @@ eng.alloc_cells(cells)
 sim = LineageSimulation(eng, cells, seed=1)
 sim.prepare(tree)
 import torch
-dev = torch.empty((cells, n), dtype=torch.int32, device="cuda:0")
+dev = torch.empty((cells, n), dtype=torch.int32, device="cuda:0") if not host else None
+hostbuf = torch.empty((cells, n), dtype=torch.int32, pin_memory=True).numpy() if host else None
 acc = {}
 def wrap(obj, name):
     f = getattr(obj, name)
@@ -33,7 +35,11 @@ for rep in range(3):
     eng.set_states_broadcast(x0)
     eng.step_kernel_stats(reset=True)
     t0 = time.perf_counter()
-    res = sim.run_all(tree, counts_dev_ptr=dev.data_ptr(), seed=5 + rep)
+    if host:
+        t1 = time.perf_counter(); eng.set_network(csr=dense_to_csr(gcs), n=n); acc["set_network"] = time.perf_counter() - t1
+        res = sim.run_all(tree, counts_out=hostbuf, seed=5 + rep)
+    else:
+        res = sim.run_all(tree, counts_dev_ptr=dev.data_ptr(), seed=5 + rep)
     wall = time.perf_counter() - t0
     kms, _ = eng.step_kernel_stats()
     print("rep %d wall %.1f ms | stepper kernel %.1f ms | " % (rep, wall * 1e3, kms) +

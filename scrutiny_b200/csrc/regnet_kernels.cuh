@@ -56,11 +56,83 @@ __device__ inline void block_exclusive_scan(int* a, int len, int* tmp) {
   __syncthreads();
 }
 
+constexpr int kTileCells = 16;    // cells per CTA of the tiled counting kernel: 128-byte reads, 32-byte key writes
+constexpr int kTileBins = 1024;   // its histogram range per cell
+
+// Counting path for count matrices, coalesced: one CTA per tile of kTileCells adjacent cells.  A warp touches two
+// gene rows x 16 cells per access (two full 128-byte lines in, two full 32-byte sectors out).  Pass A builds one
+// shared-memory histogram per cell, a warp per cell turns it into prefix sums, pass B re-reads the tile (L2-resident:
+// 16 x n x 8 bytes per CTA) and writes the keys.  A cell holding a non-integer, a negative or a value >= kTileBins is
+// only flagged in `fallback` and left to rank_cells_kernel.
+// Shared memory: int hist[kTileCells][kTileBins + 1] | int bad[kTileCells]
+__global__ void __launch_bounds__(512) rank_cells_tile_kernel(const double* __restrict__ slab, int64_t cw, int n,
+                                                              uint16_t* __restrict__ keys, int64_t cells, int64_t c0,
+                                                              int* __restrict__ fallback, int* __restrict__ path_counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* hist = reinterpret_cast<int*>(smem_raw);
+  int* bad = hist + kTileCells * (kTileBins + 1);
+  const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * kTileCells;          // first cell of the tile (slab-local)
+  const int cl = tid & (kTileCells - 1);                                      // my cell of the tile
+  const int r0 = tid / kTileCells, rstep = nthreads / kTileCells;
+  const bool live = t0 + cl < cw;
+  for (int i = tid; i < kTileCells * (kTileBins + 1); i += nthreads) hist[i] = 0;
+  if (tid < kTileCells) bad[tid] = 0;
+  __syncthreads();
+  int* myh = hist + cl * (kTileBins + 1);
+  const double* col = slab + t0 + cl;
+  int mybad = 0;
+  if (live) {
+    for (int g = r0; g < n; g += rstep) {
+      const double x = col[static_cast<int64_t>(g) * cw];
+      if (x >= 0.0 && x < static_cast<double>(kTileBins) && x == floor(x)) atomicAdd(&myh[static_cast<int>(x)], 1);
+      else mybad = 1;
+    }
+  }
+  if (mybad) bad[cl] = 1;
+  __syncthreads();
+  // warp w: exclusive prefix sums of cell w's histogram (kTileBins / 32 consecutive bins per lane)
+  for (int c = warp; c < kTileCells; c += nthreads >> 5) {
+    int* h = hist + c * (kTileBins + 1);
+    constexpr int PER = kTileBins / 32;
+    int sum = 0;
+    for (int i = 0; i < PER; ++i) sum += h[lane * PER + i];
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    int run = incl - sum;
+    for (int i = 0; i < PER; ++i) {
+      const int v = h[lane * PER + i];
+      h[lane * PER + i] = run;
+      run += v;
+    }
+    if (lane == 31) h[kTileBins] = run;
+  }
+  __syncthreads();
+  if (live) {
+    if (bad[cl]) {
+      if (r0 == 0) fallback[t0 + cl] = 1;
+    } else {
+      uint16_t* out = keys + c0 + t0 + cl;
+      for (int g = r0; g < n; g += rstep) {
+        const int v = static_cast<int>(col[static_cast<int64_t>(g) * cw]);
+        out[static_cast<int64_t>(g) * cells] = static_cast<uint16_t>(myh[v] + myh[v + 1] + 1);
+      }
+      if (r0 == 0) { fallback[t0 + cl] = 0; if (path_counts) atomicAdd(&path_counts[0], 1); }
+    }
+  }
+}
+
 // One CTA per cell of the slab (n x cw float64, row-major: column c is the cell).  Writes keys[g * cells + c0 + c].
+// With `fallback` != nullptr only the cells flagged by rank_cells_tile_kernel are processed.
 // Shared memory: double key[n_pad] | int hist[kHistBins + 1] | int tmp[32] | uint16 idx[n_pad]
 __global__ void __launch_bounds__(256) rank_cells_kernel(const double* __restrict__ slab, int64_t cw, int n, int n_pad,
                                                          uint16_t* __restrict__ keys, int64_t cells, int64_t c0,
-                                                         int* __restrict__ path_counts) {
+                                                         int* __restrict__ path_counts, const int* __restrict__ fallback) {
+  if (fallback && !fallback[blockIdx.x]) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* key = reinterpret_cast<double*>(smem_raw);
   int* hist = reinterpret_cast<int*>(key + n_pad);

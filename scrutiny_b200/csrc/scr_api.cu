@@ -1206,6 +1206,8 @@ int scr_rank_transform(scr_ctx* ctx, int64_t n, int64_t cells, double* S, int64_
   const int nbins = static_cast<int>(2 * n + 2);
   const size_t smem1 = static_cast<size_t>(n_pad) * 10 + (scr::regnet::kHistBins + 1 + 32) * 4;
   const size_t smem2 = static_cast<size_t>(nbins + 1 + 32) * 4;
+  const size_t smem_t = static_cast<size_t>(scr::regnet::kTileCells) * (scr::regnet::kTileBins + 2) * 4;
+  CK(cudaFuncSetAttribute(scr::regnet::rank_cells_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t)));
   CK(cudaFuncSetAttribute(scr::regnet::rank_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
   CK(cudaFuncSetAttribute(scr::regnet::rank_genes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
 
@@ -1217,12 +1219,15 @@ int scr_rank_transform(scr_ctx* ctx, int64_t n, int64_t cells, double* S, int64_
   uint16_t* d_keys = nullptr;
   double* d_slab[2] = {nullptr, nullptr};
   int* d_paths = nullptr;
-  auto cleanup = [&]() { cudaFree(d_keys); cudaFree(d_slab[0]); cudaFree(d_slab[1]); cudaFree(d_paths); };
+  int* d_fb[2] = {nullptr, nullptr};
+  auto cleanup = [&]() { cudaFree(d_keys); cudaFree(d_slab[0]); cudaFree(d_slab[1]); cudaFree(d_paths); cudaFree(d_fb[0]); cudaFree(d_fb[1]); };
 #define CKR(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
   CKR(cudaMalloc(&d_keys, static_cast<size_t>(n) * cells * sizeof(uint16_t)));
   CKR(cudaMalloc(&d_slab[0], static_cast<size_t>(slab_elems) * 8));
   CKR(cudaMalloc(&d_slab[1], static_cast<size_t>(slab_elems) * 8));
   CKR(cudaMalloc(&d_paths, 2 * sizeof(int)));
+  CKR(cudaMalloc(&d_fb[0], static_cast<size_t>(cw) * sizeof(int)));
+  CKR(cudaMalloc(&d_fb[1], static_cast<size_t>(cw) * sizeof(int)));
   CKR(cudaMemsetAsync(d_paths, 0, 2 * sizeof(int), ctx->stream));
   CKR(cudaStreamSynchronize(ctx->stream));
   cudaEvent_t k0[2], k1[2];
@@ -1244,9 +1249,15 @@ int scr_rank_transform(scr_ctx* ctx, int64_t n, int64_t cells, double* S, int64_
     CKR(cudaEventRecord(ctx->ev_c[b], ctx->copy_stream));
     CKR(cudaStreamWaitEvent(ctx->stream, ctx->ev_c[b], 0));
     CKR(cudaEventRecord(k0[b], ctx->stream));
-    scr::regnet::rank_cells_kernel<<<static_cast<unsigned>(cnt), 256, smem1, ctx->stream>>>(
-        d_slab[b], cnt, static_cast<int>(n), n_pad, d_keys, cells, c0, d_paths);
+    // counting path, tiled and coalesced; the cells it cannot take (non-integers, values >= 1024) are flagged
+    // and ranked one CTA per cell by the general kernel
+    scr::regnet::rank_cells_tile_kernel<<<static_cast<unsigned>((cnt + scr::regnet::kTileCells - 1) / scr::regnet::kTileCells), 512, smem_t, ctx->stream>>>(
+        d_slab[b], cnt, static_cast<int>(n), d_keys, cells, c0, d_fb[b], d_paths);
     CKR(cudaGetLastError());
+    scr::regnet::rank_cells_kernel<<<static_cast<unsigned>(cnt), 256, smem1, ctx->stream>>>(
+        d_slab[b], cnt, static_cast<int>(n), n_pad, d_keys, cells, c0, d_paths, d_fb[b]);
+    CKR(cudaGetLastError());
+    ctx->launches++;
     CKR(cudaEventRecord(k1[b], ctx->stream));
     ctx->launches++;
     used[b] = 1;
