@@ -177,6 +177,12 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
   std::iota(by_cost.begin(), by_cost.end(), 0);
   std::stable_sort(by_cost.begin(), by_cost.end(), [&](int a, int b) { return cost[a] > cost[b]; });
   std::vector<double> load(wq, 0.0);
+  // warps 0 .. nv_pad/32-1 evaluate the long-row chunks at the start of every step (step_kernel.cuh phase A):
+  // charge them for it so that LPT hands them lighter blocks
+  {
+    const double chunk_cost = env_int("SCR_CHUNK_COST", 60);
+    for (int v0 = 0; v0 < op.nv_pad; v0 += 32) load[(v0 / 32) % wq] += chunk_cost;
+  }
   std::vector<std::vector<int>> lists(wq);
   for (int b : by_cost) {
     int w = 0;

@@ -161,6 +161,12 @@ __device__ __forceinline__ double add_noise(double drive, float r, float u) { re
 #ifndef SCR_SPLIT_BARRIER
 #define SCR_SPLIT_BARRIER 1
 #endif
+#ifndef SCR_CHUNK_UNROLL
+#define SCR_CHUNK_UNROLL 1    // long-row chunks of the default length (8) are evaluated with all loads in flight
+#endif
+#ifndef SCR_CHUNK_SPREAD
+#define SCR_CHUNK_SPREAD 0    // experiment: chunk v evaluated by lane v / wq of warp v % wq (measured slower)
+#endif
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
@@ -422,15 +428,33 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       if (kSplit && s > 0) mbar_wait(bar_w, (tg - 1u) & 1u);   // all of cur is in place
       // -------- phase A: chunks of rows longer than the cap --------
       if (p.nv > 0) {
-        for (int v = qtid; v < p.nv_pad; v += qthreads) {
+        // the first nv_pad / 32 warps of the group evaluate the chunks (operator_pack.h charges them for it when it
+        // assigns blocks); chunks of the default length run with all their loads in flight
+        for (int v0 = 0; v0 < p.nv_pad; v0 += qthreads) {
+          const int v = SCR_CHUNK_SPREAD ? v0 + lane * p.wq + wq : v0 + qtid;
+          if (v >= p.nv_pad) continue;
           T acc[CPG];
 #pragma unroll
           for (int c = 0; c < CPG; ++c) acc[c] = T(0);
-          for (int k = 0; k < p.lv; ++k) {
-            const WEnt e = wchunk[k * p.nv_pad + v];
-            const RowT xv = *reinterpret_cast<const RowT*>(cur + e.off);
+          if (SCR_CHUNK_UNROLL && p.lv == 8) {
+            WEnt e[8];
+            RowT xv[8];
 #pragma unroll
-            for (int c = 0; c < CPG; ++c) acc[c] = fma(e.v, xv.v[c], acc[c]);
+            for (int k = 0; k < 8; ++k) e[k] = wchunk[k * p.nv_pad + v];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xv[k] = *reinterpret_cast<const RowT*>(cur + e[k].off);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+#pragma unroll
+              for (int c = 0; c < CPG; ++c) acc[c] = fma(e[k].v, xv[k].v[c], acc[c]);
+            }
+          } else {
+            for (int k = 0; k < p.lv; ++k) {
+              const WEnt e = wchunk[k * p.nv_pad + v];
+              const RowT xv = *reinterpret_cast<const RowT*>(cur + e.off);
+#pragma unroll
+              for (int c = 0; c < CPG; ++c) acc[c] = fma(e.v, xv.v[c], acc[c]);
+            }
           }
           RowT o;
 #pragma unroll
