@@ -217,12 +217,25 @@ int choose_config(scr_ctx* ctx) {
   return SCR_OK;
 }
 
+// When the operator does not fit in shared memory next to q cell groups, the leading part of it that the rest of the
+// SM's shared memory holds is staged there and the remainder is served by L1 (step_kernel.cuh "partial residency").
+// SCR_W_PREFIX_KB caps the staged part (0 disables it).
+int w_prefix_bytes(const scr_ctx* ctx, int q) {
+  if (ctx->w_smem) return 0;
+  long room = static_cast<long>(ctx->smem_optin) - static_cast<long>(ctx->fixed_bytes) - static_cast<long>(q) * static_cast<long>(ctx->gbytes);
+  const int cap_kb = scr::env_int("SCR_W_PREFIX_KB", -1);
+  if (cap_kb >= 0) room = std::min<long>(room, static_cast<long>(cap_kb) * 1024);
+  room = std::min<long>(room, ctx->w_bytes);
+  return room >= 128 ? static_cast<int>(room / 128 * 128) : 0;
+}
+
 template <typename T, bool PROBE, bool SUPPLIED>
 int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
   // few groups: spread them over SMs instead of stacking them in one CTA
   int q = std::min(ctx->q, std::max(1, (nitems + ctx->sm_count - 1) / ctx->sm_count));
   p.q = q;
-  const size_t smem = ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * ctx->gbytes;
+  p.w_prefix = w_prefix_bytes(ctx, q);
+  const size_t smem = ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * ctx->gbytes + p.w_prefix;
   const int threads = q * ctx->op.wq * 32;
   auto kern = ctx->w_smem ? scr::step_kernel<T, true, PROBE, SUPPLIED> : scr::step_kernel<T, false, PROBE, SUPPLIED>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -925,10 +938,11 @@ int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count) {
   if (!ctx || !out) return SCR_E_ARG;
   if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
   const PackedOperator& o = ctx->op;
-  const int64_t v[12] = {o.n_pad, o.npp, static_cast<int64_t>(o.tile_val.size()), o.nv, o.lv, o.cap, o.wq, ctx->q,
-                         static_cast<int64_t>(ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + ctx->q * ctx->gbytes),
-                         ctx->w_smem ? 1 : 0, ctx->cpg(), ctx->dense_mode ? 1 : 0};
-  for (int i = 0; i < count && i < 12; ++i) out[i] = v[i];
+  const int64_t v[14] = {o.n_pad, o.npp, static_cast<int64_t>(o.tile_val.size()), o.nv, o.lv, o.cap, o.wq, ctx->q,
+                         static_cast<int64_t>(ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + ctx->q * ctx->gbytes +
+                                              w_prefix_bytes(ctx, ctx->q)),
+                         ctx->w_smem ? 1 : 0, ctx->cpg(), ctx->dense_mode ? 1 : 0, w_prefix_bytes(ctx, ctx->q), ctx->w_bytes};
+  for (int i = 0; i < count && i < 14; ++i) out[i] = v[i];
   return SCR_OK;
 }
 

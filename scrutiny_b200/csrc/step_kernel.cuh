@@ -233,6 +233,7 @@ template <typename T> struct StepParams {
   const unsigned char* tab;   // small tables blob
   const unsigned char* wblob; // tile entries, then long-row chunk entries
   int tab_bytes, w_bytes;     // multiples of 16
+  int w_prefix;               // leading bytes of wblob staged in shared memory when the whole blob does not fit (multiple of 128)
   int off_slice, off_ovfidx, off_wblk_ptr, off_wblk;  // byte offsets inside tab
   int off_vrow;               // byte offset of chunk entries inside wblob
   int n, n_pad, npp, nb, npp_blocks, nlong_blocks, nv, nv_pad, lv;
@@ -311,7 +312,8 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   unsigned char* s_tab = smem;
   unsigned char* s_pc = s_tab + p.tab_bytes;
   unsigned char* s_w = s_pc + static_cast<size_t>(p.n_pad) * sizeof(PC);
-  unsigned char* s_groups = s_w + (W_SMEM ? p.w_bytes : 0);
+  const int wpre = W_SMEM ? p.w_bytes : p.w_prefix;   // bytes of the operator held in shared memory
+  unsigned char* s_groups = s_w + wpre;
   const size_t gbytes = group_smem_bytes(p.n_pad, p.npp, p.nv_pad);
   uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_groups + static_cast<size_t>(p.q) * gbytes);
 
@@ -332,10 +334,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t pc_bytes = static_cast<uint32_t>(p.n_pad * sizeof(PC));
-    mbar_expect_tx(s_mbar, p.tab_bytes + pc_bytes + (W_SMEM ? p.w_bytes : 0));
+    mbar_expect_tx(s_mbar, p.tab_bytes + pc_bytes + wpre);
     bulk_g2s(s_tab, p.tab, p.tab_bytes, s_mbar);
     bulk_g2s(s_pc, p.pc, pc_bytes, s_mbar);
-    if (W_SMEM) bulk_g2s(s_w, p.wblob, p.w_bytes, s_mbar);
+    if (wpre > 0) bulk_g2s(s_w, p.wblob, wpre, s_mbar);
   }
   mbar_wait(s_mbar, 0);
 
@@ -345,7 +347,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   const int* wblk = reinterpret_cast<const int*>(s_tab + p.off_wblk);
   const unsigned char* wbase = W_SMEM ? s_w : p.wblob;
   const WEnt* wtile = reinterpret_cast<const WEnt*>(wbase);
-  const WEnt* wchunk = reinterpret_cast<const WEnt*>(wbase + p.off_vrow);
+  // partial residency: blocks (and the chunk table) whose entries lie inside the staged prefix are read from shared
+  // memory, the others from global memory through L1 (generic loads serve both)
+  const bool chunks_in_smem = W_SMEM || p.off_vrow + static_cast<int>(sizeof(WEnt)) * p.lv * p.nv_pad <= wpre;
+  const WEnt* wchunk = reinterpret_cast<const WEnt*>((chunks_in_smem ? s_w : p.wblob) + p.off_vrow);
   const PC* pcs = reinterpret_cast<const PC*>(s_pc);
 
   unsigned char* bufA = s_groups + static_cast<size_t>(grp) * gbytes;
@@ -494,10 +499,12 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         }
         {
           const int o1 = blk_off[b + 1];
+          const WEnt* wt = wtile;
+          if (!W_SMEM && o1 * static_cast<int>(sizeof(WEnt)) <= wpre) wt = reinterpret_cast<const WEnt*>(s_w);
           for (int o = blk_off[b] + lane; o < o1; o += 128) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const WEnt e = wtile[o + j * 32];
+              const WEnt e = wt[o + j * 32];
               const RowT xv = *reinterpret_cast<const RowT*>(cur + e.off);
 #pragma unroll
               for (int c = 0; c < CPG; ++c) acc[j][c] = fma(e.v, xv.v[c], acc[j][c]);
