@@ -102,10 +102,13 @@ inline void make_round_keys(uint32_t k0, uint32_t k1, RoundKeys& rk) {
     k1 += 0xBB67AE85u;
   }
 }
+#ifndef SCR_PHILOX_ROUNDS
+#define SCR_PHILOX_ROUNDS 10   // measurement builds only (profiles/r1_stepper_experiments.txt); every test assumes 10
+#endif
 __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                  const RoundKeys& rk, uint32_t (&out)[4]) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < SCR_PHILOX_ROUNDS; ++r) {
     const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
     const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
     const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ rk.k[2 * r];
