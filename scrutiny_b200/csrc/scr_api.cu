@@ -62,6 +62,7 @@ struct scr_ctx {
 
   // scratch
   Item* d_items = nullptr;
+  Item* h_items = nullptr;       // pinned staging of the same capacity: run_phase builds the groups in place
   size_t items_cap = 0;
   int* d_counter = nullptr;
   int* d_err = nullptr;
@@ -351,10 +352,13 @@ int upload_node(scr_ctx* ctx, const double* proj, const double* cnst, double mu,
 int ensure_items(scr_ctx* ctx, size_t count) {
   if (count <= ctx->items_cap) return SCR_OK;
   cudaFree(ctx->d_items);
+  cudaFreeHost(ctx->h_items);
   ctx->d_items = nullptr;
+  ctx->h_items = nullptr;
   ctx->items_cap = 0;
-  const size_t cap = std::max<size_t>(count, 1024);
+  const size_t cap = std::max<size_t>(count + count / 8, 1024);
   CK(cudaMalloc(&ctx->d_items, cap * sizeof(Item)));
+  CK(cudaHostAlloc(&ctx->h_items, cap * sizeof(Item), cudaHostAllocDefault));
   ctx->items_cap = cap;
   return SCR_OK;
 }
@@ -382,38 +386,37 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
   }
   if (noise && smax > noise_steps) return fail(ctx, SCR_E_ARG, "supplied noise shorter than the longest cell");
   if (smax == 0) return SCR_OK;
-  std::vector<int64_t> bucket(static_cast<size_t>(smax) + 2, 0);
-  for (int64_t i = 0; i < m; ++i) if (steps[i] > 0) bucket[smax - steps[i] + 1]++;
-  for (int s = 0; s <= smax; ++s) bucket[s + 1] += bucket[s];
-  const int64_t live = bucket[smax];
-  std::vector<int64_t> order(live);
-  {
-    std::vector<int64_t> pos(bucket.begin(), bucket.end() - 1);
-    for (int64_t i = 0; i < m; ++i) if (steps[i] > 0) order[pos[smax - steps[i]]++] = i;
-  }
+  // one scatter pass straight into the pinned staging buffer: cell i goes to position pos[bucket]++ of the sorted order,
+  // i.e. slot (position % CPG) of group (position / CPG); each bucket writes sequentially, so this is a 500-way streaming
+  // scatter (a vector of Items + pageable copy cost 4x as much at 10^6 cells: 4 % of the bench step)
+  std::vector<int64_t> pos(static_cast<size_t>(smax) + 2, 0);
+  for (int64_t i = 0; i < m; ++i) if (steps[i] > 0) pos[smax - steps[i] + 1]++;
+  for (int s = 0; s <= smax; ++s) pos[s + 1] += pos[s];
+  const int64_t live = pos[smax];
   const int64_t nitems = (live + CPG - 1) / CPG;
   if (nitems > 0x7fffffff) return fail(ctx, SCR_E_ARG, "too many cell groups");
-  std::vector<Item> items(nitems);
-  for (int64_t g = 0; g < nitems; ++g) {
-    Item& it = items[g];
-    std::memset(&it, 0, sizeof(it));
-    it.scale = 1.0;
-    for (int c = 0; c < 4; ++c) {
-      const int64_t k = g * CPG + c;
-      if (c < CPG && k < live) {
-        const int64_t i = order[k];
-        it.cell[c] = static_cast<int>(cell_ids[i]);
-        it.steps[c] = steps[i];
-        it.base[c] = static_cast<uint32_t>(step_base ? step_base[i] : 0);
-        it.row[c] = static_cast<int>(i);
-      } else {
-        it.cell[c] = -1;
-      }
-    }
-  }
-  int rc = ensure_items(ctx, items.size());
+  int rc = ensure_items(ctx, static_cast<size_t>(nitems));
   if (rc) return rc;
-  CK(cudaMemcpyAsync(ctx->d_items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, ctx->stream));
+  Item* items = ctx->h_items;
+  for (int64_t i = 0; i < m; ++i) {
+    if (steps[i] <= 0) continue;
+    const int64_t k = pos[smax - steps[i]]++;
+    Item& it = items[k / CPG];
+    const int c = static_cast<int>(k % CPG);
+    it.cell[c] = static_cast<int>(cell_ids[i]);
+    it.steps[c] = steps[i];
+    it.base[c] = static_cast<uint32_t>(step_base ? step_base[i] : 0);
+    it.row[c] = static_cast<int>(i);
+  }
+  for (int64_t k = live; k < nitems * CPG; ++k) {   // empty slots of the last group
+    Item& it = items[k / CPG];
+    const int c = static_cast<int>(k % CPG);
+    it.cell[c] = -1;
+    it.steps[c] = 0;
+    it.base[c] = 0;
+    it.row[c] = 0;
+  }
+  CK(cudaMemcpyAsync(ctx->d_items, items, static_cast<size_t>(nitems) * sizeof(Item), cudaMemcpyHostToDevice, ctx->stream));
 
   scr::StepParams<T> p;
   fill_common(ctx, p);
@@ -827,7 +830,7 @@ void scr_destroy(scr_ctx* ctx) {
     cudaDeviceSynchronize();
     free_network(ctx);
     free_dense_work(ctx);
-    cudaFree(ctx->d_state); cudaFree(ctx->d_items); cudaFree(ctx->d_counter); cudaFree(ctx->d_err); cudaFree(ctx->d_stage);
+    cudaFree(ctx->d_state); cudaFree(ctx->d_items); cudaFreeHost(ctx->h_items); cudaFree(ctx->d_counter); cudaFree(ctx->d_err); cudaFree(ctx->d_stage);
     free_counts_scratch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

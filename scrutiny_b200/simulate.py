@@ -15,6 +15,7 @@ exchanged in the read-out.  Noise is keyed by global cell id, so the result does
 the number of ranks.
 """
 import random
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -167,16 +168,33 @@ class LineageSimulation:
         for node in tree.walk():
             mem = np.asarray(node.cellTypeMembers, dtype=np.int64)
             below = np.asarray(node.childCellTypeMembers, dtype=np.int64)
-            self.plan.append(dict(node=node, members=mem,
-                                  mem_loc=mem[(mem >= self.lo) & (mem < self.hi)] - self.lo,
-                                  below_loc=below[(below >= self.lo) & (below < self.hi)] - self.lo))
+            mem_glob = mem[(mem >= self.lo) & (mem < self.hi)]
+            below_loc = below[(below >= self.lo) & (below < self.hi)] - self.lo
+            self.plan.append(dict(node=node, members=mem, mem_glob=mem_glob, mem_loc=mem_glob - self.lo, below_loc=below_loc,
+                                  ids=np.concatenate([mem_glob - self.lo, below_loc])))
         return self
+
+    def _member_uniforms(self, p):
+        """U[0,1) per local member of a node: a pure function of (seed, node, GLOBAL cell id)."""
+        return hashed_uniform(self.seed, 2 * int(p["node"].identifier) + 11, p["mem_glob"])
+
+    def _size_factors(self, cellRadiusDisp):
+        """N(1, sd)^3 per local cell (MS:875-876), Box-Muller on hashed uniforms of the global cell id."""
+        gid = np.arange(self.lo, self.hi, dtype=np.int64)
+        u1 = 1.0 - hashed_uniform(self.seed, 5, gid)
+        u2 = hashed_uniform(self.seed, 6, gid)
+        z = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+        return (1.0 + cellRadiusDisp * z) ** 3
 
     def run_all(self, tree=None, counts_out=None, counts_dev_ptr=None, seed=None, timeStep=0.01, noiseDisp=0.05,
                 convergenceThreshold=0.1, maxNumIterations=500, convDistAvgNum=20, cellsToSample=50,
                 geneMeanLevels=0.0, fixed_iterations=None, cellRadiusDisp=0.14, expScale=1.0, do_counts=True):
         """findAllNextStates + transformData for this rank's shard (tree prepared beforehand).
-        Returns dict(global_cell_steps, local_cell_steps, h2d_bytes, iterations, types, size_factors)."""
+        Returns dict(global_cell_steps, local_cell_steps, h2d_bytes, iterations, types, size_factors).
+
+        The per-cell draws that do not depend on a node's iteration count T (member uniforms, size factors) are
+        produced by one helper thread while the main thread sits in the engine's calls (ctypes and numpy release
+        the GIL), so they stay inside the run but off its critical path."""
         if self.plan is None:
             self.prepare(tree)
         if seed is not None:
@@ -188,47 +206,49 @@ class LineageSimulation:
         types = np.zeros(nloc, dtype=np.int64)
         local_steps, h2d = 0, 0
         self.node_iterations = {}
-        for p in self.plan:
-            node, mem = p["node"], p["members"]
-            if len(mem) == 0:                                                    # MS:579-580
-                continue
-            types[p["mem_loc"]] = int(node.identifier)
-            if fixed_iterations is None:
-                pick = mem[random.sample(range(len(mem)), cellsToSample)]        # same stream as MS:644
-                mine = pick[(pick >= self.lo) & (pick < self.hi)] - self.lo
-                total = 0.0
-                if len(mine):
-                    it = self.eng.probe(mine, node.proj, node.const, dt=timeStep, sigma=noiseDisp, mu=geneMeanLevels,
-                                        thresh=convergenceThreshold, max_iter=maxNumIterations,
-                                        avg_num=convDistAvgNum, seed=self.seed + 7919 * (int(node.identifier) + 1),
-                                        stream=STREAM_PROBE)
-                    total = float(it.sum())
-                total = float(self.comm.allreduce_sum(np.array([total]))[0])
-                T = int(total / cellsToSample) - convDistAvgNum
-            else:
-                T = int(fixed_iterations)
-            self.node_iterations[int(node.identifier)] = T
-            u = hashed_uniform(self.seed, 2 * int(node.identifier) + 11, p["mem_loc"] + self.lo)
-            k = np.minimum((u * (T + 1)).astype(np.int64), T)
-            ids = np.concatenate([p["mem_loc"], p["below_loc"]])
-            steps = np.concatenate([k, np.full(len(p["below_loc"]), T, dtype=np.int64)])
-            if len(ids) and steps.max() > 0:
-                self.eng.run_phase(ids, steps, node.proj, node.const, step_base=iters[ids], dt=timeStep,
-                                   sigma=noiseDisp, mu=geneMeanLevels, seed=self.seed)
-                h2d += len(ids) * 20 + 16 * len(node.proj)
-            iters[ids] += steps
-            local_steps += int(steps.sum())
-        size = None
-        if do_counts:
-            shift = self.gene_shift(expScale=expScale)
-            gid = np.arange(self.lo, self.hi, dtype=np.int64)
-            u1 = 1.0 - hashed_uniform(self.seed, 5, gid)
-            u2 = hashed_uniform(self.seed, 6, gid)
-            z = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
-            size = (1.0 + cellRadiusDisp * z) ** 3                               # MS:875-876
-            self.eng.counts(shift, size, exp_scale=expScale, seed=self.seed, out=counts_out,
-                            out_device_ptr=counts_dev_ptr)
-            h2d += shift.nbytes + size.nbytes
+        pool = ThreadPoolExecutor(max_workers=1)
+        try:
+            draws = [pool.submit(self._member_uniforms, p) for p in self.plan]
+            size_f = pool.submit(self._size_factors, cellRadiusDisp) if do_counts else None
+            for p, draw in zip(self.plan, draws):
+                node, mem = p["node"], p["members"]
+                if len(mem) == 0:                                                # MS:579-580
+                    continue
+                types[p["mem_loc"]] = int(node.identifier)
+                if fixed_iterations is None:
+                    pick = mem[random.sample(range(len(mem)), cellsToSample)]    # same stream as MS:644
+                    mine = pick[(pick >= self.lo) & (pick < self.hi)] - self.lo
+                    total = 0.0
+                    if len(mine):
+                        it = self.eng.probe(mine, node.proj, node.const, dt=timeStep, sigma=noiseDisp, mu=geneMeanLevels,
+                                            thresh=convergenceThreshold, max_iter=maxNumIterations,
+                                            avg_num=convDistAvgNum, seed=self.seed + 7919 * (int(node.identifier) + 1),
+                                            stream=STREAM_PROBE)
+                        total = float(it.sum())
+                    total = float(self.comm.allreduce_sum(np.array([total]))[0])
+                    T = int(total / cellsToSample) - convDistAvgNum
+                else:
+                    T = int(fixed_iterations)
+                self.node_iterations[int(node.identifier)] = T
+                ids, nmem = p["ids"], len(p["mem_loc"])
+                steps = np.full(len(ids), T, dtype=np.int32)                     # descendants step T (MS:599-605)
+                np.minimum((draw.result() * (T + 1)).astype(np.int32), T, out=steps[:nmem])   # members k ~ U{0..T} (MS:589)
+                base = iters[ids]
+                if len(ids) and T > 0:
+                    self.eng.run_phase(ids, steps, node.proj, node.const, step_base=base, dt=timeStep,
+                                       sigma=noiseDisp, mu=geneMeanLevels, seed=self.seed)
+                    h2d += len(ids) * 20 + 16 * len(node.proj)
+                iters[ids] = base + steps                                        # ids are unique within a node
+                local_steps += int(steps.sum(dtype=np.int64))
+            size = None
+            if do_counts:
+                shift = self.gene_shift(expScale=expScale)
+                size = size_f.result()
+                self.eng.counts(shift, size, exp_scale=expScale, seed=self.seed, out=counts_out,
+                                out_device_ptr=counts_dev_ptr)
+                h2d += shift.nbytes + size.nbytes
+        finally:
+            pool.shutdown(wait=True)
         glob = float(self.comm.allreduce_sum(np.array([float(local_steps)]))[0])
         return dict(global_cell_steps=glob, local_cell_steps=local_steps, h2d_bytes=h2d, iterations=iters,
                     types=types, size_factors=size)
