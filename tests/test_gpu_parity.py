@@ -458,3 +458,46 @@ def test_warp_specialised_stepper_matches_single_role_kernel_and_oracle(eng_mod)
             want = X0.copy()
             fo.run_phase(fo.as_operator(W), want, steps, np.ones(n), np.zeros(n), 0.01, dump, mu=0.05)
             assert np.max(np.abs(outs[0].T - want)) <= 1e-4
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_partly_resident_operator_is_bit_identical(eng_mod, prec):
+    """When the operator does not fit in shared memory next to the cell groups, its head is staged there and the
+    rest read through L1 (StepParams::w_prefix).  Where an entry is read from must not change a single bit: compare
+    SCR_W_PREFIX_KB=0 (all global), 4 (a few blocks staged) and the default (all that fits) on a network big enough
+    that the default is partial, with long rows (chunk table beyond the prefix) and ragged steps."""
+    import os
+    n, cells, seed = 3000, 1300, 99   # > 2 x 148 groups: two groups per CTA, so the default prefix is partial
+    rng = np.random.RandomState(4)
+    W = np.zeros((n, n))
+    regs = rng.choice(n, size=2000, replace=False)
+    for r in range(n):
+        k = 1 + int(rng.rand() < 0.6) + 40 * int(rng.rand() < 0.01)
+        W[r, rng.choice(regs, size=k, replace=False)] = rng.beta(2, 3, size=k) * rng.choice([-1, 1]) * 3.0
+    X0 = rng.uniform(-1, 1, size=(n, cells))
+    steps = rng.randint(0, 25, size=cells)
+    proj = (rng.rand(n) > 0.05).astype(np.float64)
+    const = 0.1 * rng.randn(n) * (1 - proj)
+    outs, iters = [], []
+    for kb in ("0", "4", None):
+        if kb is not None:
+            os.environ["SCR_W_PREFIX_KB"] = kb
+        try:
+            e = make_engine(eng_mod, prec, W, cells, offset=123)
+            lay = e.layout()
+            e.set_states(X0)
+            e.run_phase(np.arange(cells), steps, proj, const, seed=seed)
+            it = e.probe(np.arange(0, cells, 11), proj, const, max_iter=60, seed=seed)
+        finally:
+            os.environ.pop("SCR_W_PREFIX_KB", None)
+        if kb == "0":
+            assert lay["operator_prefix_bytes"] == 0
+        elif kb == "4":
+            assert lay["operator_prefix_bytes"] == 4096
+        elif not lay["operator_in_smem"]:
+            assert 0 < lay["operator_prefix_bytes"] < lay["operator_bytes"]
+        outs.append(e.get_states())
+        iters.append(it)
+    for o, it in zip(outs[1:], iters[1:]):
+        assert np.array_equal(o, outs[0])
+        assert np.array_equal(it, iters[0])
