@@ -291,9 +291,20 @@ def main():
     gathered = [torch.empty((per_gpu, n), dtype=torch.int32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     layout = eng.layout()
 
-    def gather_counts():
+    # the count matrix is sampled in row blocks; each finished block is handed to NCCL at once (asynchronous gather to
+    # rank 0), so the transfer of block i runs under the sampling of block i+1
+    COUNT_BLOCKS = 4 if world > 1 else 1
+    pending = []
+
+    def gather_block(r0, r1):
         if world > 1:
-            dist.gather(counts_dev, gathered, dst=0)
+            pending.append(dist.gather(counts_dev[r0:r1], [g[r0:r1] for g in gathered] if rank == 0 else None,
+                                       dst=0, async_op=True))
+
+    def gather_counts():
+        for w in pending:
+            w.wait()
+        pending.clear()
 
     def barrier():
         if world > 1:
@@ -303,7 +314,8 @@ def main():
     # ---- warm-up ----
     for w in range(args.warmup):
         eng.set_states_broadcast(x0)
-        sim.run_all(tree, counts_dev_ptr=counts_dev.data_ptr(), seed=1337 + w)
+        sim.run_all(tree, counts_dev_ptr=counts_dev.data_ptr(), seed=1337 + w, counts_blocks=COUNT_BLOCKS,
+                    on_counts_block=gather_block)
         gather_counts()
     barrier()
 
@@ -322,7 +334,8 @@ def main():
         barrier()
         ev0.record()
         t0 = time.perf_counter()
-        res = sim.run_all(tree, counts_dev_ptr=counts_dev.data_ptr(), seed=2000 + k)
+        res = sim.run_all(tree, counts_dev_ptr=counts_dev.data_ptr(), seed=2000 + k, counts_blocks=COUNT_BLOCKS,
+                          on_counts_block=gather_block)
         gather_counts()
         barrier()
         ev1.record()

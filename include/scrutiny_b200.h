@@ -116,6 +116,13 @@ int scr_gene_sums(scr_ctx* ctx, double* sums_out /* n */);
 int scr_counts(scr_ctx* ctx, const double* shift /* n */, double exp_scale,
                const double* size_factors /* cells */, uint64_t seed, const double* uniforms,
                int32_t draws_per_entry, int32_t* counts_out, int out_on_device, double* lambda_out);
+/* the same for local cells [cell_begin, cell_begin + cell_count) only: size_factors, uniforms, counts_out and
+ * lambda_out hold cell_count rows.  Lets a caller hand finished row blocks on (NCCL gather, file writer) while the
+ * next block is sampled; scr_counts is this call over all cells. */
+int scr_counts_range(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const double* shift /* n */,
+                     double exp_scale, const double* size_factors /* cell_count */, uint64_t seed,
+                     const double* uniforms, int32_t draws_per_entry, int32_t* counts_out, int out_on_device,
+                     double* lambda_out);
 
 /* ---- debugging / parity aids ------------------------------------------------------------------ */
 /* raw Philox4x32-10 words for counters (c0..c3)[count] under key (k0,k1): device generator check */

@@ -1082,13 +1082,16 @@ int scr_gene_sums(scr_ctx* ctx, double* sums_out) {
   return SCR_OK;
 }
 
-int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double* size_factors, uint64_t seed,
-               const double* uniforms, int32_t draws_per_entry, int32_t* counts_out, int out_on_device, double* lambda_out) {
+int scr_counts_range(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const double* shift, double exp_scale,
+                     const double* size_factors, uint64_t seed, const double* uniforms, int32_t draws_per_entry,
+                     int32_t* counts_out, int out_on_device, double* lambda_out) {
   NEED_GPU();
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (!shift || !size_factors || !counts_out) return fail(ctx, SCR_E_ARG, "bad arguments");
+  if (cell_begin < 0 || cell_count < 0 || cell_begin + cell_count > ctx->cells) return fail(ctx, SCR_E_ARG, "cell range out of bounds");
+  if (cell_count == 0) return SCR_OK;
   const int n = ctx->op.n;
-  const int64_t cells = ctx->cells;
+  const int64_t cells = cell_count;   // rows of this call: local slots [cell_begin, cell_begin + cells)
   double *d_uni = nullptr, *d_lam = nullptr;   // parity / debug inputs only: allocated per call
   int rc = SCR_OK;
   auto cleanup = [&]() { cudaFree(d_uni); cudaFree(d_lam); };
@@ -1105,7 +1108,7 @@ int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double
 #define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
   CKC(cudaMemcpyAsync(d_order, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemcpyAsync(d_shift, shift, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CKC(cudaMemcpyAsync(d_size, size_factors, cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemcpyAsync(d_size, size_factors, cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));   // entry r <-> slot cell_begin + r
   CKC(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
   if (uniforms) {
     const size_t cnt = static_cast<size_t>(cells) * n * draws_per_entry;
@@ -1114,11 +1117,14 @@ int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double
   }
   if (lambda_out) CKC(cudaMalloc(&d_lam, static_cast<size_t>(cells) * n * sizeof(double)));
   const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_COUNTS);
+  // the kernel indexes size factors and supplied uniforms by local cell slot: rebase the range's buffers
+  const double* size_by_slot = d_size - cell_begin;
   auto launch = [&](int64_t c0, int64_t cnt, int32_t* out, double* lam) -> cudaError_t {
+    const double* uni_by_slot = d_uni ? d_uni - cell_begin * n * static_cast<int64_t>(draws_per_entry) : nullptr;
     if (ctx->prec == SCR_F64)
-      scr::counts_kernel<double><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const double*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, c0, d_shift, exp_scale, d_size, k0, k1, ctx->cell_offset, d_uni, draws_per_entry, out, lam, ctx->d_err);
+      scr::counts_kernel<double><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const double*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, cell_begin + c0, d_shift, exp_scale, size_by_slot, k0, k1, ctx->cell_offset, uni_by_slot, draws_per_entry, out, lam, ctx->d_err);
     else
-      scr::counts_kernel<float><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const float*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, c0, d_shift, exp_scale, d_size, k0, k1, ctx->cell_offset, d_uni, draws_per_entry, out, lam, ctx->d_err);
+      scr::counts_kernel<float><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const float*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, cell_begin + c0, d_shift, exp_scale, size_by_slot, k0, k1, ctx->cell_offset, uni_by_slot, draws_per_entry, out, lam, ctx->d_err);
     ctx->launches++;
     return cudaGetLastError();
   };
@@ -1152,6 +1158,13 @@ int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double
   cleanup();
   if (herr) return fail(ctx, SCR_E_DRAWS, "supplied uniforms exhausted (raise draws_per_entry)");
   return rc;
+}
+
+int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double* size_factors, uint64_t seed,
+               const double* uniforms, int32_t draws_per_entry, int32_t* counts_out, int out_on_device, double* lambda_out) {
+  if (!ctx) return SCR_E_ARG;
+  return scr_counts_range(ctx, 0, ctx->cells, shift, exp_scale, size_factors, seed, uniforms, draws_per_entry, counts_out,
+                          out_on_device, lambda_out);
 }
 
 int scr_debug_philox(scr_ctx* ctx, int64_t count, const uint32_t* ctr4, uint32_t k0, uint32_t k1, uint32_t* out4) {

@@ -156,26 +156,29 @@ class Engine:
         return out
 
     def counts(self, shift, size_factors, exp_scale=1.0, seed=0, uniforms=None, out=None, out_device_ptr=None,
-               want_lambda=False):
-        """Returns int32 (cells, n) (host) unless ``out_device_ptr`` (int) is given."""
+               want_lambda=False, cell_begin=0, cell_count=None):
+        """Returns int32 (cells, n) (host) unless ``out_device_ptr`` (int) is given.  ``cell_begin`` / ``cell_count``
+        restrict the call to a block of local cells (scr_counts_range): ``size_factors``, ``uniforms``, ``out`` /
+        ``out_device_ptr`` then describe that block's rows only."""
+        rows = self.cells - int(cell_begin) if cell_count is None else int(cell_count)
         shift, size_factors = _f64(shift), _f64(size_factors)
-        assert len(size_factors) == self.cells and len(shift) == self.n
+        assert len(size_factors) == rows and len(shift) == self.n
         uni, draws = None, 0
         if uniforms is not None:
             uni = _f64(uniforms)
-            assert uni.shape[:2] == (self.cells, self.n)
+            assert uni.shape[:2] == (rows, self.n)
             draws = uni.shape[2]
-        lam = np.zeros((self.cells, self.n)) if want_lambda else None
+        lam = np.zeros((rows, self.n)) if want_lambda else None
         if out_device_ptr is not None:
             ptr, on_dev = C.c_void_p(int(out_device_ptr)), 1
         else:
             if out is None:
-                out = np.empty((self.cells, self.n), dtype=np.int32)
-            assert out.dtype == np.int32 and out.flags.c_contiguous
+                out = np.empty((rows, self.n), dtype=np.int32)
+            assert out.dtype == np.int32 and out.flags.c_contiguous and out.shape == (rows, self.n)
             ptr, on_dev = C.c_void_p(out.ctypes.data), 0
-        self._check(self._lib.scr_counts(self._ctx, _ptr(shift, C.c_double), float(exp_scale),
-                                         _ptr(size_factors, C.c_double), int(seed) & (2 ** 64 - 1),
-                                         _ptr(uni, C.c_double), int(draws), ptr, on_dev, _ptr(lam, C.c_double)))
+        self._check(self._lib.scr_counts_range(self._ctx, int(cell_begin), rows, _ptr(shift, C.c_double), float(exp_scale),
+                                               _ptr(size_factors, C.c_double), int(seed) & (2 ** 64 - 1),
+                                               _ptr(uni, C.c_double), int(draws), ptr, on_dev, _ptr(lam, C.c_double)))
         return (out, lam) if want_lambda else out
 
     # -- RegNetInference front end ------------------------------------------------------------

@@ -188,9 +188,14 @@ class LineageSimulation:
 
     def run_all(self, tree=None, counts_out=None, counts_dev_ptr=None, seed=None, timeStep=0.01, noiseDisp=0.05,
                 convergenceThreshold=0.1, maxNumIterations=500, convDistAvgNum=20, cellsToSample=50,
-                geneMeanLevels=0.0, fixed_iterations=None, cellRadiusDisp=0.14, expScale=1.0, do_counts=True):
+                geneMeanLevels=0.0, fixed_iterations=None, cellRadiusDisp=0.14, expScale=1.0, do_counts=True,
+                counts_blocks=1, on_counts_block=None):
         """findAllNextStates + transformData for this rank's shard (tree prepared beforehand).
         Returns dict(global_cell_steps, local_cell_steps, h2d_bytes, iterations, types, size_factors).
+
+        ``counts_blocks`` > 1 samples the count matrix in that many row blocks and calls
+        ``on_counts_block(row0, row1)`` after each: the caller can pass finished rows on (NCCL gather in bench.py)
+        while the next block is sampled.
 
         The per-cell draws that do not depend on a node's iteration count T (member uniforms, size factors) are
         produced by one helper thread while the main thread sits in the engine's calls (ctypes and numpy release
@@ -244,8 +249,15 @@ class LineageSimulation:
             if do_counts:
                 shift = self.gene_shift(expScale=expScale)
                 size = size_f.result()
-                self.eng.counts(shift, size, exp_scale=expScale, seed=self.seed, out=counts_out,
-                                out_device_ptr=counts_dev_ptr)
+                nblk = max(1, min(int(counts_blocks), nloc))
+                edges = [nloc * b // nblk for b in range(nblk + 1)]
+                n_genes = len(shift)
+                for r0, r1 in zip(edges[:-1], edges[1:]):
+                    self.eng.counts(shift, size[r0:r1], exp_scale=expScale, seed=self.seed, cell_begin=r0, cell_count=r1 - r0,
+                                    out=None if counts_out is None else counts_out[r0:r1],
+                                    out_device_ptr=None if counts_dev_ptr is None else counts_dev_ptr + 4 * n_genes * r0)
+                    if on_counts_block is not None:
+                        on_counts_block(r0, r1)
                 h2d += shift.nbytes + size.nbytes
         finally:
             pool.shutdown(wait=True)

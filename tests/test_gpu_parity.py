@@ -416,6 +416,36 @@ def test_counts_float32_context_and_statistics(eng_mod):
     assert np.array_equal(buf.cpu().numpy(), got)
 
 
+def test_counts_by_row_blocks_equal_one_call(eng_mod):
+    """scr_counts_range: sampling the matrix in ragged row blocks (host and device output, Philox and supplied
+    uniforms, lambda dump) gives exactly the integers of one call over all cells; bad ranges are refused."""
+    import torch
+    n, cells = 96, 203
+    rng = np.random.RandomState(23)
+    e = make_engine(eng_mod, "f32", sparse_net(n, 81), cells, offset=777)
+    e.set_states(np.tanh(rng.randn(n, cells)))
+    shift = rng.normal(0.3, 1.5, size=n)
+    size = rng.normal(1, 0.14, size=cells) ** 3
+    U = rng.random_sample((cells, n, 40))
+    U[:, :, 20:] = np.clip(U[:, :, 20:], 0.0, 0.5)
+    whole, lam = e.counts(shift, size, seed=11, want_lambda=True)
+    whole_u = e.counts(shift, size, uniforms=U)
+    edges = [0, 1, 64, 65, 130, 203]
+    host = np.full((cells, n), -1, dtype=np.int32)
+    dev = torch.full((cells, n), -1, dtype=torch.int32, device="cuda:0")
+    for r0, r1 in zip(edges[:-1], edges[1:]):
+        got, lam_b = e.counts(shift, size[r0:r1], seed=11, cell_begin=r0, cell_count=r1 - r0, out=host[r0:r1], want_lambda=True)
+        assert np.array_equal(lam_b, lam[r0:r1])
+        e.counts(shift, size[r0:r1], seed=11, cell_begin=r0, cell_count=r1 - r0, out_device_ptr=dev.data_ptr() + 4 * n * r0)
+        assert np.array_equal(e.counts(shift, size[r0:r1], uniforms=U[r0:r1], cell_begin=r0, cell_count=r1 - r0), whole_u[r0:r1])
+    torch.cuda.synchronize()
+    assert np.array_equal(host, whole) and np.array_equal(dev.cpu().numpy(), whole)
+    for bad in ((-1, 4), (200, 4), (0, cells + 1)):
+        with pytest.raises(eng_mod.ScrutinyError) as err:
+            e.counts(shift, np.ones(bad[1]), cell_begin=bad[0], cell_count=bad[1])
+        assert err.value.code == -1
+
+
 def test_counts_uniform_exhaustion_is_an_error(eng_mod):
     n, cells = 32, 2
     e = make_engine(eng_mod, "f64", sparse_net(n, 71), cells)

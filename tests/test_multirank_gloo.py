@@ -44,9 +44,12 @@ class OracleEngine:
     def gene_sums(self):
         return self.X.sum(axis=0)
 
-    def counts(self, shift, size, exp_scale=1.0, seed=0, out=None, out_device_ptr=None):
-        self.lam = self.fo.poisson_lambda(self.X.T, shift, exp_scale, size).T
-        return self.lam
+    def counts(self, shift, size, exp_scale=1.0, seed=0, out=None, out_device_ptr=None, cell_begin=0, cell_count=None):
+        r1 = len(self.X) if cell_count is None else cell_begin + cell_count
+        if cell_begin == 0:
+            self.lam = np.zeros_like(self.X)
+        self.lam[cell_begin:r1] = self.fo.poisson_lambda(self.X[cell_begin:r1].T, shift, exp_scale, size).T
+        return self.lam[cell_begin:r1]
 
 
 def build_case():
@@ -82,7 +85,11 @@ def run_rank(rank, world, port_no, out_path):
     eng = OracleEngine(W, hi - lo, lo)
     eng.set_states_broadcast(x0)
     sim = LineageSimulation(eng, cells, lo, hi, comm=Comm(), seed=99)
-    res = sim.run_all(tree, seed=99, cellsToSample=6, maxNumIterations=60, convDistAvgNum=5, convergenceThreshold=0.6)
+    blocks = []   # the two-rank run samples its counts in three row blocks (bench.py's gather overlap), the one-rank run in one
+    res = sim.run_all(tree, seed=99, cellsToSample=6, maxNumIterations=60, convDistAvgNum=5, convergenceThreshold=0.6,
+                      counts_blocks=3 if world > 1 else 1, on_counts_block=lambda r0, r1: blocks.append((r0, r1)))
+    assert blocks[0][0] == 0 and blocks[-1][1] == hi - lo and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+    assert len(blocks) == (3 if world > 1 else 1)
     np.savez(out_path, lo=lo, hi=hi, X=eng.X, iters=res["iterations"], types=res["types"], size=res["size_factors"],
              lam=eng.lam, glob=res["global_cell_steps"], T=np.array(sorted(sim.node_iterations.items())))
     if world > 1:
