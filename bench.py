@@ -293,7 +293,7 @@ def main():
 
     # the count matrix is sampled in row blocks; each finished block is handed to NCCL at once (asynchronous gather to
     # rank 0), so the transfer of block i runs under the sampling of block i+1
-    COUNT_BLOCKS = 4 if world > 1 else 1
+    COUNT_BLOCKS = 8 if world > 1 else 1
     pending = []
 
     def gather_block(r0, r1):
