@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "aux_kernels.cuh"
@@ -377,37 +379,72 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
                 const double* proj, const double* cnst, double dt, double sigma, double mu, uint64_t seed,
                 const double* noise, int64_t noise_steps) {
   constexpr int CPG = scr::Traits<T>::CPG;
-  // longest first (counting sort on the step count), then groups of CPG consecutive cells
-  int smax = 0;
-  for (int64_t i = 0; i < m; ++i) {
-    if (cell_ids[i] < 0 || cell_ids[i] >= ctx->cells) return fail(ctx, SCR_E_ARG, "cell id out of range");
-    if (steps[i] < 0) return fail(ctx, SCR_E_ARG, "negative step count");
-    smax = std::max(smax, steps[i]);
-  }
+  // Longest first (counting sort on the step count), then groups of CPG consecutive cells, built straight in the
+  // pinned staging buffer: cell i goes to position pos[bucket]++ of the sorted order, i.e. slot (position % CPG) of
+  // group (position / CPG).  Each bucket writes sequentially, so this is a ~500-way streaming scatter.  Large phases
+  // split the cell list over a few host threads (per-thread histograms -> per-thread start positions), which keeps
+  // the sequential order exactly.
+  const int nthr = m >= (1 << 16) ? std::max(1, std::min(scr::env_int("SCR_HOST_THREADS", 4), 16)) : 1;
+  auto span = [&](int t) { return std::make_pair(m * t / nthr, m * (t + 1) / nthr); };
+  auto parallel = [&](auto&& fn) {
+    std::vector<std::thread> th;
+    int started = 1;
+    try {
+      for (int t = 1; t < nthr; ++t) { th.emplace_back(fn, t); ++started; }
+    } catch (...) {}                                     // no exception crosses the C ABI: unstarted spans run here
+    fn(0);
+    for (int t = started; t < nthr; ++t) fn(t);
+    for (auto& x : th) x.join();
+  };
+  std::vector<int> t_smax(nthr, 0), t_bad(nthr, 0);
+  parallel([&](int t) {
+    int mx = 0, bad = 0;
+    for (int64_t i = span(t).first; i < span(t).second; ++i) {
+      if (cell_ids[i] < 0 || cell_ids[i] >= ctx->cells) bad |= 1;
+      if (steps[i] < 0) bad |= 2;
+      mx = std::max(mx, steps[i]);
+    }
+    t_smax[t] = mx;
+    t_bad[t] = bad;
+  });
+  int smax = 0, bad = 0;
+  for (int t = 0; t < nthr; ++t) { smax = std::max(smax, t_smax[t]); bad |= t_bad[t]; }
+  if (bad & 1) return fail(ctx, SCR_E_ARG, "cell id out of range");
+  if (bad & 2) return fail(ctx, SCR_E_ARG, "negative step count");
   if (noise && smax > noise_steps) return fail(ctx, SCR_E_ARG, "supplied noise shorter than the longest cell");
   if (smax == 0) return SCR_OK;
-  // one scatter pass straight into the pinned staging buffer: cell i goes to position pos[bucket]++ of the sorted order,
-  // i.e. slot (position % CPG) of group (position / CPG); each bucket writes sequentially, so this is a 500-way streaming
-  // scatter (a vector of Items + pageable copy cost 4x as much at 10^6 cells: 4 % of the bench step)
-  std::vector<int64_t> pos(static_cast<size_t>(smax) + 2, 0);
-  for (int64_t i = 0; i < m; ++i) if (steps[i] > 0) pos[smax - steps[i] + 1]++;
-  for (int s = 0; s <= smax; ++s) pos[s + 1] += pos[s];
-  const int64_t live = pos[smax];
+  const size_t nbuckets = static_cast<size_t>(smax);                 // bucket b <-> step count smax - b
+  std::vector<int64_t> pos(static_cast<size_t>(nthr) * nbuckets, 0);  // pos[t * nbuckets + b]
+  parallel([&](int t) {
+    int64_t* h = pos.data() + static_cast<size_t>(t) * nbuckets;
+    for (int64_t i = span(t).first; i < span(t).second; ++i) if (steps[i] > 0) h[smax - steps[i]]++;
+  });
+  int64_t live = 0;
+  for (size_t b = 0; b < nbuckets; ++b)
+    for (int t = 0; t < nthr; ++t) {
+      int64_t& h = pos[static_cast<size_t>(t) * nbuckets + b];
+      const int64_t cnt = h;
+      h = live;
+      live += cnt;
+    }
   const int64_t nitems = (live + CPG - 1) / CPG;
   if (nitems > 0x7fffffff) return fail(ctx, SCR_E_ARG, "too many cell groups");
   int rc = ensure_items(ctx, static_cast<size_t>(nitems));
   if (rc) return rc;
   Item* items = ctx->h_items;
-  for (int64_t i = 0; i < m; ++i) {
-    if (steps[i] <= 0) continue;
-    const int64_t k = pos[smax - steps[i]]++;
-    Item& it = items[k / CPG];
-    const int c = static_cast<int>(k % CPG);
-    it.cell[c] = static_cast<int>(cell_ids[i]);
-    it.steps[c] = steps[i];
-    it.base[c] = static_cast<uint32_t>(step_base ? step_base[i] : 0);
-    it.row[c] = static_cast<int>(i);
-  }
+  parallel([&](int t) {
+    int64_t* next = pos.data() + static_cast<size_t>(t) * nbuckets;
+    for (int64_t i = span(t).first; i < span(t).second; ++i) {
+      if (steps[i] <= 0) continue;
+      const int64_t k = next[smax - steps[i]]++;
+      Item& it = items[k / CPG];
+      const int c = static_cast<int>(k % CPG);
+      it.cell[c] = static_cast<int>(cell_ids[i]);
+      it.steps[c] = steps[i];
+      it.base[c] = static_cast<uint32_t>(step_base ? step_base[i] : 0);
+      it.row[c] = static_cast<int>(i);
+    }
+  });
   for (int64_t k = live; k < nitems * CPG; ++k) {   // empty slots of the last group
     Item& it = items[k / CPG];
     const int c = static_cast<int>(k % CPG);

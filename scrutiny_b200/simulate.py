@@ -213,13 +213,25 @@ class LineageSimulation:
         self.node_iterations = {}
         pool = ThreadPoolExecutor(max_workers=1)
         try:
-            draws = [pool.submit(self._member_uniforms, p) for p in self.plan]
+            # helper-thread work, in submission order: the type record (no dependence on T), then per node the member
+            # uniforms; the iteration bookkeeping of a node is queued right before its phase is launched, so it runs
+            # under that phase and the next node finds its step bases ready
+            live = [p for p in self.plan if len(p["members"])]                   # MS:579-580 skips empty types
+
+            def record_types():
+                for p in live:
+                    types[p["mem_loc"]] = int(p["node"].identifier)
+
+            def bookkeeping(ids, steps, next_ids):
+                iters[ids] += steps                                              # ids are unique within a node
+                return iters[next_ids] if next_ids is not None else None
+
+            typed = pool.submit(record_types)
+            draws = [pool.submit(self._member_uniforms, p) for p in live]
             size_f = pool.submit(self._size_factors, cellRadiusDisp) if do_counts else None
-            for p, draw in zip(self.plan, draws):
+            base_f = None
+            for i, (p, draw) in enumerate(zip(live, draws)):
                 node, mem = p["node"], p["members"]
-                if len(mem) == 0:                                                # MS:579-580
-                    continue
-                types[p["mem_loc"]] = int(node.identifier)
                 if fixed_iterations is None:
                     pick = mem[random.sample(range(len(mem)), cellsToSample)]    # same stream as MS:644
                     mine = pick[(pick >= self.lo) & (pick < self.hi)] - self.lo
@@ -238,13 +250,17 @@ class LineageSimulation:
                 ids, nmem = p["ids"], len(p["mem_loc"])
                 steps = np.full(len(ids), T, dtype=np.int32)                     # descendants step T (MS:599-605)
                 np.minimum((draw.result() * (T + 1)).astype(np.int32), T, out=steps[:nmem])   # members k ~ U{0..T} (MS:589)
-                base = iters[ids]
+                base = base_f.result() if base_f is not None else iters[ids]
+                next_ids = live[i + 1]["ids"] if i + 1 < len(live) else None
+                base_f = pool.submit(bookkeeping, ids, steps, next_ids)
                 if len(ids) and T > 0:
                     self.eng.run_phase(ids, steps, node.proj, node.const, step_base=base, dt=timeStep,
                                        sigma=noiseDisp, mu=geneMeanLevels, seed=self.seed)
                     h2d += len(ids) * 20 + 16 * len(node.proj)
-                iters[ids] = base + steps                                        # ids are unique within a node
                 local_steps += int(steps.sum(dtype=np.int64))
+            if base_f is not None:
+                base_f.result()
+            typed.result()
             size = None
             if do_counts:
                 shift = self.gene_shift(expScale=expScale)

@@ -57,6 +57,14 @@ def test_determinism_and_independence_of_partitioning(big):
     parts = np.array_split(perm, 7)
     d = sample_states(run(big, parts), probe)
     assert np.array_equal(a, d)                                           # seven launches instead of one
+    import os
+    for threads in ("1", "3"):                                            # host-side group building: 4 threads by default
+        os.environ["SCR_HOST_THREADS"] = threads
+        try:
+            t = sample_states(run(big, [perm]), probe)
+        finally:
+            del os.environ["SCR_HOST_THREADS"]
+        assert np.array_equal(a, t)
     assert not np.array_equal(a[:, 0], a[:, 1])
 
 
