@@ -65,9 +65,10 @@ struct UniformSource {
   const double* supplied;   // nullptr -> Philox
   int64_t sup_base;
   int sup_count, used;
-  uint32_t c0, c2, c3, k0, k1, call;
-  uint32_t w[4];
-  int have;
+  uint32_t c0, c2, c3, call;
+  const RoundKeys* rk;      // Philox round keys of (seed, SCR_STREAM_COUNTS): kernel parameter, constant bank
+  uint32_t w0, w1, w2, w3;  // words of the current call, consumed front to back (scalars: a dynamically indexed
+  int have;                 //  array would live in local memory)
   int* err;
   __device__ double next() {
     if (supplied) {
@@ -75,10 +76,13 @@ struct UniformSource {
       return supplied[sup_base + used++];
     }
     if (have == 0) {
-      philox4x32_10(c0, call++, c2, c3, k0, k1, w);
+      uint32_t w[4];
+      philox4x32_10_rk(c0, call++, c2, c3, *rk, w);
+      w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3];
       have = 4;
     }
-    const uint32_t v = w[4 - have];
+    const uint32_t v = w0;
+    w0 = w1; w1 = w2; w2 = w3;
     --have;
     ++used;
     return (static_cast<double>(v) + 0.5) * 2.3283064365386963e-10;   // (v + 1/2) / 2^32 in (0,1)
@@ -119,10 +123,14 @@ __device__ inline int poisson_draw(double lam, UniformSource& u) {
 // their shift (the dominant term of log lambda): the 32 lanes of a warp then see similar lambda and leave
 // the sampler's loops together instead of waiting for the largest one.  Counts are staged in shared
 // memory and written as one coalesced int32 row in the caller's gene order.
+#ifndef SCR_COUNTS_CTAS_PER_SM
+#define SCR_COUNTS_CTAS_PER_SM 4   // 64 registers: the sampler is latency-bound (dependent FP64 chains), more warps pay (2 / 3 / 4 CTAs: 28.8 / 22.5 / 21.5 ms at 400k cells)
+#endif
 template <typename T>
-__global__ void counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ inv,
+__global__ void __launch_bounds__(256, SCR_COUNTS_CTAS_PER_SM)
+counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ inv,
                               const int* __restrict__ order, int n, int64_t cell0, const double* __restrict__ shift,
-                              double exp_scale, const double* __restrict__ sizef, uint32_t k0, uint32_t k1,
+                              double exp_scale, const double* __restrict__ sizef, const RoundKeys rk,
                               int64_t cell_offset, const double* __restrict__ uniforms, int draws,
                               int32_t* __restrict__ out, double* __restrict__ lam_out, int* err) {
   extern __shared__ int32_t s_counts[];
@@ -143,7 +151,8 @@ __global__ void counts_kernel(const T* __restrict__ state, int64_t ld, const int
     u.c0 = static_cast<uint32_t>(o);
     u.c2 = static_cast<uint32_t>(gid);
     u.c3 = static_cast<uint32_t>(gid >> 32);
-    u.k0 = k0; u.k1 = k1; u.call = 0; u.have = 0; u.err = err;
+    u.rk = &rk; u.call = 0; u.have = 0; u.err = err;
+    u.w0 = u.w1 = u.w2 = u.w3 = 0;
     s_counts[o] = poisson_draw(lam, u);
     if (lam_out) lam_out[static_cast<int64_t>(blockIdx.x) * n + o] = lam;
   }

@@ -1153,15 +1153,16 @@ int scr_counts_range(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const
     CKC(cudaMemcpyAsync(d_uni, uniforms, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
   if (lambda_out) CKC(cudaMalloc(&d_lam, static_cast<size_t>(cells) * n * sizeof(double)));
-  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_COUNTS);
+  scr::RoundKeys crk;
+  scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_COUNTS), crk);
   // the kernel indexes size factors and supplied uniforms by local cell slot: rebase the range's buffers
   const double* size_by_slot = d_size - cell_begin;
   auto launch = [&](int64_t c0, int64_t cnt, int32_t* out, double* lam) -> cudaError_t {
     const double* uni_by_slot = d_uni ? d_uni - cell_begin * n * static_cast<int64_t>(draws_per_entry) : nullptr;
     if (ctx->prec == SCR_F64)
-      scr::counts_kernel<double><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const double*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, cell_begin + c0, d_shift, exp_scale, size_by_slot, k0, k1, ctx->cell_offset, uni_by_slot, draws_per_entry, out, lam, ctx->d_err);
+      scr::counts_kernel<double><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const double*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, cell_begin + c0, d_shift, exp_scale, size_by_slot, crk, ctx->cell_offset, uni_by_slot, draws_per_entry, out, lam, ctx->d_err);
     else
-      scr::counts_kernel<float><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const float*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, cell_begin + c0, d_shift, exp_scale, size_by_slot, k0, k1, ctx->cell_offset, uni_by_slot, draws_per_entry, out, lam, ctx->d_err);
+      scr::counts_kernel<float><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const float*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, cell_begin + c0, d_shift, exp_scale, size_by_slot, crk, ctx->cell_offset, uni_by_slot, draws_per_entry, out, lam, ctx->d_err);
     ctx->launches++;
     return cudaGetLastError();
   };
