@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=1000000, help="cells per GPU")
     ap.add_argument("--genes", type=int, default=GENES)
+    ap.add_argument("--network", default="powerlaw", choices=["powerlaw", "trrust"],
+                    help="powerlaw = the contract workload; trrust = the same pass on the TRRUST network (n = 2895)")
     ap.add_argument("--alpha", type=float, default=None, help="skip the search")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
@@ -58,10 +60,14 @@ def parse():
 # ---------------------------------------------------------------------------------------------
 # workload construction (host, deterministic, identical on every rank)
 # ---------------------------------------------------------------------------------------------
-def build_network(n):
+def build_network(n, kind="powerlaw"):
+    """kind "powerlaw" (the default workload) or "trrust" (the other network BASELINE.json's config 5 names;
+    n is then TRRUST's own 2895, MS:99-100)."""
     from scrutiny_b200 import network
     np.random.seed(1337)
     random.seed(1337)
+    if kind == "trrust":
+        return network.generate_gene_correlation_matrix(0, "TRRUST")
     gc, tf = network.generate_gene_correlation_matrix(n, "SimulatedPowerLaw", powerLawExponent=EXPONENT)
     return gc, tf
 
@@ -212,10 +218,10 @@ def cpu_baseline(gc, proj, const, x0, seconds):
 def run_reference(args, rank):
     if rank != 0:
         return
-    n = args.genes
-    gc, tf = build_network(n)
+    gc, tf = build_network(args.genes, args.network)
+    n = gc.shape[0]
     tree = build_tree(n, 1000, tf)
-    alpha = args.alpha if args.alpha else ALPHA_SEARCHED
+    alpha = args.alpha if args.alpha else (0.1 if args.network == "trrust" else ALPHA_SEARCHED)
     gc = gc / alpha
     x0 = 2.0 * np.random.rand(n) - 1.0
     vals, infos = [], None
@@ -237,10 +243,10 @@ def run_reference(args, rank):
 
 
 def workload_config(args, n, nnz, alpha, note=None):
-    cfg = {"workload": "c5: MatriSeq SimulatedPowerLaw n=%d powerLawExponent=%.1f, %d cells per GPU, 7-type/4-leaf "
-                       "lineage tree, count sampling" % (n, EXPONENT, args.cells),
+    net = "TRRUST n=%d" % n if args.network == "trrust" else "SimulatedPowerLaw n=%d powerLawExponent=%.1f" % (n, EXPONENT)
+    cfg = {"workload": "c5: MatriSeq %s, %d cells per GPU, 7-type/4-leaf lineage tree, count sampling" % (net, args.cells),
            "genes": n, "nnz": nnz, "alpha": alpha, "cells_per_gpu": args.cells, "tree_parents": PARENTS,
-           "l2": "inputs exceed L2 (state %.1f GB per GPU)" % (args.cells * 3072 * 4 / 1e9)}
+           "l2": "inputs exceed L2 (state %.1f GB per GPU)" % (args.cells * (-(-n // 128) * 128) * 4 / 1e9)}
     if note:
         cfg["note"] = note
     return cfg
@@ -269,10 +275,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     comm = Comm(device=dev)
 
-    n = args.genes
     per_gpu = args.cells
     cells = per_gpu * world
-    gc, tf = build_network(n)
+    gc, tf = build_network(args.genes, args.network)
+    n = gc.shape[0]
     nnz = int(np.count_nonzero(gc))
     tree = build_tree(n, cells, tf)
     x0 = 2.0 * np.random.rand(n) - 1.0
