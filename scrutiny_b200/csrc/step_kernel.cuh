@@ -138,12 +138,20 @@ __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float rscal
   n_sin = r * sn;
 }
 
-// accurate tanh.  fp32: 1 - 2/(1+e^{2|z|}) with ex2/rcp approximations: absolute error ~2e-7,
-// which enters the state scaled by dt (DESIGN.md "Precision").  fp64: CUDA libm.
+// accurate tanh.  fp32: 1 - 2/(1+e^{2z}) with ex2/rcp approximations, evaluated on z itself (no |z| / copysign pair:
+// the form is exact in the limits -- ex2 -> +inf gives rcp -> 0 -> +1, ex2 -> 0 gives -1 -- and its absolute error is
+// ~2.5e-7 on either side, entering the state scaled by dt; DESIGN.md "Precision").  SCR_TANH_SYMMETRIC=1 restores the
+// odd-symmetric |z| form (one LOP3 more per element).  fp64: CUDA libm.
+#ifndef SCR_TANH_SYMMETRIC
+#define SCR_TANH_SYMMETRIC 0
+#endif
 __device__ __forceinline__ float tanh_acc(float z) {
-  const float e = ptx_ex2(fabsf(z) * 2.88539008177792681472f);  // 2*log2(e)
-  const float t = fmaf(-2.0f, ptx_rcp(e + 1.0f), 1.0f);
-  return copysignf(t, z);
+  if (SCR_TANH_SYMMETRIC) {
+    const float e = ptx_ex2(fabsf(z) * 2.88539008177792681472f);  // 2*log2(e)
+    return copysignf(fmaf(-2.0f, ptx_rcp(e + 1.0f), 1.0f), z);
+  }
+  const float e = ptx_ex2(z * 2.88539008177792681472f);
+  return fmaf(-2.0f, ptx_rcp(e + 1.0f), 1.0f);
 }
 __device__ __forceinline__ double tanh_acc(double z) { return tanh(z); }
 
@@ -194,13 +202,19 @@ __device__ __forceinline__ void box_muller_polar2(uint32_t wa0, uint32_t wb0, ui
 }
 // tanh of a pair (same formula as tanh_acc(float))
 __device__ __forceinline__ f32x2 tanh_acc2(f32x2 z) {
-  float m0, m1, z0, z1;
+  float m0, m1;
   upk2(mul2(z, pk2(2.88539008177792681472f, 2.88539008177792681472f)), m0, m1);
-  upk2(z, z0, z1);
   float s0, s1;
-  upk2(add2(pk2(ptx_ex2(fabsf(m0)), ptx_ex2(fabsf(m1))), pk2(1.0f, 1.0f)), s0, s1);
-  float t0, t1;
-  upk2(fma2(pk2(ptx_rcp(s0), ptx_rcp(s1)), pk2(-2.0f, -2.0f), pk2(1.0f, 1.0f)), t0, t1);
+  if (SCR_TANH_SYMMETRIC) {
+    upk2(add2(pk2(ptx_ex2(fabsf(m0)), ptx_ex2(fabsf(m1))), pk2(1.0f, 1.0f)), s0, s1);
+  } else {
+    upk2(add2(pk2(ptx_ex2(m0), ptx_ex2(m1)), pk2(1.0f, 1.0f)), s0, s1);
+  }
+  const f32x2 t = fma2(pk2(ptx_rcp(s0), ptx_rcp(s1)), pk2(-2.0f, -2.0f), pk2(1.0f, 1.0f));
+  if (!SCR_TANH_SYMMETRIC) return t;
+  float t0, t1, z0, z1;
+  upk2(t, t0, t1);
+  upk2(z, z0, z1);
   return pk2(copysignf(t0, z0), copysignf(t1, z1));
 }
 
