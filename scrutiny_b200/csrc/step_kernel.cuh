@@ -105,10 +105,12 @@ inline void make_round_keys(uint32_t k0, uint32_t k1, RoundKeys& rk) {
 #ifndef SCR_PHILOX_ROUNDS
 #define SCR_PHILOX_ROUNDS 10   // measurement builds only (profiles/r1_stepper_experiments.txt); every test assumes 10
 #endif
-__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                 const RoundKeys& rk, uint32_t (&out)[4]) {
+// rounds [R0, SCR_PHILOX_ROUNDS) on a state that has already been through rounds [0, R0)
+template <int R0>
+__device__ __forceinline__ void philox_rounds_from(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                   const RoundKeys& rk, uint32_t (&out)[4]) {
 #pragma unroll
-  for (int r = 0; r < SCR_PHILOX_ROUNDS; ++r) {
+  for (int r = R0; r < SCR_PHILOX_ROUNDS; ++r) {
     const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
     const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
     const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ rk.k[2 * r];
@@ -119,6 +121,23 @@ __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint3
     c2 = n2;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 const RoundKeys& rk, uint32_t (&out)[4]) {
+  philox_rounds_from<0>(c0, c1, c2, c3, rk, out);
+}
+// Per-cell invariants of round 0 for the stepper's counter layout (c0 = 32*block + lane, c1 = step, c2:c3 = global
+// cell id): the product with c2 and the XOR of c3 with the round key do not depend on block, lane or step, so they are
+// computed once per cell group (CellRound0 in shared memory) instead of once per 128-gene block.
+struct CellRound0 { uint32_t hi_p1_k0, lo_p1, c3_k1; };
+__device__ __forceinline__ CellRound0 philox_cell_round0(uint32_t gid_lo, uint32_t gid_hi, const RoundKeys& rk) {
+  const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * gid_lo;
+  return {static_cast<uint32_t>(p1 >> 32) ^ rk.k[0], static_cast<uint32_t>(p1), gid_hi ^ rk.k[1]};
+}
+// the same call as philox4x32_10_rk(c0, step, gid_lo, gid_hi): p0 = 0xD2511F53 * c0 is shared by the cells of a group
+__device__ __forceinline__ void philox4x32_10_cell(uint64_t p0, uint32_t step, uint32_t hi_p1_k0, uint32_t lo_p1,
+                                                   uint32_t c3_k1, const RoundKeys& rk, uint32_t (&out)[4]) {
+  philox_rounds_from<1>(hi_p1_k0 ^ step, lo_p1, static_cast<uint32_t>(p0 >> 32) ^ c3_k1, static_cast<uint32_t>(p0), rk, out);
 }
 
 // two N(0, sigma^2) values from two words: u1 = 2 - f(wa) in (0,1], theta = 2*pi*f(wb) - 3*pi,
@@ -391,6 +410,8 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   while (reg_end < my_b1 && wblk[reg_end] < p.npp_blocks) ++reg_end;
   uint32_t tg = 0;            // steps this group has completed so far (mbarrier phase counter)
   const bool has_bias = p.bias != nullptr;
+  constexpr bool kPacked = !PROBE && !SUPPLIED && SCR_PACKED_F32X2 && sizeof(T) == 4;
+  uint32_t* cell_r0 = reinterpret_cast<uint32_t*>(red);   // [3][4] words: CellRound0 per cell (`red` itself is PROBE-only)
 
   for (;;) {
     if (qtid == 0) ctrl[0] = atomicAdd(p.counter, 1);
@@ -398,6 +419,20 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
     const int item_idx = ctrl[0];
     if (item_idx >= p.nitems) break;
     const Item it = p.items[item_idx];
+
+    // per-cell Philox round-0 invariants (published by the barrier that ends the state load below)
+    if (kPacked) {
+#pragma unroll
+      for (int c = 0; c < CPG; ++c) {
+        if (qtid == c) {
+          const uint64_t gid = static_cast<uint64_t>(p.cell_offset + (it.cell[c] >= 0 ? it.cell[c] : 0));
+          const CellRound0 r0 = philox_cell_round0(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), p.rk);
+          cell_r0[c] = r0.hi_p1_k0;
+          cell_r0[4 + c] = r0.lo_p1;
+          cell_r0[8 + c] = r0.c3_k1;
+        }
+      }
+    }
 
     // ---- load the group's states: CPG cell rows -> interleaved x[gene][cell] ----
     for (int g0 = qtid * CPG; g0 < p.n_pad; g0 += qthreads * CPG) {
@@ -445,7 +480,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
     }
     const T wscale = PROBE ? static_cast<T>(it.scale) : T(1);
 
-    constexpr bool kPacked = !PROBE && !SUPPLIED && SCR_PACKED_F32X2 && sizeof(T) == 4;
+    uint32_t sctr[CPG];       // Philox counter word c1 of the current step: iterations done before this phase + s
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) sctr[c] = it.base[c];
     for (int s = 0; s < smax; ++s) {
       if (kSplit && s > 0) mbar_wait(bar_w, (tg - 1u) & 1u);   // all of cur is in place
       // -------- phase A: chunks of rows longer than the cap --------
@@ -562,15 +599,19 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         const uint32_t ctr0 = static_cast<uint32_t>(b * 32 + lane);
         if (kPacked && all_active) {
           uint32_t w[CPG][4];
+          const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * ctr0;
+          uint32_t hp[4], lp[4], ck[4];
+          *reinterpret_cast<uint4*>(hp) = *reinterpret_cast<const uint4*>(cell_r0);
+          *reinterpret_cast<uint4*>(lp) = *reinterpret_cast<const uint4*>(cell_r0 + 4);
+          *reinterpret_cast<uint4*>(ck) = *reinterpret_cast<const uint4*>(cell_r0 + 8);
 #pragma unroll
-          for (int c = 0; c < CPG; ++c)
-            philox4x32_10_rk(ctr0, it.base[c] + static_cast<uint32_t>(s), gid_lo[c], gid_hi[c], p.rk, w[c]);
+          for (int c = 0; c < CPG; ++c) philox4x32_10_cell(p0, sctr[c], hp[c % 4], lp[c % 4], ck[c % 4], p.rk, w[c]);
           fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
         } else if (all_active && !SUPPLIED) {
           uint32_t w[CPG][4];
 #pragma unroll
           for (int c = 0; c < CPG; ++c)
-            philox4x32_10_rk(ctr0, it.base[c] + static_cast<uint32_t>(s), gid_lo[c], gid_hi[c], p.rk, w[c]);
+            philox4x32_10_rk(ctr0, sctr[c], gid_lo[c], gid_hi[c], p.rk, w[c]);
 #pragma unroll
           for (int c = 0; c < CPG; ++c) {
             float r0, c0, s0, r1, c1, s1;
@@ -608,7 +649,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
                 for (int j = 0; j < 4; ++j) nz[j] = og[j] >= 0 ? p.noise[nbase + og[j]] : T(0);
               } else {
                 uint32_t w[4];
-                philox4x32_10_rk(ctr0, it.base[c] + static_cast<uint32_t>(s), gid_lo[c], gid_hi[c], p.rk, w);
+                philox4x32_10_rk(ctr0, sctr[c], gid_lo[c], gid_hi[c], p.rk, w);
                 box_muller_polar(w[0], w[1], p.rscale, rr[0], uu[0], uu[1]);
                 box_muller_polar(w[2], w[3], p.rscale, rr[2], uu[2], uu[3]);
                 rr[1] = rr[0];
@@ -661,6 +702,8 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         named_bar_sync(bar_id, qthreads);   // end of step: every new value is in place
       }
       { unsigned char* t = cur; cur = oth; oth = t; }
+#pragma unroll
+      for (int c = 0; c < CPG; ++c) ++sctr[c];
 
       if (PROBE) {
         if (qtid == 0) {
