@@ -133,7 +133,7 @@ int scr_debug_noise(scr_ctx* ctx, int64_t global_cell, uint32_t step, double sig
                     uint32_t stream, double* out /* n */);
 /* kernel launches issued by this context so far (bench.py reports gpu_launches) */
 int64_t scr_launch_count(const scr_ctx* ctx);
-/* launches of a specific stepper so far: which = 0 warp-specialised sparse stepper, 1 dense GEMM stepper */
+/* launches of a specific stepper so far: which = 0 persistent sparse stepper (phases), 1 dense GEMM stepper (steps) */
 int64_t scr_debug_path_launches(const scr_ctx* ctx, int which);
 /* device-time of the last scr_run_phase stepping kernel in milliseconds (CUDA events on the
  * context's stream); < 0 if none yet */

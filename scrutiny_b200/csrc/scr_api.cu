@@ -17,7 +17,6 @@
 #include "operator_pack.h"
 #include "regnet_kernels.cuh"
 #include "step_kernel.cuh"
-#include "step_kernel_ws.cuh"
 
 using scr::Item;
 using scr::PackedOperator;
@@ -56,7 +55,7 @@ struct scr_ctx {
   int *d_row_cell = nullptr, *d_row_steps = nullptr, *d_row_src = nullptr, *d_tile_steps = nullptr;
   uint32_t* d_row_base = nullptr;
   int64_t* d_row_gid = nullptr;
-  int64_t dense_launches = 0, ws_launches = 0;
+  int64_t dense_launches = 0, sparse_launches = 0;
 
   // cells
   void* d_state = nullptr;
@@ -138,13 +137,13 @@ void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std:
   w.assign(std::max(wtotal, 16), 0);
   for (size_t s = 0; s < nslots; ++s) {
     WEnt e{};
-    e.v = static_cast<T>(op.tile_val[s]);
+    e.v = static_cast<T>(op.tile_val[s] * scr::Traits<T>::kDriveScale);   // float32: drive carried as K z (step_kernel.cuh)
     e.off = op.tile_col[s] * 16;
     std::memcpy(w.data() + s * sizeof(WEnt), &e, sizeof(WEnt));
   }
   for (size_t s = 0; s < nch; ++s) {
     WEnt e{};
-    e.v = static_cast<T>(op.chunk_val[s]);
+    e.v = static_cast<T>(op.chunk_val[s] * scr::Traits<T>::kDriveScale);
     e.off = op.chunk_col[s] * 16;
     std::memcpy(w.data() + off_vrow + s * sizeof(WEnt), &e, sizeof(WEnt));
   }
@@ -256,58 +255,12 @@ int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_ms = ms;
-  if (!PROBE) { ctx->total_step_ms += ms; ctx->total_step_launches++; }
+  if (!PROBE) { ctx->total_step_ms += ms; ctx->total_step_launches++; ctx->sparse_launches++; }
   return SCR_OK;
-}
-
-// warp-specialised float32 stepper (step_kernel_ws.cuh): EXPERIMENT, opt-in with SCR_WS=1.  Measured
-// slower than the single-role kernel on B200 (131 vs 180 M cell-steps/s, power law n=3000): the update
-// warps are latency-bound per warp and the noise tiles squeeze L1 (operator hit rate 96 % -> 43 %);
-// see DESIGN.md 3.1 and profiles/r1_ws_experiment.txt
-int launch_step_ws(scr_ctx* ctx, scr::StepParams<float>& p, int nitems, bool* used) {
-  *used = false;
-  const int q = std::min(ctx->q, std::max(1, (nitems + ctx->sm_count - 1) / ctx->sm_count));
-  const int uwarps = q * ctx->op.wq;
-  const size_t smem = ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * ctx->gbytes +
-                      scr::ws_extra_smem(uwarps);
-  // setmaxnreg works on warp groups of 4: the update warps must be a multiple of 4 (noise warps mirror them)
-  if (uwarps % 4 != 0 || uwarps > 16 || smem > static_cast<size_t>(ctx->smem_optin) || scr::env_int("SCR_WS", 0) == 0) return SCR_OK;
-  p.q = q;
-  p.dbg = scr::env_int("SCR_WS_DEBUG", 0);
-  auto kern = ctx->w_smem ? scr::step_kernel_ws<true> : scr::step_kernel_ws<false>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int grid = std::max(1, std::min((nitems + q - 1) / q, ctx->sm_count));
-  CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-  CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  kern<<<grid, 2 * uwarps * 32, smem, ctx->stream>>>(p);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(ctx->ev1, ctx->stream));
-  ctx->launches++;
-  CK(cudaStreamSynchronize(ctx->stream));
-  float ms = 0.f;
-  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-  ctx->last_ms = ms;
-  ctx->total_step_ms += ms;
-  ctx->total_step_launches++;
-  ctx->ws_launches++;
-  *used = true;
-  return SCR_OK;
-}
-
-template <typename T>
-int launch_step_ws_if(scr_ctx*, scr::StepParams<T>&, int, bool* used) { *used = false; return SCR_OK; }
-template <>
-int launch_step_ws_if<float>(scr_ctx* ctx, scr::StepParams<float>& p, int nitems, bool* used) {
-  return launch_step_ws(ctx, p, nitems, used);
 }
 
 template <typename T>
 int launch_step(scr_ctx* ctx, scr::StepParams<T>& p, int nitems, bool probe, bool supplied) {
-  if (!probe && !supplied) {
-    bool used = false;
-    const int rc = launch_step_ws_if<T>(ctx, p, nitems, &used);
-    if (rc || used) return rc;
-  }
   if (probe) return supplied ? launch_step_t<T, true, true>(ctx, p, nitems) : launch_step_t<T, true, false>(ctx, p, nitems);
   return supplied ? launch_step_t<T, false, true>(ctx, p, nitems) : launch_step_t<T, false, false>(ctx, p, nitems);
 }
@@ -330,9 +283,10 @@ void fill_common(scr_ctx* ctx, scr::StepParams<T>& p) {
   p.perm = ctx->d_perm;
 }
 
-// proj/const (+mu) and the -mu*rowsum bias of one node, internal order
+// proj/const (+mu) and the -mu*rowsum bias of one node, internal order; drive_scale = Traits<T>::kDriveScale for the
+// sparse stepper (its drive is carried scaled), 1 for the GEMM stepper
 template <typename T>
-int upload_node(scr_ctx* ctx, const double* proj, const double* cnst, double mu, scr::StepParams<T>& p) {
+int upload_node(scr_ctx* ctx, const double* proj, const double* cnst, double mu, scr::StepParams<T>& p, double drive_scale) {
   const PackedOperator& op = ctx->op;
   std::vector<T> pc(static_cast<size_t>(op.n_pad) * 2, T(0));
   for (int i = 0; i < op.n; ++i) {
@@ -343,7 +297,7 @@ int upload_node(scr_ctx* ctx, const double* proj, const double* cnst, double mu,
   p.bias = nullptr;
   if (mu != 0.0) {
     std::vector<T> bias(op.n_pad, T(0));
-    for (int i = 0; i < op.n; ++i) bias[i] = static_cast<T>(-mu * op.rowsum[i]);
+    for (int i = 0; i < op.n; ++i) bias[i] = static_cast<T>(-mu * op.rowsum[i] * drive_scale);
     CK(cudaMemcpyAsync(ctx->d_bias, bias.data(), bias.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     p.bias = static_cast<const T*>(ctx->d_bias);
   }
@@ -457,12 +411,12 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
 
   scr::StepParams<T> p;
   fill_common(ctx, p);
-  rc = upload_node<T>(ctx, proj, cnst, mu, p);
+  rc = upload_node<T>(ctx, proj, cnst, mu, p, scr::Traits<T>::kDriveScale);
   if (rc) return rc;
   p.items = ctx->d_items;
   p.nitems = static_cast<int>(nitems);
   p.dt = static_cast<T>(dt);
-  p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma);
+  p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma * scr::Traits<T>::kDriveScale * scr::Traits<T>::kDriveScale);   // radius of K sigma xi
   scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_STEP), p.rk);
   T* d_noise = nullptr;
   if (noise) {
@@ -534,7 +488,7 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
 
   scr::StepParams<float> sp;           // reuse the node upload (proj/const/bias in identity order)
   fill_common(ctx, sp);
-  int rc = upload_node<float>(ctx, proj, cnst, mu, sp);
+  int rc = upload_node<float>(ctx, proj, cnst, mu, sp, 1.0);
   if (rc) return rc;
 
   CUtensorMap tm_a[2], tm_alo[2];
@@ -645,7 +599,7 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   CKP(cudaMemcpyAsync(d_gid, h_gid.data(), m_pad * 8, cudaMemcpyHostToDevice, ctx->stream));
   scr::StepParams<float> sp;
   fill_common(ctx, sp);
-  int rc = upload_node<float>(ctx, proj, cnst, mu, sp);
+  int rc = upload_node<float>(ctx, proj, cnst, mu, sp, 1.0);
   if (rc) { cleanup(); return rc; }
   CUtensorMap tm_a[2], tm_alo[2];
   for (int i = 0; i < 2; ++i) {
@@ -749,12 +703,12 @@ int probe_t(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_
 
   scr::StepParams<T> p;
   fill_common(ctx, p);
-  rc = upload_node<T>(ctx, proj, cnst, mu, p);
+  rc = upload_node<T>(ctx, proj, cnst, mu, p, scr::Traits<T>::kDriveScale);
   if (rc) return rc;
   p.items = ctx->d_items;
   p.nitems = nitems;
   p.dt = static_cast<T>(dt);
-  p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma);
+  p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma * scr::Traits<T>::kDriveScale * scr::Traits<T>::kDriveScale);   // radius of K sigma xi
   scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ stream, p.rk);
   p.thresh = thresh;
   p.max_iter = max_iter;
@@ -1251,7 +1205,7 @@ int scr_debug_noise(scr_ctx* ctx, int64_t global_cell, uint32_t step, double sig
 int64_t scr_launch_count(const scr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int64_t scr_debug_path_launches(const scr_ctx* ctx, int which) {
   if (!ctx) return 0;
-  return which == 0 ? ctx->ws_launches : ctx->dense_launches;
+  return which == 0 ? ctx->sparse_launches : ctx->dense_launches;
 }
 double scr_last_kernel_ms(const scr_ctx* ctx) { return ctx ? ctx->last_ms : -1.0; }
 int scr_step_kernel_stats(scr_ctx* ctx, double* total_ms, int64_t* launches, int reset) {

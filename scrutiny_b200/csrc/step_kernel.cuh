@@ -179,6 +179,25 @@ __device__ __forceinline__ double tanh_acc(double z) { return tanh(z); }
 __device__ __forceinline__ float add_noise(float drive, float r, float u) { return fmaf(r, u, drive); }
 __device__ __forceinline__ double add_noise(double drive, float r, float u) { return drive + static_cast<double>(r * u); }
 
+// One element of developCell (MS:529-535): x' = proj * (x + dt (tanh z - x)) + const.
+// fp32: with r = 1/(1 + 2^m), m = K z, tanh z = 1 - 2 r and the Euler blend folds into two FMAs,
+//   x + dt (tanh z - x) = fma(r, -2 dt, fma(x, 1 - dt, dt)),
+// the second of which does not wait for the MUFU chain.  Exact in the limits (2^m -> inf gives r -> 0, 2^m -> 0 gives
+// r = 1); absolute error of the tanh part ~2.5e-7 on either side, entering the state scaled by dt (DESIGN.md
+// "Precision").  Every float32 path of the sparse stepper (packed fast path, ragged tail, probe, supplied noise) goes
+// through this one formula, so results do not depend on how cells are grouped.
+__device__ __forceinline__ float next_state(float m, float x, float dt, float proj, float cnst) {
+  const float r = ptx_rcp(ptx_ex2(m) + 1.0f);
+  return fmaf(proj, fmaf(r, -2.0f * dt, fmaf(x, 1.0f - dt, dt)), cnst);
+}
+// fp64: libm tanh on the unscaled drive, the reference's order of operations
+__device__ __forceinline__ double next_state(double z, double x, double dt, double proj, double cnst) {
+  return fma(proj, fma(dt, tanh(z) - x, x), cnst);
+}
+// supplied noise arrives in the reference's units: scale it like the drive
+__device__ __forceinline__ float add_supplied(float drive, float nz) { return fmaf(nz, 2.88539008177792681472f, drive); }
+__device__ __forceinline__ double add_supplied(double drive, double nz) { return drive + nz; }
+
 
 // ------------------------------------------------------------------------------------------
 // packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2): one issue slot, two IEEE fp32 results,
@@ -219,35 +238,21 @@ __device__ __forceinline__ void box_muller_polar2(uint32_t wa0, uint32_t wb0, ui
   c = pk2(ptx_cos(h0), ptx_cos(h1));
   sn = pk2(ptx_sin(h0), ptx_sin(h1));
 }
-// tanh of a pair (same formula as tanh_acc(float))
-__device__ __forceinline__ f32x2 tanh_acc2(f32x2 z) {
-  float m0, m1;
-  upk2(mul2(z, pk2(2.88539008177792681472f, 2.88539008177792681472f)), m0, m1);
-  float s0, s1;
-  if (SCR_TANH_SYMMETRIC) {
-    upk2(add2(pk2(ptx_ex2(fabsf(m0)), ptx_ex2(fabsf(m1))), pk2(1.0f, 1.0f)), s0, s1);
-  } else {
-    upk2(add2(pk2(ptx_ex2(m0), ptx_ex2(m1)), pk2(1.0f, 1.0f)), s0, s1);
-  }
-  const f32x2 t = fma2(pk2(ptx_rcp(s0), ptx_rcp(s1)), pk2(-2.0f, -2.0f), pk2(1.0f, 1.0f));
-  if (!SCR_TANH_SYMMETRIC) return t;
-  float t0, t1, z0, z1;
-  upk2(t, t0, t1);
-  upk2(z, z0, z1);
-  return pk2(copysignf(t0, z0), copysignf(t1, z1));
-}
-
 // ------------------------------------------------------------------------------------------
 // types
 // ------------------------------------------------------------------------------------------
 template <typename T> struct Traits;
 template <> struct Traits<float> {
   static constexpr int CPG = 4;
+  // the float32 stepper carries the drive as m = K z, K = 2 log2(e), the argument of ex2 in tanh z = 1 - 2/(1 + 2^m):
+  // operator entries, the mean-level bias and the noise radius are scaled by K on the host (scr_api.cu)
+  static constexpr double kDriveScale = 2.88539008177792681472;
   struct __align__(8) WEnt { float v; int off; };
   using PC = float2;
 };
 template <> struct Traits<double> {
   static constexpr int CPG = 2;
+  static constexpr double kDriveScale = 1.0;
   struct __align__(16) WEnt { double v; int off; int pad; };
   using PC = double2;
 };
@@ -295,14 +300,16 @@ template <typename T> struct StepParams {
   int max_iter, avg_num;
   int* iters_out;
   double* nd;                 // [k][max_iter]
-  int dbg;                    // developer timing experiments only (SCR_WS_DEBUG): 1 = skip noise generation, 2 = skip update
 };
 
 
-// element-wise update of one 128-gene block for a fully active group of 4 float cells, packed fp32x2
+// element-wise update of one 128-gene block for a fully active group of 4 float cells, packed fp32x2: next_state()
+// on cell pairs, instruction for instruction (FFMA2 / FADD2 are per-lane IEEE, so the results are bit-identical)
 __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&w)[4][4], float rscale, float dt, const float (&acc)[4][4],
                                                   Row<float> (&xo)[4], const float2 (&pcv)[4]) {
-  const f32x2 rscale2 = pk2(rscale, rscale), dt2 = pk2(dt, dt), neg1 = pk2(-1.0f, -1.0f);
+  const float omdt = 1.0f - dt, m2dt = -2.0f * dt;
+  const f32x2 rscale2 = pk2(rscale, rscale), dt2 = pk2(dt, dt), omdt2 = pk2(omdt, omdt), m2dt2 = pk2(m2dt, m2dt);
+  const f32x2 one2 = pk2(1.0f, 1.0f);
 #pragma unroll
   for (int pr = 0; pr < 2; ++pr) {          // cell pairs (0,1) and (2,3)
     const int c0 = 2 * pr, c1 = 2 * pr + 1;
@@ -313,14 +320,12 @@ __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&w)[4][4], flo
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = 2 * h + e;
-        const f32x2 z = fma2(r, e == 0 ? cs : sn, pk2(acc[j][c0], acc[j][c1]));
-        const f32x2 t = tanh_acc2(z);
-        const f32x2 x = pk2(xo[j].v[c0], xo[j].v[c1]);
-        const f32x2 x1 = fma2(dt2, fma2(x, neg1, t), x);                       // x + dt (t - x)
-        float a, b;
-        upk2(fma2(pk2(pcv[j].x, pcv[j].x), x1, pk2(pcv[j].y, pcv[j].y)), a, b);
-        xo[j].v[c0] = a;
-        xo[j].v[c1] = b;
+        float m0, m1, s0, s1;
+        upk2(fma2(r, e == 0 ? cs : sn, pk2(acc[j][c0], acc[j][c1])), m0, m1);          // m = K (W x) + K sigma xi
+        upk2(add2(pk2(ptx_ex2(m0), ptx_ex2(m1)), one2), s0, s1);
+        const f32x2 u = fma2(pk2(xo[j].v[c0], xo[j].v[c1]), omdt2, dt2);               // (1 - dt) x + dt
+        const f32x2 v = fma2(pk2(ptx_rcp(s0), ptx_rcp(s1)), m2dt2, u);                 // ... - 2 dt / (1 + 2^m)
+        upk2(fma2(pk2(pcv[j].x, pcv[j].x), v, pk2(pcv[j].y, pcv[j].y)), xo[j].v[c0], xo[j].v[c1]);
       }
     }
   }
@@ -624,9 +629,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
               const T x = xo[j].v[c];
               T drive = acc[j][c];
               if (PROBE) drive *= wscale;
-              const T t = tanh_acc(add_noise(drive, rr[j], uu[j]));
-              const T x1 = fma(p.dt, t - x, x);
-              const T xn = fma(pcv[j].x, x1, pcv[j].y);
+              const T xn = next_state(add_noise(drive, rr[j], uu[j]), x, p.dt, pcv[j].x, pcv[j].y);
               if (PROBE) dsum[c] += fabs(xn - x);
               xo[j].v[c] = xn;
             }
@@ -660,10 +663,8 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
                 const T x = xo[j].v[c];
                 T drive = acc[j][c];
                 if (PROBE) drive *= wscale;
-                const T z = SUPPLIED ? drive + nz[j] : add_noise(drive, rr[j], uu[j]);
-                const T t = tanh_acc(z);
-                const T x1 = fma(p.dt, t - x, x);
-                const T xn = fma(pcv[j].x, x1, pcv[j].y);
+                const T z = SUPPLIED ? add_supplied(drive, nz[j]) : add_noise(drive, rr[j], uu[j]);
+                const T xn = next_state(z, x, p.dt, pcv[j].x, pcv[j].y);
                 if (PROBE) dsum[c] += fabs(xn - x);
                 xo[j].v[c] = xn;
               }

@@ -230,7 +230,7 @@ class Engine:
         return int(self._lib.scr_launch_count(self._ctx))
 
     def path_launches(self):
-        return {"warp_specialised": int(self._lib.scr_debug_path_launches(self._ctx, 0)),
+        return {"sparse_persistent": int(self._lib.scr_debug_path_launches(self._ctx, 0)),
                 "dense_gemm": int(self._lib.scr_debug_path_launches(self._ctx, 1))}
 
     def step_kernel_stats(self, reset=False):

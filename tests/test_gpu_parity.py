@@ -455,41 +455,6 @@ def test_counts_uniform_exhaustion_is_an_error(eng_mod):
     assert err.value.code == -5
 
 
-def test_warp_specialised_stepper_matches_single_role_kernel_and_oracle(eng_mod):
-    """The warp-specialised float32 stepper (noise warps feeding update warps through shared memory)
-    must draw exactly the documented noise: compare with the single-role kernel (SCR_WS=0) and with
-    the float64 oracle fed the dumped noise.  Ragged steps, > 148 groups so both CTA shapes occur."""
-    import os
-    n, seed = 1100, 424242
-    W = sparse_net(n, 77, gain=4.0)
-    rng = np.random.RandomState(9)
-    for cells, smax in ((40, 12), (1300, 6)):
-        X0 = rng.uniform(-1, 1, size=(cells, n)).astype(np.float32).astype(np.float64)
-        steps = rng.randint(0, smax + 1, size=cells)
-        steps[:4] = smax
-        base = rng.randint(0, 100, size=cells)
-        outs = []
-        for ws in ("1", "0"):
-            os.environ["SCR_WS"] = ws
-            try:
-                e = make_engine(eng_mod, "f32", W, cells, offset=5000)
-                e.set_states(X0.T.copy())
-                e.run_phase(np.arange(cells), steps, np.ones(n), np.zeros(n), step_base=base, seed=seed, mu=0.05)
-            finally:
-                del os.environ["SCR_WS"]
-            assert (e.path_launches()["warp_specialised"] > 0) == (ws == "1")   # opt-in experiment, default off
-            outs.append(e.get_states())
-        assert np.max(np.abs(outs[0] - outs[1])) <= 2e-5
-        if cells <= 64:
-            dump = np.zeros((cells, smax, n))
-            for c in range(cells):
-                for s in range(int(steps[c])):
-                    dump[c, s] = e.debug_noise(5000 + c, base[c] + s, 0.05, seed)
-            want = X0.copy()
-            fo.run_phase(fo.as_operator(W), want, steps, np.ones(n), np.zeros(n), 0.01, dump, mu=0.05)
-            assert np.max(np.abs(outs[0].T - want)) <= 1e-4
-
-
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 def test_partly_resident_operator_is_bit_identical(eng_mod, prec):
     """When the operator does not fit in shared memory next to the cell groups, its head is staged there and the
