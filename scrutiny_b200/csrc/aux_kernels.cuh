@@ -119,14 +119,44 @@ __device__ inline int poisson_draw(double lam, UniformSource& u) {
   return static_cast<int>(lam);
 }
 
+// Float32 screening of the multiplication method (lambda < 10), EXACT by construction: the same Philox words, the same
+// draw order, but product and threshold carried in float32 with a guard band.  With eps = 2^-24:
+//   lambda_f = ex2(t2) * size  (t2 = log2(e) * expScale * (x + shift) rounded to float32, |t2| < 64, size in [0.05, 8]):
+//              |lambda_f - lambda| <= lambda (2^-22 + 2 eps) + lambda |t2| eps ln 2 <= 6.8e-6 for lambda < 10;
+//   enlam_f  = ex2(-log2(e) lambda_f): relative error <= 6.8e-6 + 14.5 * 2 eps * ln 2 + 2^-22 <= 8e-6;
+//   prod_f   : each uniform (v + 1/2) / 2^32 is one I2F and one FMA (2 eps), each multiply eps: <= 64 * 3 eps = 1.2e-5
+// so prod_f and enlam_f together are within 2e-5 of the float64 quantities the exact sampler compares; a comparison
+// is taken only when prod_f lies outside enlam_f (1 +- 1e-4), otherwise (about 2e-4 of the entries, or any input outside
+// the ranges above) -1 is returned and the caller runs the float64 sampler from the first uniform again.
+// tests/test_counts_guard.py checks the bound on the host; the GPU suite compares both paths entry for entry.
+__device__ __forceinline__ int poisson_small_f32(float lam_f, uint32_t gene, uint64_t gid, const RoundKeys& rk) {
+  const float enlam = ptx_ex2(lam_f * -1.44269504088896340736f);
+  const float hi = enlam * (1.0f + 1e-4f), lo = enlam * (1.0f - 1e-4f);
+  float prod = 1.0f;
+  int k = 0;
+  for (uint32_t call = 0; call < 16; ++call) {   // 64 uniforms: P(Poisson(10) >= 64) < 1e-28
+    uint32_t w[4];
+    philox4x32_10_rk(gene, call, static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), rk, w);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      prod *= fmaf(__uint2float_rn(w[j]), 2.3283064365386963e-10f, 1.16415321826934814e-10f);   // (v + 1/2) / 2^32
+      if (prod > hi) ++k;
+      else return prod < lo ? k : -1;
+    }
+  }
+  return -1;
+}
+
 // one CTA per cell of the chunk.  Thread t handles gene `order[t]`, where `order` sorts the genes by
 // their shift (the dominant term of log lambda): the 32 lanes of a warp then see similar lambda and leave
 // the sampler's loops together instead of waiting for the largest one.  Counts are staged in shared
 // memory and written as one coalesced int32 row in the caller's gene order.
+// FAST (free-running Philox stream, no lambda dump): entries with lambda < 10 go through poisson_small_f32 first and
+// fall back to the float64 sampler only when it declines; results are identical to FAST = false.
 #ifndef SCR_COUNTS_CTAS_PER_SM
 #define SCR_COUNTS_CTAS_PER_SM 4   // 64 registers: the sampler is latency-bound (dependent FP64 chains), more warps pay (2 / 3 / 4 CTAs: 28.8 / 22.5 / 21.5 ms at 400k cells)
 #endif
-template <typename T>
+template <typename T, bool FAST>
 __global__ void __launch_bounds__(256, SCR_COUNTS_CTAS_PER_SM)
 counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ inv,
                               const int* __restrict__ order, int n, int64_t cell0, const double* __restrict__ shift,
@@ -138,23 +168,37 @@ counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ i
   const uint64_t gid = static_cast<uint64_t>(cell_offset + c);
   const double sf = sizef[c];
   const T* row = state + c * ld;
+  const bool sf_ok = FAST && sf >= 0.05 && sf <= 8.0;
+  const float sf_f = static_cast<float>(sf);
+  const double esl = exp_scale * 1.4426950408889634;
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     const int o = order[t];
     const double x = static_cast<double>(row[inv[o]]);
-    double lam = exp(exp_scale * (x + shift[o])) * sf;
-    if (lam < 0.0) lam = 0.0;
-    UniformSource u;
-    u.supplied = uniforms;
-    u.sup_base = (c * n + o) * static_cast<int64_t>(draws);
-    u.sup_count = draws;
-    u.used = 0;
-    u.c0 = static_cast<uint32_t>(o);
-    u.c2 = static_cast<uint32_t>(gid);
-    u.c3 = static_cast<uint32_t>(gid >> 32);
-    u.rk = &rk; u.call = 0; u.have = 0; u.err = err;
-    u.w0 = u.w1 = u.w2 = u.w3 = 0;
-    s_counts[o] = poisson_draw(lam, u);
-    if (lam_out) lam_out[static_cast<int64_t>(blockIdx.x) * n + o] = lam;
+    int cnt = -1;
+    if (FAST && sf_ok) {
+      const float t2 = static_cast<float>((x + shift[o]) * esl);
+      if (t2 > -64.0f && t2 < 8.0f) {
+        const float lam_f = ptx_ex2(t2) * sf_f;
+        if (lam_f < 9.999f) cnt = poisson_small_f32(lam_f, static_cast<uint32_t>(o), gid, rk);
+      }
+    }
+    if (cnt < 0) {
+      double lam = exp(exp_scale * (x + shift[o])) * sf;
+      if (lam < 0.0) lam = 0.0;
+      UniformSource u;
+      u.supplied = uniforms;
+      u.sup_base = (c * n + o) * static_cast<int64_t>(draws);
+      u.sup_count = draws;
+      u.used = 0;
+      u.c0 = static_cast<uint32_t>(o);
+      u.c2 = static_cast<uint32_t>(gid);
+      u.c3 = static_cast<uint32_t>(gid >> 32);
+      u.rk = &rk; u.call = 0; u.have = 0; u.err = err;
+      u.w0 = u.w1 = u.w2 = u.w3 = 0;
+      cnt = poisson_draw(lam, u);
+      if (lam_out) lam_out[static_cast<int64_t>(blockIdx.x) * n + o] = lam;
+    }
+    s_counts[o] = cnt;
   }
   __syncthreads();
   int32_t* orow = out + static_cast<int64_t>(blockIdx.x) * n;

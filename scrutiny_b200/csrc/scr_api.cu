@@ -1111,12 +1111,18 @@ int scr_counts_range(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const
   scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_COUNTS), crk);
   // the kernel indexes size factors and supplied uniforms by local cell slot: rebase the range's buffers
   const double* size_by_slot = d_size - cell_begin;
+  // free-running stream without a lambda dump: float32 screening of the lambda < 10 sampler (identical integers,
+  // aux_kernels.cuh); SCR_COUNTS_EXACT=1 forces the float64 sampler for every entry (A/B tests)
+  const bool fast = !uniforms && !lambda_out && scr::env_int("SCR_COUNTS_EXACT", 0) == 0;
   auto launch = [&](int64_t c0, int64_t cnt, int32_t* out, double* lam) -> cudaError_t {
     const double* uni_by_slot = d_uni ? d_uni - cell_begin * n * static_cast<int64_t>(draws_per_entry) : nullptr;
-    if (ctx->prec == SCR_F64)
-      scr::counts_kernel<double><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const double*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, cell_begin + c0, d_shift, exp_scale, size_by_slot, crk, ctx->cell_offset, uni_by_slot, draws_per_entry, out, lam, ctx->d_err);
-    else
-      scr::counts_kernel<float><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>(static_cast<const float*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, cell_begin + c0, d_shift, exp_scale, size_by_slot, crk, ctx->cell_offset, uni_by_slot, draws_per_entry, out, lam, ctx->d_err);
+#define SCR_LAUNCH_COUNTS(T, FAST) \
+    scr::counts_kernel<T, FAST><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>( \
+        static_cast<const T*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, cell_begin + c0, d_shift, exp_scale, \
+        size_by_slot, crk, ctx->cell_offset, uni_by_slot, draws_per_entry, out, lam, ctx->d_err)
+    if (ctx->prec == SCR_F64) { if (fast) SCR_LAUNCH_COUNTS(double, true); else SCR_LAUNCH_COUNTS(double, false); }
+    else                      { if (fast) SCR_LAUNCH_COUNTS(float, true);  else SCR_LAUNCH_COUNTS(float, false); }
+#undef SCR_LAUNCH_COUNTS
     ctx->launches++;
     return cudaGetLastError();
   };

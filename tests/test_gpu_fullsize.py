@@ -124,3 +124,13 @@ def test_count_readout_moments_at_scale(big):
     rel = np.abs(got.sum(axis=1)[big_genes] - mass[big_genes]) / np.sqrt(mass[big_genes])
     assert rel.max() < 6.0, rel.max()                                    # Poisson: sd of the sum = sqrt(mass)
     assert abs((got == 0).mean() - np.exp(-lam).mean()) < 0.005          # zero fraction = E[exp(-lambda)]
+    # the float32-screened sampler (default) and the float64 sampler alone give the same 3e8 integers
+    import os
+    os.environ["SCR_COUNTS_EXACT"] = "1"
+    try:
+        ref = torch.empty((cells, n), dtype=torch.int32, device="cuda:0")
+        e.counts(shift, size, seed=9, out_device_ptr=ref.data_ptr())
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["SCR_COUNTS_EXACT"]
+    assert torch.equal(buf, ref)

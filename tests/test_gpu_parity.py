@@ -416,6 +416,36 @@ def test_counts_float32_context_and_statistics(eng_mod):
     assert np.array_equal(buf.cpu().numpy(), got)
 
 
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_counts_float32_screening_equals_float64_sampler(eng_mod, prec):
+    """The free-running read-out screens lambda < 10 entries in float32 with a guard band (aux_kernels.cuh,
+    poisson_small_f32) and redoes everything it cannot decide in float64: the integers must be those of the float64
+    sampler alone (forced by a lambda dump or SCR_COUNTS_EXACT=1) entry for entry -- lambda from 1e-12 to 200, size
+    factors inside and outside the screened range, 2 M entries (~400 of them land in the guard band)."""
+    import os
+    n, cells = 512, 4000
+    rng = np.random.RandomState(29)
+    e = make_engine(eng_mod, prec, sparse_net(n, 91), cells, offset=2 ** 33 + 5)        # cell ids beyond 32 bits
+    e.set_states(np.tanh(rng.randn(n, cells)))
+    shift = np.concatenate([np.log(rng.gamma(0.35, 1 / 0.19, size=n - 64)), np.linspace(-28, 5.3, 64)])[rng.permutation(n)]
+    size = rng.normal(1, 0.14, size=cells) ** 3
+    size[:8] = [0.01, 0.049, 0.051, 7.9, 8.1, -0.2, 0.0, 30.0]
+    exact, lam = e.counts(shift, size, seed=41, want_lambda=True)
+    fast = e.counts(shift, size, seed=41)
+    assert np.array_equal(fast, exact)
+    os.environ["SCR_COUNTS_EXACT"] = "1"
+    try:
+        forced = e.counts(shift, size, seed=41)
+    finally:
+        del os.environ["SCR_COUNTS_EXACT"]
+    assert np.array_equal(forced, exact)
+    assert ((lam > 0) & (lam < 1e-6)).sum() > 1000 and ((lam > 5) & (lam < 10)).sum() > 10000 and (lam >= 10).sum() > 10000
+    assert (exact[5] == 0).all() and (exact[6] == 0).all()
+    other = e.counts(shift, size, seed=42, exp_scale=0.7)
+    exact_other = e.counts(shift, size, seed=42, exp_scale=0.7, want_lambda=True)[0]
+    assert np.array_equal(other, exact_other) and not np.array_equal(other, fast)
+
+
 def test_counts_by_row_blocks_equal_one_call(eng_mod):
     """scr_counts_range: sampling the matrix in ragged row blocks (host and device output, Philox and supplied
     uniforms, lambda dump) gives exactly the integers of one call over all cells; bad ranges are refused."""
