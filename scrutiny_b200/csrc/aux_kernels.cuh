@@ -101,7 +101,7 @@ __device__ inline int poisson_draw(double lam, UniformSource& u) {
       if (k > 100000) return k;   // unreachable for lam < 10 unless the uniforms are degenerate
     }
   }
-  const double slam = sqrt(lam), loglam = log(lam);
+  const double slam = sqrt(lam);   // log(lam) is only needed by the full acceptance test (~1 draw in 8): formed there
   const double b = 0.931 + 2.53 * slam;
   const double a = -0.059 + 0.02483 * b;
   const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
@@ -113,7 +113,7 @@ __device__ inline int poisson_draw(double lam, UniformSource& u) {
     const double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
     if (us >= 0.07 && V <= vr) return static_cast<int>(kf);
     if (kf < 0.0 || (us < 0.013 && V > us)) continue;
-    if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-lam + kf * loglam - lgamma(kf + 1.0)))
+    if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-lam + kf * log(lam) - lgamma(kf + 1.0)))
       return static_cast<int>(kf);
   }
   return static_cast<int>(lam);
