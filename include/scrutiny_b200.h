@@ -112,7 +112,10 @@ int scr_gene_sums(scr_ctx* ctx, double* sums_out /* n */);
  *   uniforms NULL -> Philox uniforms keyed (seed, global cell, gene, draw);
  *            else float64 (cells, n, draws_per_entry) consumed in order per entry.
  *   counts_out: int32 (cells, n) row-major, host or device memory (out_on_device);
- *   lambda_out: float64 (cells, n) HOST buffer or NULL (parity aid). */
+ *   lambda_out: float64 (cells, n) HOST buffer or NULL (parity aid).
+ *   With Philox uniforms and no lambda_out, entries with lambda < 10 are first screened in float32 with a guard band
+ *   and redone by the float64 sampler when undecided: the integers are those of the float64 sampler in every case
+ *   (environment SCR_COUNTS_EXACT=1 switches the screening off, for A/B tests). */
 int scr_counts(scr_ctx* ctx, const double* shift /* n */, double exp_scale,
                const double* size_factors /* cells */, uint64_t seed, const double* uniforms,
                int32_t draws_per_entry, int32_t* counts_out, int out_on_device, double* lambda_out);

@@ -49,12 +49,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 // try_wait suspends the thread in hardware until the phase completes or the hint (ns) elapses; without
 // the hint the default limit is short and the loop below spins, stealing issue slots from other warps
+#ifndef SCR_TRYWAIT_HINT
+#define SCR_TRYWAIT_HINT 1   // 0: try_wait without a suspend-time hint (A/B measurement)
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if SCR_TRYWAIT_HINT
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -213,6 +223,9 @@ __device__ __forceinline__ double add_supplied(double drive, double nz) { return
 #ifndef SCR_CHUNK_UNROLL
 #define SCR_CHUNK_UNROLL 1    // long-row chunks of the default length (8) are evaluated with all loads in flight
 #endif
+#ifndef SCR_CHUNK_ARRIVE_ALL
+#define SCR_CHUNK_ARRIVE_ALL 0   // 1: every warp of the group arrives on the chunk barrier (the earlier behaviour)
+#endif
 #ifndef SCR_CHUNK_SPREAD
 #define SCR_CHUNK_SPREAD 0    // experiment: chunk v evaluated by lane v / wq of warp v % wq (measured slower)
 #endif
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
     uint64_t* b0 = reinterpret_cast<uint64_t*>(g0 + static_cast<size_t>(p.n_pad + p.npp + p.nv_pad + 8) * 16 + 16);
     mbar_init(b0, p.wq);
     mbar_init(b0 + 1, p.wq);
-    mbar_init(b0 + 2, p.wq);
+    mbar_init(b0 + 2, (SCR_CHUNK_ARRIVE_ALL || SCR_CHUNK_SPREAD) ? p.wq : max(1, min(p.wq, p.nv_pad / 32)));   // bar_a: one arrival per chunk-evaluating warp
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -526,8 +539,12 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           ovf[v] = o;
         }
         if (kSplit) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_a);
+          // only the warps that evaluate chunks (the first nv_pad / 32 of the group) arrive: fewer mbarrier events, and
+          // every arrival wakes the warps suspended in a try_wait
+          if (SCR_CHUNK_ARRIVE_ALL || SCR_CHUNK_SPREAD || wq * 32 < p.nv_pad) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a);
+          }
         } else {
           named_bar_sync(bar_id, qthreads);
         }
