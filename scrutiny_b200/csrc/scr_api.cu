@@ -116,20 +116,34 @@ template <typename T>
 void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std::vector<unsigned char>& w,
                  int& off_slice, int& off_ovfidx, int& off_wblk_ptr, int& off_wblk, int& off_vrow) {
   using WEnt = typename scr::Traits<T>::WEnt;
-  const int nslices = op.nb;   // one offset per 128-gene block
+  // fixed part (step_kernel.cuh "Shared-memory layout"): block records in the order of the warps' lists, list bounds;
+  // variable part: chunk ranges of the long rows
   off_slice = 0;
-  off_ovfidx = align16(off_slice + (nslices + 1) * 4);
-  off_wblk_ptr = align16(off_ovfidx + static_cast<int>(op.ovf_start.size()) * 8);
-  off_wblk = align16(off_wblk_ptr + (op.wq + 1) * 4);
-  const int total = align16(off_wblk + static_cast<int>(op.wblk.size()) * 4);
-  tab.assign(std::max(total, 16), 0);
-  std::memcpy(tab.data() + off_slice, op.slice_off.data(), (nslices + 1) * 4);
+  off_wblk = 0;
+  off_wblk_ptr = scr::kRecBytes;
+  off_ovfidx = scr::kFixedTab;
+  const int total = align16(off_ovfidx + static_cast<int>(op.ovf_start.size()) * 8);
+  tab.assign(total, 0);
+  for (int w = 0; w < op.wq; ++w) {
+    int reg_end = op.wblk_ptr[w];
+    while (reg_end < op.wblk_ptr[w + 1] && op.wblk[reg_end] < op.npp_blocks) ++reg_end;
+    for (int bi = op.wblk_ptr[w]; bi < op.wblk_ptr[w + 1]; ++bi) {
+      const int b = op.wblk[bi];
+      const bool pp = b < op.npp_blocks;
+      int flags = 0;
+      if (pp) flags |= scr::kBlkPP;
+      if (b < op.nlong_blocks) flags |= scr::kBlkLong;
+      if (bi == reg_end - 1) flags |= scr::kBlkLastReg;
+      if (bi == op.wblk_ptr[w] && pp) flags |= scr::kBlkFirstPP;
+      const int4 rec = make_int4(b * 128, op.slice_off[b], op.slice_off[b + 1], flags);
+      std::memcpy(tab.data() + static_cast<size_t>(bi) * 16, &rec, 16);
+    }
+  }
   for (size_t i = 0; i < op.ovf_start.size(); ++i) {
     int2 v = make_int2(op.ovf_start[i], op.ovf_cnt[i]);
     std::memcpy(tab.data() + off_ovfidx + i * 8, &v, 8);
   }
   std::memcpy(tab.data() + off_wblk_ptr, op.wblk_ptr.data(), (op.wq + 1) * 4);
-  if (!op.wblk.empty()) std::memcpy(tab.data() + off_wblk, op.wblk.data(), op.wblk.size() * 4);
 
   const size_t nslots = op.tile_val.size(), nch = op.chunk_val.size();
   off_vrow = align16(static_cast<int>(nslots * sizeof(WEnt)));
@@ -855,6 +869,7 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
   // the gene order must not change under allocated cells (alpha rescaling keeps the pattern, hence the order)
   if (ctx->cells > 0 && ctx->has_net && op.perm != ctx->op.perm)
     return fail(ctx, SCR_E_STATE, "network pattern changed while cells are allocated");
+  if (op.nb > scr::kMaxBlocks) return fail(ctx, SCR_E_RESOURCE, "n too large: one cell group does not fit in shared memory");
   std::vector<unsigned char> tab, w;
   if (ctx->prec == SCR_F64) build_blobs<double>(op, tab, w, ctx->off_slice, ctx->off_ovfidx, ctx->off_wblk_ptr, ctx->off_wblk, ctx->off_vrow);
   else build_blobs<float>(op, tab, w, ctx->off_slice, ctx->off_ovfidx, ctx->off_wblk_ptr, ctx->off_wblk, ctx->off_vrow);

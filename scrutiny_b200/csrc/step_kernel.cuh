@@ -74,6 +74,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// 128-bit load from a shared-space address (LDS.128 with the table offset folded into the immediate)
+__device__ __forceinline__ int4 lds_i4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -347,8 +353,23 @@ __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&w)[4][4], flo
 __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&)[2][4], float, double, const double (&)[4][2],
                                                   Row<double> (&)[4], const double2 (&)[4]) {}
 
+// Shared-memory layout of a CTA (byte offsets from the start of dynamic shared memory):
+//   [0, kRecBytes)                   BlockRec table: one 16-byte record per entry of the warps' block lists
+//   [kRecBytes, kFixedTab)           wblk_ptr: list bounds per warp of a group
+//   [kFixedTab, + n_pad * PC)        proj/const pairs of the node           (compile-time start: LDS [reg + imm])
+//   then ovfidx (long-row chunk ranges), the staged head of the operator, and the cell groups:
+//   group = [kGroupHdr: ctrl words, three mbarriers, CellRound0 words, probe partials][bufA][bufB][chunk partials]
+// The tables a 128-gene block needs sit at compile-time offsets so that their addresses cost no instructions.
+constexpr int kMaxBlocks = 128;                 // n_pad <= 16384 (a cell group of that size cannot fit an SM anyway)
+constexpr int kRecBytes = kMaxBlocks * 16;
+constexpr int kFixedTab = kRecBytes + 128;
+constexpr int kGroupHdr = 384;                  // ctrl 16 | mbarriers 24 (+8 pad) | CellRound0 48 | probe partials 16 x 16
+constexpr int kHdrBar = 16, kHdrR0 = 48, kHdrRed = 96;
+// block record flags
+constexpr int kBlkPP = 1, kBlkLong = 2, kBlkLastReg = 4, kBlkFirstPP = 8;
+
 __host__ __device__ inline size_t group_smem_bytes(int n_pad, int npp, int nv_pad) {
-  return static_cast<size_t>(n_pad + npp + nv_pad) * 16 + 8 * 16 + 64;
+  return static_cast<size_t>(n_pad + npp + nv_pad) * 16 + kGroupHdr;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -363,9 +384,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   constexpr int CPG = TR::CPG;
 
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* s_tab = smem;
-  unsigned char* s_pc = s_tab + p.tab_bytes;
-  unsigned char* s_w = s_pc + static_cast<size_t>(p.n_pad) * sizeof(PC);
+  unsigned char* s_pc = smem + kFixedTab;
+  unsigned char* s_var = s_pc + static_cast<size_t>(p.n_pad) * sizeof(PC);   // ovfidx
+  const int var_bytes = p.tab_bytes - kFixedTab;
+  unsigned char* s_w = s_var + var_bytes;
   const int wpre = W_SMEM ? p.w_bytes : p.w_prefix;   // bytes of the operator held in shared memory
   unsigned char* s_groups = s_w + wpre;
   const size_t gbytes = group_smem_bytes(p.n_pad, p.npp, p.nv_pad);
@@ -374,12 +396,12 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = warp >> p.wq_log2, wq = warp & (p.wq - 1);
   const int qthreads = p.wq * 32, qtid = wq * 32 + lane, bar_id = 1 + grp;
+  unsigned char* ghdr = s_groups + static_cast<size_t>(grp) * gbytes;
 
   // ---- stage operator tables and the node's proj/const with the bulk-copy engine ----
   if (threadIdx.x == 0) mbar_init(s_mbar, 1);
   if (SCR_SPLIT_BARRIER && !PROBE && qtid == 0) {
-    unsigned char* g0 = s_groups + static_cast<size_t>(grp) * gbytes;
-    uint64_t* b0 = reinterpret_cast<uint64_t*>(g0 + static_cast<size_t>(p.n_pad + p.npp + p.nv_pad + 8) * 16 + 16);
+    uint64_t* b0 = reinterpret_cast<uint64_t*>(ghdr + kHdrBar);
     mbar_init(b0, p.wq);
     mbar_init(b0 + 1, p.wq);
     mbar_init(b0 + 2, (SCR_CHUNK_ARRIVE_ALL || SCR_CHUNK_SPREAD) ? p.wq : max(1, min(p.wq, p.nv_pad / 32)));   // bar_a: one arrival per chunk-evaluating warp
@@ -389,16 +411,16 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   if (threadIdx.x == 0) {
     const uint32_t pc_bytes = static_cast<uint32_t>(p.n_pad * sizeof(PC));
     mbar_expect_tx(s_mbar, p.tab_bytes + pc_bytes + wpre);
-    bulk_g2s(s_tab, p.tab, p.tab_bytes, s_mbar);
+    bulk_g2s(smem, p.tab, kFixedTab, s_mbar);
     bulk_g2s(s_pc, p.pc, pc_bytes, s_mbar);
+    if (var_bytes > 0) bulk_g2s(s_var, p.tab + kFixedTab, var_bytes, s_mbar);
     if (wpre > 0) bulk_g2s(s_w, p.wblob, wpre, s_mbar);
   }
   mbar_wait(s_mbar, 0);
 
-  const int* blk_off = reinterpret_cast<const int*>(s_tab + p.off_slice);   // block b: slots [blk_off[b], blk_off[b+1])
-  const int2* ovfidx = reinterpret_cast<const int2*>(s_tab + p.off_ovfidx);
-  const int* wblk_ptr = reinterpret_cast<const int*>(s_tab + p.off_wblk_ptr);
-  const int* wblk = reinterpret_cast<const int*>(s_tab + p.off_wblk);
+  const uint32_t s_rec = smem_u32(smem);                                     // BlockRec table (shared-space address)
+  const int2* ovfidx = reinterpret_cast<const int2*>(s_var);
+  const int* wblk_ptr = reinterpret_cast<const int*>(smem + kRecBytes);
   const unsigned char* wbase = W_SMEM ? s_w : p.wblob;
   const WEnt* wtile = reinterpret_cast<const WEnt*>(wbase);
   // partial residency: blocks (and the chunk table) whose entries lie inside the staged prefix are read from shared
@@ -407,29 +429,28 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   const WEnt* wchunk = reinterpret_cast<const WEnt*>((chunks_in_smem ? s_w : p.wblob) + p.off_vrow);
   const PC* pcs = reinterpret_cast<const PC*>(s_pc);
 
-  unsigned char* bufA = s_groups + static_cast<size_t>(grp) * gbytes;
-  unsigned char* bufB = bufA + static_cast<size_t>(p.n_pad) * 16;
-  RowT* ovf = reinterpret_cast<RowT*>(bufB + static_cast<size_t>(p.npp) * 16);
-  RowT* red = ovf + p.nv_pad;
-  volatile int* ctrl = reinterpret_cast<volatile int*>(red + 8);
+  volatile int* ctrl = reinterpret_cast<volatile int*>(ghdr);
   // split step barriers (non-probe runs): three mbarriers per group, one arrival per warp
   //   bar_w: this step's new regulator values are all written     (waited at the start of the next step)
   //   bar_r: every read of this step's `cur` buffer has finished   (waited before the next step's first regulator store)
   //   bar_a: the long-row chunk partials of this step are in place (waited by the owners of long rows)
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(const_cast<int*>(ctrl) + 4);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(ghdr + kHdrBar);
   uint64_t* bar_r = bar_w + 1;
   uint64_t* bar_a = bar_w + 2;
+  uint32_t* cell_r0 = reinterpret_cast<uint32_t*>(ghdr + kHdrR0);   // [3][4] words: CellRound0 per cell
+  RowT* red = reinterpret_cast<RowT*>(ghdr + kHdrRed);              // PROBE: per-warp partial sums of |dx|
+  unsigned char* bufA = ghdr + kGroupHdr;
+  unsigned char* bufB = bufA + static_cast<size_t>(p.n_pad) * 16;
+  RowT* ovf = reinterpret_cast<RowT*>(bufB + static_cast<size_t>(p.npp) * 16);
 
   const int my_b0 = wblk_ptr[wq], my_b1 = wblk_ptr[wq + 1];
   // the warp's list is ordered [regulator blocks without long rows | blocks with long rows | the rest]
-  // (operator_pack.h); reg_end = end of the ping-ponged (regulator) part
+  // (operator_pack.h); a warp whose first block is not ping-ponged has no regulator blocks at all
   constexpr bool kSplit = SCR_SPLIT_BARRIER && !PROBE;
-  int reg_end = my_b0;
-  while (reg_end < my_b1 && wblk[reg_end] < p.npp_blocks) ++reg_end;
+  const bool no_reg_blocks = my_b0 >= my_b1 || !(lds_i4(s_rec + my_b0 * 16).w & kBlkPP);
   uint32_t tg = 0;            // steps this group has completed so far (mbarrier phase counter)
   const bool has_bias = p.bias != nullptr;
   constexpr bool kPacked = !PROBE && !SUPPLIED && SCR_PACKED_F32X2 && sizeof(T) == 4;
-  uint32_t* cell_r0 = reinterpret_cast<uint32_t*>(red);   // [3][4] words: CellRound0 per cell (`red` itself is PROBE-only)
 
   for (;;) {
     if (qtid == 0) ctrl[0] = atomicAdd(p.counter, 1);
@@ -549,7 +570,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           named_bar_sync(bar_id, qthreads);
         }
       }
-      if (kSplit && reg_end == my_b0) {   // a warp without regulator blocks has nothing to publish
+      if (kSplit && no_reg_blocks) {   // a warp without regulator blocks has nothing to publish
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_w);
       }
@@ -562,11 +583,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       // all cells of the group active (the common case: groups are sorted by step count): no
       // per-cell branches, so the four Philox chains and sixteen tanh's interleave freely
       const bool all_active = PROBE ? (alive == full_mask) : (s < smin);
-      int bnext = (my_b0 < my_b1) ? wblk[my_b0] : 0;
       for (int bi = my_b0; bi < my_b1; ++bi) {
-        const int b = bnext;
-        bnext = (bi + 1 < my_b1) ? wblk[bi + 1] : 0;   // prefetched a block ahead: off the critical path
-        const int gbase = b * 128 + lane;
+        const int4 rec = lds_i4(s_rec + bi * 16);   // {first gene, first slot, end slot, flags} of the block
+        const int gbase = rec.x + lane;
+        const int bflags = rec.w;
         T acc[4][CPG];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -574,10 +594,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           for (int c = 0; c < CPG; ++c) acc[j][c] = T(0);
         }
         {
-          const int o1 = blk_off[b + 1];
+          const int o1 = rec.z;
           const WEnt* wt = wtile;
           if (!W_SMEM && o1 * static_cast<int>(sizeof(WEnt)) <= wpre) wt = reinterpret_cast<const WEnt*>(s_w);
-          for (int o = blk_off[b] + lane; o < o1; o += 128) {
+          for (int o = rec.y + lane; o < o1; o += 128) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const WEnt e = wt[o + j * 32];
@@ -595,7 +615,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
             for (int c = 0; c < CPG; ++c) acc[j][c] += b0;
           }
         }
-        if (b < p.nlong_blocks) {
+        if (bflags & kBlkLong) {
           if (kSplit) mbar_wait(bar_a, tg & 1u);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -607,7 +627,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
             }
           }
         }
-        const bool pp = b < p.npp_blocks;
+        const bool pp = bflags & kBlkPP;
         const unsigned char* src = pp ? cur : bufA;
         unsigned char* dst = pp ? oth : bufA;
         RowT xo[4];
@@ -618,7 +638,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           xo[j] = *reinterpret_cast<const RowT*>(src + static_cast<size_t>(g) * 16);
           pcv[j] = pcs[g];
         }
-        const uint32_t ctr0 = static_cast<uint32_t>(b * 32 + lane);
+        const uint32_t ctr0 = static_cast<uint32_t>((rec.x >> 2) + lane);   // 32 * block + lane
         if (kPacked && all_active) {
           uint32_t w[CPG][4];
           const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * ctr0;
@@ -689,11 +709,11 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           }
         }
         // the first regulator store of a step overwrites the buffer the previous step read from
-        if (kSplit && s > 0 && bi == my_b0 && pp) mbar_wait(bar_r, (tg - 1u) & 1u);
+        if (kSplit && s > 0 && (bflags & kBlkFirstPP)) mbar_wait(bar_r, (tg - 1u) & 1u);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<RowT*>(dst + static_cast<size_t>(gbase + j * 32) * 16) = xo[j];
-        if (kSplit && bi == reg_end - 1) {   // this warp's share of the next step's inputs is published
+        if (kSplit && (bflags & kBlkLastReg)) {   // this warp's share of the next step's inputs is published
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_w);
         }
