@@ -366,7 +366,7 @@ constexpr int kFixedTab = kRecBytes + 128;
 constexpr int kGroupHdr = 384;                  // ctrl 16 | mbarriers 24 (+8 pad) | CellRound0 48 | probe partials 16 x 16
 constexpr int kHdrBar = 16, kHdrR0 = 48, kHdrRed = 96;
 // block record flags
-constexpr int kBlkPP = 1, kBlkLong = 2, kBlkLastReg = 4, kBlkFirstPP = 8;
+constexpr int kBlkPP = 1, kBlkLong = 2, kBlkLastReg = 4, kBlkFirstPP = 8, kBlkBias = 16, kBlkFlagMask = 127;
 
 __host__ __device__ inline size_t group_smem_bytes(int n_pad, int npp, int nv_pad) {
   return static_cast<size_t>(n_pad + npp + nv_pad) * 16 + kGroupHdr;
@@ -418,13 +418,32 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   }
   mbar_wait(s_mbar, 0);
 
+  // Block records arrive as {first gene, first slot, end slot, flags}; each CTA rewrites them once into the form the block
+  // loop consumes: {first gene | flags, slot count, generic pointer to the block's first entry}.  The pointer already
+  // says where the entries are read from (partial residency: blocks whose entries lie inside the staged prefix gather
+  // from shared memory, the others from global memory through L1 -- generic loads serve both), and the launch's bias
+  // switch becomes a block flag, so neither costs instructions per block.
   const uint32_t s_rec = smem_u32(smem);                                     // BlockRec table (shared-space address)
+  {
+    const int nrec = *reinterpret_cast<const int*>(smem + kRecBytes + p.wq * 4);   // wblk_ptr[wq] = number of records
+    const int wpre_bytes = W_SMEM ? p.w_bytes : p.w_prefix;
+    for (int r = threadIdx.x; r < nrec; r += blockDim.x) {
+      const int4 rec = lds_i4(s_rec + r * 16);
+      const bool in_smem = W_SMEM || rec.z * static_cast<int>(sizeof(WEnt)) <= wpre_bytes;
+      const unsigned long long ptr = reinterpret_cast<unsigned long long>(in_smem ? s_w : p.wblob) +
+                                     static_cast<unsigned long long>(rec.y) * sizeof(WEnt);
+      int4 out;
+      out.x = rec.x | rec.w | (p.bias != nullptr ? kBlkBias : 0);
+      out.y = rec.z - rec.y;
+      out.z = static_cast<int>(static_cast<uint32_t>(ptr));
+      out.w = static_cast<int>(static_cast<uint32_t>(ptr >> 32));
+      *reinterpret_cast<int4*>(smem + r * 16) = out;
+    }
+    __syncthreads();
+  }
   const int2* ovfidx = reinterpret_cast<const int2*>(s_var);
   const int* wblk_ptr = reinterpret_cast<const int*>(smem + kRecBytes);
-  const unsigned char* wbase = W_SMEM ? s_w : p.wblob;
-  const WEnt* wtile = reinterpret_cast<const WEnt*>(wbase);
-  // partial residency: blocks (and the chunk table) whose entries lie inside the staged prefix are read from shared
-  // memory, the others from global memory through L1 (generic loads serve both)
+  // the chunk table is read from shared memory when it lies inside the staged part of the operator
   const bool chunks_in_smem = W_SMEM || p.off_vrow + static_cast<int>(sizeof(WEnt)) * p.lv * p.nv_pad <= wpre;
   const WEnt* wchunk = reinterpret_cast<const WEnt*>((chunks_in_smem ? s_w : p.wblob) + p.off_vrow);
   const PC* pcs = reinterpret_cast<const PC*>(s_pc);
@@ -447,9 +466,8 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   // the warp's list is ordered [regulator blocks without long rows | blocks with long rows | the rest]
   // (operator_pack.h); a warp whose first block is not ping-ponged has no regulator blocks at all
   constexpr bool kSplit = SCR_SPLIT_BARRIER && !PROBE;
-  const bool no_reg_blocks = my_b0 >= my_b1 || !(lds_i4(s_rec + my_b0 * 16).w & kBlkPP);
+  const bool no_reg_blocks = my_b0 >= my_b1 || !(lds_i4(s_rec + my_b0 * 16).x & kBlkPP);
   uint32_t tg = 0;            // steps this group has completed so far (mbarrier phase counter)
-  const bool has_bias = p.bias != nullptr;
   constexpr bool kPacked = !PROBE && !SUPPLIED && SCR_PACKED_F32X2 && sizeof(T) == 4;
 
   for (;;) {
@@ -584,9 +602,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       // per-cell branches, so the four Philox chains and sixteen tanh's interleave freely
       const bool all_active = PROBE ? (alive == full_mask) : (s < smin);
       for (int bi = my_b0; bi < my_b1; ++bi) {
-        const int4 rec = lds_i4(s_rec + bi * 16);   // {first gene, first slot, end slot, flags} of the block
-        const int gbase = rec.x + lane;
-        const int bflags = rec.w;
+        const int4 rec = lds_i4(s_rec + bi * 16);   // {first gene | flags, slots, pointer to the first entry}
+        const int bflags = rec.x & kBlkFlagMask;
+        const int gbase = (rec.x & ~kBlkFlagMask) + lane;
         T acc[4][CPG];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -594,20 +612,19 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           for (int c = 0; c < CPG; ++c) acc[j][c] = T(0);
         }
         {
-          const int o1 = rec.z;
-          const WEnt* wt = wtile;
-          if (!W_SMEM && o1 * static_cast<int>(sizeof(WEnt)) <= wpre) wt = reinterpret_cast<const WEnt*>(s_w);
-          for (int o = rec.y + lane; o < o1; o += 128) {
+          const WEnt* wt = reinterpret_cast<const WEnt*>((static_cast<unsigned long long>(static_cast<uint32_t>(rec.w)) << 32) |
+                                                         static_cast<uint32_t>(rec.z)) + lane;
+          for (int o = lane; o < rec.y; o += 128, wt += 128) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const WEnt e = wt[o + j * 32];
+              const WEnt e = wt[j * 32];
               const RowT xv = *reinterpret_cast<const RowT*>(cur + e.off);
 #pragma unroll
               for (int c = 0; c < CPG; ++c) acc[j][c] = fma(e.v, xv.v[c], acc[j][c]);
             }
           }
         }
-        if (has_bias) {   // geneMeanLevels != 0 only: -mu * rowsum(W)
+        if (bflags & kBlkBias) {   // geneMeanLevels != 0 only: -mu * rowsum(W)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const T b0 = p.bias[gbase + j * 32];
@@ -638,7 +655,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           xo[j] = *reinterpret_cast<const RowT*>(src + static_cast<size_t>(g) * 16);
           pcv[j] = pcs[g];
         }
-        const uint32_t ctr0 = static_cast<uint32_t>((rec.x >> 2) + lane);   // 32 * block + lane
+        const uint32_t ctr0 = static_cast<uint32_t>(((rec.x & ~kBlkFlagMask) >> 2) + lane);   // 32 * block + lane
         if (kPacked && all_active) {
           uint32_t w[CPG][4];
           const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * ctr0;
