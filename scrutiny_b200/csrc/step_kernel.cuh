@@ -80,6 +80,16 @@ __device__ __forceinline__ int4 lds_i4(uint32_t addr) {
   asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ float2 lds_pc(uint32_t addr, float2*) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 lds_pc(uint32_t addr, double2*) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+  return v;
+}
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -363,8 +373,8 @@ __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&)[2][4], floa
 constexpr int kMaxBlocks = 128;                 // n_pad <= 16384 (a cell group of that size cannot fit an SM anyway)
 constexpr int kRecBytes = kMaxBlocks * 16;
 constexpr int kFixedTab = kRecBytes + 128;
-constexpr int kGroupHdr = 384;                  // ctrl 16 | mbarriers 24 (+8 pad) | CellRound0 48 | probe partials 16 x 16
-constexpr int kHdrBar = 16, kHdrR0 = 48, kHdrRed = 96;
+constexpr int kGroupHdr = 384;                  // ctrl 16 | mbarriers 24 (+8 pad) | CellRound0 48 | steps 16 | cells 16 | probe partials 16 x 16
+constexpr int kHdrBar = 16, kHdrR0 = 48, kHdrSteps = 96, kHdrCells = 112, kHdrRed = 128;
 // block record flags
 constexpr int kBlkPP = 1, kBlkLong = 2, kBlkLastReg = 4, kBlkFirstPP = 8, kBlkBias = 16, kBlkFlagMask = 127;
 
@@ -393,9 +403,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   const size_t gbytes = group_smem_bytes(p.n_pad, p.npp, p.nv_pad);
   uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_groups + static_cast<size_t>(p.q) * gbytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane_id = threadIdx.x & 31;
   const int grp = warp >> p.wq_log2, wq = warp & (p.wq - 1);
-  const int qthreads = p.wq * 32, qtid = wq * 32 + lane, bar_id = 1 + grp;
+  const int qthreads = p.wq * 32, qtid = wq * 32 + lane_id, bar_id = 1 + grp;
   unsigned char* ghdr = s_groups + static_cast<size_t>(grp) * gbytes;
 
   // ---- stage operator tables and the node's proj/const with the bulk-copy engine ----
@@ -423,7 +433,25 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   // says where the entries are read from (partial residency: blocks whose entries lie inside the staged prefix gather
   // from shared memory, the others from global memory through L1 -- generic loads serve both), and the launch's bias
   // switch becomes a block flag, so neither costs instructions per block.
-  const uint32_t s_rec = smem_u32(smem);                                     // BlockRec table (shared-space address)
+#ifndef SCR_PC_ASM
+#define SCR_PC_ASM 0   // 1: proj/const pairs through ld.shared on the record-table base (measured 0.5 % slower)
+#endif
+#ifndef SCR_PIN_LOOP_INVARIANTS
+#define SCR_PIN_LOOP_INVARIANTS 0   // measured: -7 instructions per block, but 1 % slower (profiles/r1_stepper_experiments.txt)
+#endif
+  // The lane id and the shared-space address of the record table are used by every 128-gene block; ptxas prefers to
+  // re-derive them from special registers (S2R + address arithmetic, five instructions) in every block instead of
+  // keeping two registers alive.  A round trip through a volatile shared-memory slot (the still unused state buffer)
+  // makes them plain register values.
+  uint32_t s_rec = smem_u32(smem);                                           // BlockRec table (shared-space address)
+  int lane = lane_id;
+  if (SCR_PIN_LOOP_INVARIANTS) {
+    volatile uint32_t* pin = reinterpret_cast<volatile uint32_t*>(ghdr + kGroupHdr) + qtid * 2;
+    pin[0] = static_cast<uint32_t>(lane_id);
+    pin[1] = s_rec;
+    lane = static_cast<int>(pin[0]);
+    s_rec = pin[1];
+  }
   {
     const int nrec = *reinterpret_cast<const int*>(smem + kRecBytes + p.wq * 4);   // wblk_ptr[wq] = number of records
     const int wpre_bytes = W_SMEM ? p.w_bytes : p.w_prefix;
@@ -446,7 +474,6 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   // the chunk table is read from shared memory when it lies inside the staged part of the operator
   const bool chunks_in_smem = W_SMEM || p.off_vrow + static_cast<int>(sizeof(WEnt)) * p.lv * p.nv_pad <= wpre;
   const WEnt* wchunk = reinterpret_cast<const WEnt*>((chunks_in_smem ? s_w : p.wblob) + p.off_vrow);
-  const PC* pcs = reinterpret_cast<const PC*>(s_pc);
 
   volatile int* ctrl = reinterpret_cast<volatile int*>(ghdr);
   // split step barriers (non-probe runs): three mbarriers per group, one arrival per warp
@@ -457,6 +484,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   uint64_t* bar_r = bar_w + 1;
   uint64_t* bar_a = bar_w + 2;
   uint32_t* cell_r0 = reinterpret_cast<uint32_t*>(ghdr + kHdrR0);   // [3][4] words: CellRound0 per cell
+  // per-cell step counts and local slots of the current group: read back where they are needed (ragged tail, write-back)
+  // instead of being carried in registers through the block loop
+  int* hsteps = reinterpret_cast<int*>(ghdr + kHdrSteps);
+  int* hcells = reinterpret_cast<int*>(ghdr + kHdrCells);
   RowT* red = reinterpret_cast<RowT*>(ghdr + kHdrRed);              // PROBE: per-warp partial sums of |dx|
   unsigned char* bufA = ghdr + kGroupHdr;
   unsigned char* bufB = bufA + static_cast<size_t>(p.n_pad) * 16;
@@ -478,16 +509,16 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
     const Item it = p.items[item_idx];
 
     // per-cell Philox round-0 invariants (published by the barrier that ends the state load below)
-    if (kPacked) {
 #pragma unroll
-      for (int c = 0; c < CPG; ++c) {
-        if (qtid == c) {
-          const uint64_t gid = static_cast<uint64_t>(p.cell_offset + (it.cell[c] >= 0 ? it.cell[c] : 0));
-          const CellRound0 r0 = philox_cell_round0(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), p.rk);
-          cell_r0[c] = r0.hi_p1_k0;
-          cell_r0[4 + c] = r0.lo_p1;
-          cell_r0[8 + c] = r0.c3_k1;
-        }
+    for (int c = 0; c < CPG; ++c) {
+      if (qtid == c) {
+        const uint64_t gid = static_cast<uint64_t>(p.cell_offset + (it.cell[c] >= 0 ? it.cell[c] : 0));
+        const CellRound0 r0 = philox_cell_round0(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), p.rk);
+        cell_r0[c] = r0.hi_p1_k0;
+        cell_r0[4 + c] = r0.lo_p1;
+        cell_r0[8 + c] = r0.c3_k1;
+        hsteps[c] = it.steps[c];
+        hcells[c] = it.cell[c];
       }
     }
 
@@ -516,14 +547,8 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
     unsigned char* cur = bufA;   // holds the current values of the ping-ponged genes
     unsigned char* oth = bufB;
     int smax = 0;
-    uint32_t gid_lo[CPG], gid_hi[CPG];
 #pragma unroll
-    for (int c = 0; c < CPG; ++c) {
-      smax = max(smax, it.steps[c]);
-      const uint64_t gid = static_cast<uint64_t>(p.cell_offset + (it.cell[c] >= 0 ? it.cell[c] : 0));
-      gid_lo[c] = static_cast<uint32_t>(gid);
-      gid_hi[c] = static_cast<uint32_t>(gid >> 32);
-    }
+    for (int c = 0; c < CPG; ++c) smax = max(smax, it.steps[c]);
     int smin = 0x7fffffff;    // steps every cell of the group takes (0 if a slot is empty)
 #pragma unroll
     for (int c = 0; c < CPG; ++c) smin = min(smin, it.steps[c]);
@@ -596,7 +621,6 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       T dsum[CPG];
 #pragma unroll
       for (int c = 0; c < CPG; ++c) dsum[c] = T(0);
-
       // -------- phase B: tiles + element-wise update, one 128-gene block at a time --------
       // all cells of the group active (the common case: groups are sorted by step count): no
       // per-cell branches, so the four Philox chains and sixteen tanh's interleave freely
@@ -604,7 +628,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       for (int bi = my_b0; bi < my_b1; ++bi) {
         const int4 rec = lds_i4(s_rec + bi * 16);   // {first gene | flags, slots, pointer to the first entry}
         const int bflags = rec.x & kBlkFlagMask;
-        const int gbase = (rec.x & ~kBlkFlagMask) + lane;
+        const int gbase = (rec.x & ~kBlkFlagMask) | lane;   // first gene is a multiple of 128: one LOP3
         T acc[4][CPG];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -645,17 +669,22 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           }
         }
         const bool pp = bflags & kBlkPP;
-        const unsigned char* src = pp ? cur : bufA;
-        unsigned char* dst = pp ? oth : bufA;
+        // regulator blocks read the current buffer and write the other one; the rest update in place
+        const unsigned char* src = (pp ? cur : bufA) + static_cast<size_t>(gbase) * 16;
+        unsigned char* dst = (pp ? oth : bufA) + static_cast<size_t>(gbase) * 16;
         RowT xo[4];
         PC pcv[4];
+        const uint32_t pc_addr = s_rec + kFixedTab + static_cast<uint32_t>(gbase) * static_cast<uint32_t>(sizeof(PC));
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int g = gbase + j * 32;
-          xo[j] = *reinterpret_cast<const RowT*>(src + static_cast<size_t>(g) * 16);
-          pcv[j] = pcs[g];
+          xo[j] = *reinterpret_cast<const RowT*>(src + j * 512);
+#if SCR_PC_ASM
+          pcv[j] = lds_pc(pc_addr + j * 32 * static_cast<uint32_t>(sizeof(PC)), static_cast<PC*>(nullptr));
+#else
+          pcv[j] = reinterpret_cast<const PC*>(s_pc)[gbase + j * 32];
+#endif
         }
-        const uint32_t ctr0 = static_cast<uint32_t>(((rec.x & ~kBlkFlagMask) >> 2) + lane);   // 32 * block + lane
+        const uint32_t ctr0 = static_cast<uint32_t>(((rec.x >> 2) & ~31) | lane);   // 32 * block + lane
         if (kPacked && all_active) {
           uint32_t w[CPG][4];
           const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * ctr0;
@@ -668,9 +697,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
         } else if (all_active && !SUPPLIED) {
           uint32_t w[CPG][4];
+          const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * ctr0;
 #pragma unroll
           for (int c = 0; c < CPG; ++c)
-            philox4x32_10_rk(ctr0, sctr[c], gid_lo[c], gid_hi[c], p.rk, w[c]);
+            philox4x32_10_cell(p0, sctr[c], cell_r0[c], cell_r0[4 + c], cell_r0[8 + c], p.rk, w[c]);
 #pragma unroll
           for (int c = 0; c < CPG; ++c) {
             float r0, c0, s0, r1, c1, s1;
@@ -696,7 +726,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           }
 #pragma unroll
           for (int c = 0; c < CPG; ++c) {
-            const bool active = PROBE ? ((alive >> c) & 1u) : (s < it.steps[c]);
+            const bool active = PROBE ? ((alive >> c) & 1u) : (s < hsteps[c]);
             if (active) {   // uniform over the group's warps
               T nz[4];
               float rr[4] = {0.f, 0.f, 0.f, 0.f}, uu[4] = {0.f, 0.f, 0.f, 0.f};
@@ -706,7 +736,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
                 for (int j = 0; j < 4; ++j) nz[j] = og[j] >= 0 ? p.noise[nbase + og[j]] : T(0);
               } else {
                 uint32_t w[4];
-                philox4x32_10_rk(ctr0, sctr[c], gid_lo[c], gid_hi[c], p.rk, w);
+                philox4x32_10_cell(static_cast<uint64_t>(0xD2511F53u) * ctr0, sctr[c], cell_r0[c], cell_r0[4 + c], cell_r0[8 + c], p.rk, w);
                 box_muller_polar(w[0], w[1], p.rscale, rr[0], uu[0], uu[1]);
                 box_muller_polar(w[2], w[3], p.rscale, rr[2], uu[2], uu[3]);
                 rr[1] = rr[0];
@@ -729,7 +759,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         if (kSplit && s > 0 && (bflags & kBlkFirstPP)) mbar_wait(bar_r, (tg - 1u) & 1u);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<RowT*>(dst + static_cast<size_t>(gbase + j * 32) * 16) = xo[j];
+          *reinterpret_cast<RowT*>(dst + j * 512) = xo[j];
         if (kSplit && (bflags & kBlkLastReg)) {   // this warp's share of the next step's inputs is published
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_w);
@@ -807,9 +837,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           for (int c = 0; c < CPG; ++c) r[c].v[jj] = o.v[c];
         }
 #pragma unroll
-        for (int c = 0; c < CPG; ++c)
-          if (it.cell[c] >= 0)
-            *reinterpret_cast<RowT*>(p.state + static_cast<int64_t>(it.cell[c]) * p.ld + g0) = r[c];
+        for (int c = 0; c < CPG; ++c) {
+          const int cell = hcells[c];
+          if (cell >= 0) *reinterpret_cast<RowT*>(p.state + static_cast<int64_t>(cell) * p.ld + g0) = r[c];
+        }
       }
     }
     named_bar_sync(bar_id, qthreads);   // smem is reused by the next group
