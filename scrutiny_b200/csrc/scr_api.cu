@@ -39,7 +39,7 @@ struct scr_ctx {
   bool has_net = false;
   PackedOperator op;
   unsigned char *d_tab = nullptr, *d_w = nullptr;
-  int tab_bytes = 0, w_bytes = 0, off_slice = 0, off_ovfidx = 0, off_wblk_ptr = 0, off_wblk = 0, off_vrow = 0;
+  int tab_bytes = 0, w_bytes = 0, off_vrow = 0;
   int *d_perm = nullptr, *d_inv = nullptr;
   void *d_pc = nullptr, *d_bias = nullptr;
   int q = 1;
@@ -114,14 +114,11 @@ int align16(int x) { return (x + 15) & ~15; }
 
 template <typename T>
 void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std::vector<unsigned char>& w,
-                 int& off_slice, int& off_ovfidx, int& off_wblk_ptr, int& off_wblk, int& off_vrow) {
+                 int& off_vrow) {
   using WEnt = typename scr::Traits<T>::WEnt;
   // fixed part (step_kernel.cuh "Shared-memory layout"): block records in the order of the warps' lists, list bounds;
   // variable part: chunk ranges of the long rows
-  off_slice = 0;
-  off_wblk = 0;
-  off_wblk_ptr = scr::kRecBytes;
-  off_ovfidx = scr::kFixedTab;
+  const int off_wblk_ptr = scr::kRecBytes, off_ovfidx = scr::kFixedTab;
   const int total = align16(off_ovfidx + static_cast<int>(op.ovf_start.size()) * 8);
   tab.assign(total, 0);
   for (int w = 0; w < op.wq; ++w) {
@@ -284,8 +281,7 @@ void fill_common(scr_ctx* ctx, scr::StepParams<T>& p) {
   const PackedOperator& op = ctx->op;
   std::memset(&p, 0, sizeof(p));
   p.tab = ctx->d_tab; p.wblob = ctx->d_w; p.tab_bytes = ctx->tab_bytes; p.w_bytes = ctx->w_bytes;
-  p.off_slice = ctx->off_slice; p.off_ovfidx = ctx->off_ovfidx; p.off_wblk_ptr = ctx->off_wblk_ptr;
-  p.off_wblk = ctx->off_wblk; p.off_vrow = ctx->off_vrow;
+  p.off_vrow = ctx->off_vrow;
   p.n = op.n; p.n_pad = op.n_pad; p.npp = op.npp; p.nb = op.nb; p.npp_blocks = op.npp_blocks;
   p.nlong_blocks = op.nlong_blocks; p.nv = op.nv; p.nv_pad = op.nv_pad; p.lv = op.lv;
   p.wq = op.wq; p.wq_log2 = op.wq_log2; p.q = ctx->q;
@@ -871,8 +867,8 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
     return fail(ctx, SCR_E_STATE, "network pattern changed while cells are allocated");
   if (op.nb > scr::kMaxBlocks) return fail(ctx, SCR_E_RESOURCE, "n too large: one cell group does not fit in shared memory");
   std::vector<unsigned char> tab, w;
-  if (ctx->prec == SCR_F64) build_blobs<double>(op, tab, w, ctx->off_slice, ctx->off_ovfidx, ctx->off_wblk_ptr, ctx->off_wblk, ctx->off_vrow);
-  else build_blobs<float>(op, tab, w, ctx->off_slice, ctx->off_ovfidx, ctx->off_wblk_ptr, ctx->off_wblk, ctx->off_vrow);
+  if (ctx->prec == SCR_F64) build_blobs<double>(op, tab, w, ctx->off_vrow);
+  else build_blobs<float>(op, tab, w, ctx->off_vrow);
   ctx->tab_bytes = static_cast<int>(tab.size());
   ctx->w_bytes = static_cast<int>(w.size());
   ctx->op = std::move(op);

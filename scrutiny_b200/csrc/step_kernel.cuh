@@ -17,6 +17,10 @@
 //     the rest are updated in place, which is what lets several groups share one SM;
 //   * operator tables + per-node proj/const are staged once per CTA with a bulk async copy
 //     (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier;
+//   * everything a 128-gene block needs to get going is ONE 16-byte record at a compile-time shared-memory
+//     offset: {first gene | flags, slot count, generic pointer to the block's first operator entry}; the flags carry
+//     what used to be per-block comparisons (ping-ponged? long rows? last regulator block of the warp? bias?), the
+//     pointer already encodes whether the entries are read from the staged part of the operator or from global memory;
 //   * CTAs are persistent and pull groups (sorted by step count, longest first) from an atomic
 //     counter; each group synchronises on its own named barrier.
 #pragma once
@@ -304,7 +308,6 @@ template <typename T> struct StepParams {
   const unsigned char* wblob; // tile entries, then long-row chunk entries
   int tab_bytes, w_bytes;     // multiples of 16
   int w_prefix;               // leading bytes of wblob staged in shared memory when the whole blob does not fit (multiple of 128)
-  int off_slice, off_ovfidx, off_wblk_ptr, off_wblk;  // byte offsets inside tab
   int off_vrow;               // byte offset of chunk entries inside wblob
   int n, n_pad, npp, nb, npp_blocks, nlong_blocks, nv, nv_pad, lv;
   int wq, wq_log2, q;
