@@ -243,6 +243,9 @@ __device__ __forceinline__ double add_supplied(double drive, double nz) { return
 #ifndef SCR_CHUNK_UNROLL
 #define SCR_CHUNK_UNROLL 1    // long-row chunks of the default length (8) are evaluated with all loads in flight
 #endif
+#ifndef SCR_MERGE_RARE
+#define SCR_MERGE_RARE 1
+#endif
 #ifndef SCR_CHUNK_ARRIVE_ALL
 #define SCR_CHUNK_ARRIVE_ALL 0   // 1: every warp of the group arrives on the chunk barrier (the earlier behaviour)
 #endif
@@ -651,6 +654,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
             }
           }
         }
+#if SCR_MERGE_RARE
+        if (bflags & (kBlkBias | kBlkLong)) {   // both rare: one test on the common path
+#endif
         if (bflags & kBlkBias) {   // geneMeanLevels != 0 only: -mu * rowsum(W)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -671,6 +677,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
             }
           }
         }
+#if SCR_MERGE_RARE
+        }
+#endif
         const bool pp = bflags & kBlkPP;
         // regulator blocks read the current buffer and write the other one; the rest update in place
         const unsigned char* src = (pp ? cur : bufA) + static_cast<size_t>(gbase) * 16;
