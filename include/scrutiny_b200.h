@@ -69,7 +69,8 @@ int scr_debug_host_matvec(const scr_ctx* ctx, const double* x, double* y);
  * [3]=long-row chunks, [4]=chunk length, [5]=row cap, [6]=warps per cell group,
  * [7]=cell groups per CTA, [8]=dynamic smem bytes, [9]=operator resident in smem (0/1),
  * [10]=cells per group, [11]=dense (tcgen05 GEMM) stepper selected (0/1), [12]=operator bytes staged in
- * smem when it is only partly resident, [13]=operator bytes in total. */
+ * smem when it is only partly resident, [13]=operator bytes in total, [14]=modelled shared-memory wavefronts of one
+ * step's gathers (LDS.128 bank model, csrc/operator_pack.h), [15]=their conflict-free floor. */
 int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count);
 
 /* ---- cell states: `currentStates` of findAllNextStates (MS:540-554) --------------------------- */

@@ -35,11 +35,116 @@ struct PackedOperator {
   std::vector<int> ovf_start, ovf_cnt;
   std::vector<double> rowsum;   // internal order, length n_pad
   std::vector<int> wblk_ptr, wblk;
+  // shared-memory wavefront model of one step's gathers (LDS.128: a quarter warp per wavefront, 8 x 16-byte bank groups;
+  // rows in the same bank group at different addresses serialise), over the quarter-warp reads that have at least one
+  // real entry: modelled count and its conflict-free floor
+  int64_t gather_wavefronts = 0, gather_wavefronts_floor = 0;
 };
 
 inline int env_int(const char* name, int dflt) {
   const char* v = std::getenv(name);
   return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// Cost of the quarter-warp read sets of a gene order under the LDS.128 bank model.  A read set is the (up to) eight
+// state rows the lanes of one quarter warp gather in the same slot: rows 8m .. 8m+7 of the order at tile entry k, or
+// eight consecutive chunks of long rows at chunk entry k.  Its cost is the largest number of DISTINCT positions that
+// share a bank group (position mod 8); lanes without an entry read position 0.  The stepper's gathers are 30 % bank
+// conflicts on the bench network (profiles/r1_final_step_kernel_ncu_summary.txt).
+struct BankModel {
+  int n = 0, cap = 0, lv = 0;
+  const int32_t* rowptr = nullptr;
+  const int32_t* col = nullptr;
+  std::vector<int> pos;                         // gene -> position
+  std::vector<std::vector<int>> sets;           // read set -> column genes (padding lanes counted in `pad`)
+  std::vector<int> pad;
+  std::vector<std::vector<int>> readers;        // gene -> read sets it appears in
+  int cost(int s) const {
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int seen[8][8];
+    if (pad[s] > 0) { seen[0][0] = 0; cnt[0] = 1; }
+    for (int g : sets[s]) {
+      const int p = pos[g], b = p & 7;
+      bool dup = false;
+      for (int i = 0; i < cnt[b]; ++i) dup |= seen[b][i] == p;
+      if (!dup && cnt[b] < 8) seen[b][cnt[b]++] = p;
+    }
+    int m = 1;
+    for (int b = 0; b < 8; ++b) m = std::max(m, cnt[b]);
+    return m;
+  }
+  void build(const std::vector<int>& order, const std::vector<int>& indeg, int nlong) {
+    pos.assign(n, 0);
+    for (int i = 0; i < n; ++i) pos[order[i]] = i;
+    sets.clear(); pad.clear();
+    readers.assign(n, {});
+    auto add = [&](int s, int g) { sets[s].push_back(g); readers[g].push_back(s); };
+    // tile entries: quarter m = positions [8m, 8m+8), slot k
+    for (int m = 0; m * 8 < n; ++m) {
+      int len = 0;
+      for (int i = m * 8; i < std::min(n, m * 8 + 8); ++i) len = std::max(len, std::min(indeg[order[i]], cap));
+      for (int k = 0; k < len; ++k) {
+        const int s = static_cast<int>(sets.size());
+        sets.emplace_back(); pad.push_back(0);
+        for (int i = m * 8; i < m * 8 + 8; ++i) {
+          if (i < n && k < std::min(indeg[order[i]], cap)) add(s, col[rowptr[order[i]] + k]);
+          else pad[s]++;
+        }
+      }
+    }
+    // chunk entries of the long rows (order positions 0 .. nlong-1 in sequence, lv entries per chunk)
+    std::vector<std::pair<int, int>> chunks;   // (row gene, first entry)
+    for (int i = 0; i < nlong; ++i)
+      for (int e = cap; e < indeg[order[i]]; e += lv) chunks.emplace_back(order[i], e);
+    for (size_t v0 = 0; v0 < chunks.size(); v0 += 8)
+      for (int k = 0; k < lv; ++k) {
+        const int s = static_cast<int>(sets.size());
+        sets.emplace_back(); pad.push_back(0);
+        for (size_t v = v0; v < v0 + 8; ++v) {
+          if (v < chunks.size() && chunks[v].second + k < indeg[chunks[v].first]) add(s, col[rowptr[chunks[v].first] + chunks[v].second + k]);
+          else pad[s]++;
+        }
+      }
+  }
+  int64_t total() const {
+    int64_t t = 0;
+    for (size_t s = 0; s < sets.size(); ++s) t += cost(static_cast<int>(s));
+    return t;
+  }
+};
+
+// SCR_BANK_OPT=1 (opt-in, measured lead for the next round): genes are exchanged inside aligned groups of 8 positions
+// -- which keeps every block's row set, the class prefixes and the rows of each quarter warp, and only changes the bank
+// group a gene's state row falls into -- whenever that lowers the modelled wavefront count.  Long rows stay where they
+// are (their order numbers the chunks, i.e. decides which chunks share a quarter warp), so every read set keeps its
+// members while positions move.
+inline void bank_optimize(BankModel& bm, std::vector<int>& order, const std::vector<int>& klass, int passes) {
+  const int n = bm.n;
+  for (int ps = 0; ps < passes; ++ps) {
+    int64_t gain = 0;
+    for (int g0 = 0; g0 < n; g0 += 8)
+      for (int a = g0; a < std::min(n, g0 + 8); ++a)
+        for (int b = a + 1; b < std::min(n, g0 + 8); ++b) {
+          const int ga = order[a], gb = order[b];
+          if (klass[ga] != klass[gb] || klass[ga] == 0) continue;
+          if (bm.readers[ga].empty() && bm.readers[gb].empty()) continue;
+          std::vector<int> touched(bm.readers[ga]);
+          touched.insert(touched.end(), bm.readers[gb].begin(), bm.readers[gb].end());
+          std::sort(touched.begin(), touched.end());
+          touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+          int64_t before = 0, after = 0;
+          for (int s : touched) before += bm.cost(s);
+          std::swap(bm.pos[ga], bm.pos[gb]);
+          for (int s : touched) after += bm.cost(s);
+          if (after < before) {
+            std::swap(order[a], order[b]);
+            gain += before - after;
+          } else {
+            std::swap(bm.pos[ga], bm.pos[gb]);
+          }
+        }
+    if (gain == 0) break;
+  }
 }
 
 // identity_order: keep the caller's gene order and no row cap (dense networks: every row is long and
@@ -85,6 +190,22 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
       if (ca != cb) return ca < cb;
       return indeg[a] > indeg[b];
     });
+  if (!identity_order && nnz > 0) {
+    BankModel bm;
+    bm.n = n; bm.cap = cap; bm.lv = op.lv; bm.rowptr = rowptr; bm.col = col;
+    int nlong = 0;
+    std::vector<int> klass(n);
+    for (int g = 0; g < n; ++g) { klass[g] = cls(g); nlong += klass[g] == 0; }
+    if (env_int("SCR_BANK_OPT", 0)) {
+      // the rows of a quarter warp are the members of its 8-group whatever their order inside it, but WHICH slot a
+      // row's k-th entry shares with its neighbours' k-th entries is fixed: rebuild the read sets after the exchange
+      bm.build(order, indeg, nlong);
+      bank_optimize(bm, order, klass, 6);
+    }
+    bm.build(order, indeg, nlong);
+    op.gather_wavefronts = bm.total();
+    op.gather_wavefronts_floor = static_cast<int64_t>(bm.sets.size());
+  }
   op.perm.assign(op.n_pad, -1);
   op.inv.assign(n, -1);
   int n_read = 0;

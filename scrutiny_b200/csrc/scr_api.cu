@@ -943,11 +943,12 @@ int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count) {
   if (!ctx || !out) return SCR_E_ARG;
   if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
   const PackedOperator& o = ctx->op;
-  const int64_t v[14] = {o.n_pad, o.npp, static_cast<int64_t>(o.tile_val.size()), o.nv, o.lv, o.cap, o.wq, ctx->q,
+  const int64_t v[16] = {o.n_pad, o.npp, static_cast<int64_t>(o.tile_val.size()), o.nv, o.lv, o.cap, o.wq, ctx->q,
                          static_cast<int64_t>(ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + ctx->q * ctx->gbytes +
                                               w_prefix_bytes(ctx, ctx->q)),
-                         ctx->w_smem ? 1 : 0, ctx->cpg(), ctx->dense_mode ? 1 : 0, w_prefix_bytes(ctx, ctx->q), ctx->w_bytes};
-  for (int i = 0; i < count && i < 14; ++i) out[i] = v[i];
+                         ctx->w_smem ? 1 : 0, ctx->cpg(), ctx->dense_mode ? 1 : 0, w_prefix_bytes(ctx, ctx->q), ctx->w_bytes,
+                         o.gather_wavefronts, o.gather_wavefronts_floor};
+  for (int i = 0; i < count && i < 16; ++i) out[i] = v[i];
   return SCR_OK;
 }
 

@@ -82,11 +82,12 @@ class Engine:
         return y
 
     def layout(self):
-        out = np.zeros(14, dtype=np.int64)
-        self._check(self._lib.scr_get_layout(self._ctx, _ptr(out, C.c_int64), 14))
+        out = np.zeros(16, dtype=np.int64)
+        self._check(self._lib.scr_get_layout(self._ctx, _ptr(out, C.c_int64), 16))
         keys = ("n_pad", "pingpong_genes", "tile_slots", "chunks", "chunk_len", "row_cap",
                 "warps_per_group", "groups_per_cta", "smem_bytes", "operator_in_smem",
-                "cells_per_group", "dense_stepper", "operator_prefix_bytes", "operator_bytes")
+                "cells_per_group", "dense_stepper", "operator_prefix_bytes", "operator_bytes",
+                "gather_wavefronts_model", "gather_wavefronts_floor")
         return dict(zip(keys, (int(v) for v in out)))
 
     # -- states -----------------------------------------------------------------------------
