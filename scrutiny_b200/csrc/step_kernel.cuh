@@ -22,7 +22,9 @@
 //     what used to be per-block comparisons (ping-ponged? long rows? last regulator block of the warp? bias?), the
 //     pointer already encodes whether the entries are read from the staged part of the operator or from global memory;
 //   * CTAs are persistent and pull groups (sorted by step count, longest first) from an atomic
-//     counter; each group synchronises on its own named barrier.
+//     counter; inside a step a group synchronises through three mbarriers (regulator values written / reads of
+//     the old buffer finished / long-row partials in place: arrive early, wait late), between groups and in PROBE
+//     mode through its own named barrier.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
