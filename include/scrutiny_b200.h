@@ -65,6 +65,12 @@ int scr_set_network_dense(scr_ctx* ctx, int32_t n, const double* gc_rowmajor);
 /* Test hook, host only (no GPU work): y = W x computed by walking the SAME packed operator the
  * kernels read (internal order, tiles, chunks), so packing bugs show up in the CPU test-suite. */
 int scr_debug_host_matvec(const scr_ctx* ctx, const double* x, double* y);
+/* The block records the stepper's warps walk, as the host uploads them (csrc/step_kernel.cuh "Shared-memory layout"):
+ * records[4*i .. 4*i+3] = {first gene, first slot, end slot, flags (1 ping-ponged, 2 long rows, 4 last regulator block of
+ * its warp, 8 first block of its warp and ping-ponged)} for list position i; list_bounds[w] .. list_bounds[w+1] is the
+ * list of warp w of a cell group.  Returns the number of records (= 128-gene blocks) or a negative error code. */
+int scr_debug_block_records(const scr_ctx* ctx, int32_t* records, int32_t max_records, int32_t* list_bounds,
+                            int32_t max_bounds);
 /* Layout facts for DESIGN.md / tests: out[0]=n_pad, [1]=ping-pong genes, [2]=tile slots,
  * [3]=long-row chunks, [4]=chunk length, [5]=row cap, [6]=warps per cell group,
  * [7]=cell groups per CTA, [8]=dynamic smem bytes, [9]=operator resident in smem (0/1),

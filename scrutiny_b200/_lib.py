@@ -26,6 +26,7 @@ SIGNATURES = {
     "scr_set_network_csr": (C.c_int, [c_ctx, C.c_int32, C.c_int64, _i32p, _i32p, _f64p]),
     "scr_set_network_dense": (C.c_int, [c_ctx, C.c_int32, _f64p]),
     "scr_debug_host_matvec": (C.c_int, [c_ctx, _f64p, _f64p]),
+    "scr_debug_block_records": (C.c_int, [c_ctx, _i32p, C.c_int32, _i32p, C.c_int32]),
     "scr_get_layout": (C.c_int, [c_ctx, _i64p, C.c_int]),
     "scr_alloc_cells": (C.c_int, [c_ctx, C.c_int64, C.c_int64]),
     "scr_set_states": (C.c_int, [c_ctx, C.c_int64, C.c_int64, _f64p, C.c_int64]),

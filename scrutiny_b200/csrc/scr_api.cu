@@ -39,6 +39,7 @@ struct scr_ctx {
   bool has_net = false;
   PackedOperator op;
   unsigned char *d_tab = nullptr, *d_w = nullptr;
+  std::vector<unsigned char> h_tab;   // host copy of the table blob (scr_debug_block_records)
   int tab_bytes = 0, w_bytes = 0, off_vrow = 0;
   int *d_perm = nullptr, *d_inv = nullptr;
   void *d_pc = nullptr, *d_bias = nullptr;
@@ -871,6 +872,7 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
   else build_blobs<float>(op, tab, w, ctx->off_vrow);
   ctx->tab_bytes = static_cast<int>(tab.size());
   ctx->w_bytes = static_cast<int>(w.size());
+  ctx->h_tab = tab;
   ctx->op = std::move(op);
   ctx->has_net = false;
   int rc = choose_config(ctx);
@@ -937,6 +939,16 @@ int scr_debug_host_matvec(const scr_ctx* ctx, const double* x, double* y) {
   if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
   scr::host_matvec(ctx->op, x, y);
   return SCR_OK;
+}
+
+int scr_debug_block_records(const scr_ctx* ctx, int32_t* records, int32_t max_records, int32_t* list_bounds, int32_t max_bounds) {
+  if (!ctx || !records || !list_bounds) return SCR_E_ARG;
+  if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
+  const PackedOperator& o = ctx->op;
+  if (max_records < o.nb || max_bounds < o.wq + 1) return fail(ctx, SCR_E_ARG, "output buffers too small");
+  std::memcpy(records, ctx->h_tab.data(), static_cast<size_t>(o.nb) * 16);
+  std::memcpy(list_bounds, ctx->h_tab.data() + scr::kRecBytes, static_cast<size_t>(o.wq + 1) * 4);
+  return o.nb;
 }
 
 int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count) {

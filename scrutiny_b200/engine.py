@@ -81,6 +81,16 @@ class Engine:
         self._check(self._lib.scr_debug_host_matvec(self._ctx, _ptr(x, C.c_double), _ptr(y, C.c_double)))
         return y
 
+    def block_records(self):
+        """(records (blocks, 4) int32 = first gene / first slot / end slot / flags, list bounds per warp of a group)."""
+        rec = np.zeros((128, 4), dtype=np.int32)
+        bounds = np.zeros(17, dtype=np.int32)
+        nb = self._lib.scr_debug_block_records(self._ctx, _ptr(rec, C.c_int32), 128, _ptr(bounds, C.c_int32), 17)
+        if nb < 0:
+            self._check(nb)
+        wq = self.layout()["warps_per_group"]
+        return rec[:nb].copy(), bounds[:wq + 1].copy()
+
     def layout(self):
         out = np.zeros(16, dtype=np.int64)
         self._check(self._lib.scr_get_layout(self._ctx, _ptr(out, C.c_int64), 16))

@@ -90,6 +90,41 @@ def test_bank_aware_gene_order_is_a_valid_packing(n, seed, heavy):
         assert b["gather_wavefronts_model"] < 0.9 * a["gather_wavefronts_model"]
 
 
+@pytest.mark.parametrize("n,seed,heavy", [(1, 0, 0), (64, 2, 1), (129, 3, 2), (1000, 5, 0), (3000, 6, 2)])
+def test_block_records_describe_the_warp_lists(n, seed, heavy):
+    """The 16-byte records the stepper walks (step_kernel.cuh): every 128-gene block exactly once, slot ranges tiling the
+    operator, and the flags that replace per-block comparisons in the kernel."""
+    eng = engine.Engine(device=-1)
+    eng.set_network(power_law_like(n, seed, heavy))
+    lay = eng.layout()
+    rec, bounds = eng.block_records()
+    nb = lay["n_pad"] // 128
+    assert rec.shape == (nb, 4) and bounds[0] == 0 and bounds[-1] == nb and (np.diff(bounds) >= 0).all()
+    assert sorted(rec[:, 0].tolist()) == [128 * b for b in range(nb)]             # each block once
+    by_gene = rec[np.argsort(rec[:, 0])]
+    assert by_gene[0, 1] == 0 and by_gene[-1, 2] == lay["tile_slots"]
+    assert np.array_equal(by_gene[1:, 1], by_gene[:-1, 2])                        # slot ranges tile the operator
+    assert ((by_gene[:, 2] - by_gene[:, 1]) % 128 == 0).all()
+    pp = (rec[:, 3] & 1) != 0
+    assert np.array_equal(pp, rec[:, 0] < lay["pingpong_genes"])                  # ping-ponged = read by some row
+    long_blocks = sorted(rec[(rec[:, 3] & 2) != 0, 0].tolist())
+    assert long_blocks == [128 * b for b in range(len(long_blocks))]              # long rows are a prefix of the order
+    assert (len(long_blocks) > 0) == (lay["chunks"] > 0)
+    for w in range(len(bounds) - 1):
+        mine = rec[bounds[w]:bounds[w + 1]]
+        mpp = (mine[:, 3] & 1) != 0
+        assert not (~mpp[:-1] & mpp[1:]).any()                                    # regulator blocks first
+        last = (mine[:, 3] & 4) != 0
+        first = (mine[:, 3] & 8) != 0
+        if mpp.any():
+            assert last.sum() == 1 and last[mpp.sum() - 1]                        # arrival after the last regulator block
+            assert first.sum() == 1 and first[0]                                  # wait before the first regulator store
+        else:
+            assert not last.any() and not first.any()
+        lng = (mine[:, 3] & 2) != 0
+        assert not (lng & ~mpp).any()
+
+
 def test_dense_and_empty_networks():
     rng = np.random.RandomState(3)
     W = rng.randn(200, 200)                       # fully dense: no long-row chunks expected
