@@ -245,6 +245,13 @@ __device__ __forceinline__ double add_supplied(double drive, double nz) { return
 #ifndef SCR_CHUNK_UNROLL
 #define SCR_CHUNK_UNROLL 1    // long-row chunks of the default length (8) are evaluated with all loads in flight
 #endif
+#ifndef SCR_EARLY_READ_ARRIVE
+// A/B candidate for the next round (default off, bit-identical by construction): the "reads of the old buffer finished"
+// arrival is made right after the last block's loads instead of at the end of the step, i.e. before that block's
+// Philox / Box-Muller / tanh work.  Arrivals at step ends are what wakes the warps already parked on the next step's
+// barrier (profiles/r1_final_step_kernel_ncu_summary.txt: 33 wake-ups per warp and step).
+#define SCR_EARLY_READ_ARRIVE 0
+#endif
 #ifndef SCR_MERGE_RARE
 #define SCR_MERGE_RARE 1
 #endif
@@ -698,6 +705,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           pcv[j] = reinterpret_cast<const PC*>(s_pc)[gbase + j * 32];
 #endif
         }
+        if (kSplit && SCR_EARLY_READ_ARRIVE && bi + 1 == my_b1) {   // the warp's last read of cur in this step is behind it
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_r);
+        }
         const uint32_t ctr0 = static_cast<uint32_t>(((rec.x >> 2) & ~31) | lane);   // 32 * block + lane
         if (kPacked && all_active) {
           uint32_t w[CPG][4];
@@ -794,8 +805,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         }
       }
       if (kSplit) {   // this warp no longer reads cur
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_r);
+        if (!SCR_EARLY_READ_ARRIVE || my_b0 >= my_b1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_r);
+        }
         ++tg;
       } else {
         named_bar_sync(bar_id, qthreads);   // end of step: every new value is in place
