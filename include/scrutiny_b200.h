@@ -45,6 +45,11 @@ enum { SCR_F32 = 0, SCR_F64 = 1 };
 enum { SCR_STREAM_STEP = 0, SCR_STREAM_PROBE = 1, SCR_STREAM_COUNTS = 2, SCR_STREAM_ALPHA = 16 };
 
 int scr_abi_version(void);
+/* Free-running noise stream of the sparse stepper (csrc/step_kernel.cuh): 2 = one Philox4x32-10 call per (cell, step,
+ * 128-gene block, lane pair) carrying eight normals, each word split into a 16-bit radius and a 16-bit angle uniform
+ * (restated in oracle/philox_ref.py: stepper_noise); 1 = the round-1 stream (one call per lane, 23-bit uniforms), only in
+ * A/B builds with -DSCR_NOISE16=0. */
+int scr_noise_stream_version(void);
 
 /* ---- context ------------------------------------------------------------------------------ */
 int scr_create(scr_ctx** out, int device_ordinal, int precision /* SCR_F32 | SCR_F64 */);
@@ -71,6 +76,9 @@ int scr_debug_host_matvec(const scr_ctx* ctx, const double* x, double* y);
  * list of warp w of a cell group.  Returns the number of records (= 128-gene blocks) or a negative error code. */
 int scr_debug_block_records(const scr_ctx* ctx, int32_t* records, int32_t max_records, int32_t* list_bounds,
                             int32_t max_bounds);
+/* The internal gene order (DESIGN.md "Data layout"): perm_out[i] = original gene at internal position i, -1 for padding;
+ * count must be n_pad (scr_get_layout out[0]). */
+int scr_debug_gene_order(const scr_ctx* ctx, int32_t* perm_out, int32_t count);
 /* Layout facts for DESIGN.md / tests: out[0]=n_pad, [1]=ping-pong genes, [2]=tile slots,
  * [3]=long-row chunks, [4]=chunk length, [5]=row cap, [6]=warps per cell group,
  * [7]=cell groups per CTA, [8]=dynamic smem bytes, [9]=operator resident in smem (0/1),

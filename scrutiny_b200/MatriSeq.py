@@ -277,14 +277,18 @@ def findAllNextStates(gc, cellTypeNode, cellTypeTree, currentStates, cellTypesRe
 
 
 def transformData(n, cells, finalCellStates, dropoutProportion=0.0, cellRadiusDisp=0.14, geneScale=0.0, expScale=1.0,
-                  expLambda=0.0, shape=0.35, rate=0.19, gammaDistMean=True, precision=None):
+                  expLambda=0.0, shape=0.35, rate=0.19, gammaDistMean=True, precision=None, capture=None):
     """MS:816-891 -> (counts (n, cells) float64 holding integers, cellSizeFactors).
-    ``dropoutProportion`` is accepted and unused, exactly like the reference (MS:819)."""
+    ``dropoutProportion`` is accepted and unused, exactly like the reference (MS:819).
+    ``capture`` (extension, parity aid): a dict that receives the Poisson rate matrix ``lambda`` (n, cells) and the
+    per-gene ``shift`` the read-out used."""
     eng = _engine_for(np.zeros((n, n)), cells, finalCellStates, precision)
-    sim = LineageSimulation(eng, cells, seed=_next_seed())
-    counts, size = sim.counts(cellRadiusDisp=cellRadiusDisp, expScale=expScale, shape=shape, rate=rate,
-                              geneScale=geneScale, expLambda=expLambda, gammaDistMean=gammaDistMean)
-    eng.close()
+    try:
+        sim = LineageSimulation(eng, cells, seed=_next_seed())
+        counts, size = sim.counts(cellRadiusDisp=cellRadiusDisp, expScale=expScale, shape=shape, rate=rate,
+                                  geneScale=geneScale, expLambda=expLambda, gammaDistMean=gammaDistMean, capture=capture)
+    finally:
+        eng.close()
     return np.ascontiguousarray(counts.T, dtype=np.float64), size
 
 

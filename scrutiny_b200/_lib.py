@@ -19,6 +19,7 @@ _f64p = C.POINTER(C.c_double)
 # name -> (restype, argtypes); mirrors include/scrutiny_b200.h one to one
 SIGNATURES = {
     "scr_abi_version": (C.c_int, []),
+    "scr_noise_stream_version": (C.c_int, []),
     "scr_create": (C.c_int, [C.POINTER(c_ctx), C.c_int, C.c_int]),
     "scr_destroy": (None, [c_ctx]),
     "scr_last_error": (C.c_char_p, [c_ctx]),
@@ -27,6 +28,7 @@ SIGNATURES = {
     "scr_set_network_dense": (C.c_int, [c_ctx, C.c_int32, _f64p]),
     "scr_debug_host_matvec": (C.c_int, [c_ctx, _f64p, _f64p]),
     "scr_debug_block_records": (C.c_int, [c_ctx, _i32p, C.c_int32, _i32p, C.c_int32]),
+    "scr_debug_gene_order": (C.c_int, [c_ctx, _i32p, C.c_int32]),
     "scr_get_layout": (C.c_int, [c_ctx, _i64p, C.c_int]),
     "scr_alloc_cells": (C.c_int, [c_ctx, C.c_int64, C.c_int64]),
     "scr_set_states": (C.c_int, [c_ctx, C.c_int64, C.c_int64, _f64p, C.c_int64]),

@@ -224,10 +224,18 @@ __global__ void debug_noise_kernel(int nb, uint32_t gid_lo, uint32_t gid_hi, uin
   if (t >= nb * 32) return;
   const int b = t >> 5, lane = t & 31;
   uint32_t w[4];
-  philox4x32_10(static_cast<uint32_t>(b * 32 + lane), step, gid_lo, gid_hi, k0, k1, w);
   float a[4];
+#if SCR_NOISE16
+  // stream v2 (step_kernel.cuh): one call per lane pair; the lane of the cell id's parity takes words 0, 1
+  philox4x32_10(static_cast<uint32_t>(b * 16 + (lane >> 1)), step, gid_lo, gid_hi, k0, k1, w);
+  const bool partner_half = ((static_cast<uint32_t>(lane) ^ gid_lo) & 1u) != 0;
+  box_muller16(partner_half ? w[2] : w[0], rscale, a[0], a[1]);
+  box_muller16(partner_half ? w[3] : w[1], rscale, a[2], a[3]);
+#else
+  philox4x32_10(static_cast<uint32_t>(b * 32 + lane), step, gid_lo, gid_hi, k0, k1, w);
   box_muller(w[0], w[1], rscale, a[0], a[1]);
   box_muller(w[2], w[3], rscale, a[2], a[3]);
+#endif
   for (int j = 0; j < 4; ++j) {
     const int o = perm[b * 128 + j * 32 + lane];
     if (o >= 0) out[o] = static_cast<double>(a[j]);

@@ -343,12 +343,13 @@ template <typename T>
 int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t* steps, const int64_t* step_base,
                 const double* proj, const double* cnst, double dt, double sigma, double mu, uint64_t seed,
                 const double* noise, int64_t noise_steps) {
-  constexpr int CPG = scr::Traits<T>::CPG;
-  // Longest first (counting sort on the step count), then groups of CPG consecutive cells, built straight in the
-  // pinned staging buffer: cell i goes to position pos[bucket]++ of the sorted order, i.e. slot (position % CPG) of
-  // group (position / CPG).  Each bucket writes sequentially, so this is a ~500-way streaming scatter.  Large phases
-  // split the cell list over a few host threads (per-thread histograms -> per-thread start positions), which keeps
-  // the sequential order exactly.
+  constexpr int CPG = scr::Traits<T>::CPG, H = CPG / 2;
+  // Longest first (counting sort on the step count), then groups of CPG cells, built straight in the pinned staging
+  // buffer.  Parity placement (step_kernel.cuh, noise stream v2): cells with an even GLOBAL id fill slots [0, H) of the
+  // groups, odd ones slots [H, CPG), each parity class in its own sorted sequence -- position k of a class goes to slot
+  // (k % H) of its half of group (k / H).  Each (class, bucket) writes sequentially, so this is a ~1000-way streaming
+  // scatter.  Large phases split the cell list over a few host threads (per-thread histograms -> per-thread start
+  // positions), which keeps the sequential order exactly.
   const int nthr = m >= (1 << 16) ? std::max(1, std::min(scr::env_int("SCR_HOST_THREADS", 4), 16)) : 1;
   auto span = [&](int t) { return std::make_pair(m * t / nthr, m * (t + 1) / nthr); };
   auto parallel = [&](auto&& fn) {
@@ -362,10 +363,17 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
     for (auto& x : th) x.join();
   };
   std::vector<int> t_smax(nthr, 0), t_bad(nthr, 0);
+  // "each cell at most once" (a duplicate would race on its state row): one bit per local slot, set atomically
+  std::vector<uint64_t> seen((static_cast<size_t>(ctx->cells) + 63) / 64, 0);
   parallel([&](int t) {
     int mx = 0, bad = 0;
     for (int64_t i = span(t).first; i < span(t).second; ++i) {
-      if (cell_ids[i] < 0 || cell_ids[i] >= ctx->cells) bad |= 1;
+      if (cell_ids[i] < 0 || cell_ids[i] >= ctx->cells) {
+        bad |= 1;
+      } else {
+        const uint64_t bit = 1ULL << (cell_ids[i] & 63);
+        if (__atomic_fetch_or(&seen[static_cast<size_t>(cell_ids[i]) >> 6], bit, __ATOMIC_RELAXED) & bit) bad |= 4;
+      }
       if (steps[i] < 0) bad |= 2;
       mx = std::max(mx, steps[i]);
     }
@@ -376,48 +384,63 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
   for (int t = 0; t < nthr; ++t) { smax = std::max(smax, t_smax[t]); bad |= t_bad[t]; }
   if (bad & 1) return fail(ctx, SCR_E_ARG, "cell id out of range");
   if (bad & 2) return fail(ctx, SCR_E_ARG, "negative step count");
+  if (bad & 4) return fail(ctx, SCR_E_ARG, "cell id listed twice in one phase");
   if (noise && smax > noise_steps) return fail(ctx, SCR_E_ARG, "supplied noise shorter than the longest cell");
   if (smax == 0) return SCR_OK;
   const size_t nbuckets = static_cast<size_t>(smax);                 // bucket b <-> step count smax - b
-  std::vector<int64_t> pos(static_cast<size_t>(nthr) * nbuckets, 0);  // pos[t * nbuckets + b]
+  const int64_t par0 = ctx->cell_offset & 1;                         // parity of the global id of local slot 0
+  auto klass = [&](int64_t i) { return static_cast<size_t>((cell_ids[i] + par0) & 1); };
+  std::vector<int64_t> pos(static_cast<size_t>(nthr) * 2 * nbuckets, 0);  // pos[(t * 2 + class) * nbuckets + b]
   parallel([&](int t) {
-    int64_t* h = pos.data() + static_cast<size_t>(t) * nbuckets;
-    for (int64_t i = span(t).first; i < span(t).second; ++i) if (steps[i] > 0) h[smax - steps[i]]++;
+    int64_t* h = pos.data() + static_cast<size_t>(t) * 2 * nbuckets;
+    for (int64_t i = span(t).first; i < span(t).second; ++i) if (steps[i] > 0) h[klass(i) * nbuckets + (smax - steps[i])]++;
   });
-  int64_t live = 0;
-  for (size_t b = 0; b < nbuckets; ++b)
-    for (int t = 0; t < nthr; ++t) {
-      int64_t& h = pos[static_cast<size_t>(t) * nbuckets + b];
-      const int64_t cnt = h;
-      h = live;
-      live += cnt;
-    }
-  const int64_t nitems = (live + CPG - 1) / CPG;
+  int64_t live[2] = {0, 0};
+  for (size_t k = 0; k < 2; ++k)
+    for (size_t b = 0; b < nbuckets; ++b)
+      for (int t = 0; t < nthr; ++t) {
+        int64_t& h = pos[(static_cast<size_t>(t) * 2 + k) * nbuckets + b];
+        const int64_t cnt = h;
+        h = live[k];
+        live[k] += cnt;
+      }
+  const int64_t nitems = (std::max(live[0], live[1]) + H - 1) / H;
   if (nitems > 0x7fffffff) return fail(ctx, SCR_E_ARG, "too many cell groups");
   int rc = ensure_items(ctx, static_cast<size_t>(nitems));
   if (rc) return rc;
   Item* items = ctx->h_items;
   parallel([&](int t) {
-    int64_t* next = pos.data() + static_cast<size_t>(t) * nbuckets;
+    int64_t* next = pos.data() + static_cast<size_t>(t) * 2 * nbuckets;
     for (int64_t i = span(t).first; i < span(t).second; ++i) {
       if (steps[i] <= 0) continue;
-      const int64_t k = next[smax - steps[i]]++;
-      Item& it = items[k / CPG];
-      const int c = static_cast<int>(k % CPG);
+      const size_t kl = klass(i);
+      const int64_t k = next[kl * nbuckets + (smax - steps[i])]++;
+      Item& it = items[k / H];
+      const int c = static_cast<int>(kl) * H + static_cast<int>(k % H);
       it.cell[c] = static_cast<int>(cell_ids[i]);
       it.steps[c] = steps[i];
       it.base[c] = static_cast<uint32_t>(step_base ? step_base[i] : 0);
       it.row[c] = static_cast<int>(i);
     }
   });
-  for (int64_t k = live; k < nitems * CPG; ++k) {   // empty slots of the last group
-    Item& it = items[k / CPG];
-    const int c = static_cast<int>(k % CPG);
-    it.cell[c] = -1;
-    it.steps[c] = 0;
-    it.base[c] = 0;
-    it.row[c] = 0;
-  }
+  for (int kl = 0; kl < 2; ++kl)
+    for (int64_t k = live[kl]; k < nitems * H; ++k) {   // empty slots of this class
+      Item& it = items[k / H];
+      const int c = kl * H + static_cast<int>(k % H);
+      it.cell[c] = -1;
+      it.steps[c] = 0;
+      it.base[c] = 0;
+      it.row[c] = 0;
+    }
+  parallel([&](int t) {
+    for (int64_t g = nitems * t / nthr; g < nitems * (t + 1) / nthr; ++g) {
+      items[g].scale = 1.0;
+      items[g].flags = scr::kItemParity;
+      items[g].pad_ = 0;
+      if (CPG < 4)
+        for (int c = CPG; c < 4; ++c) { items[g].cell[c] = -1; items[g].steps[c] = 0; items[g].base[c] = 0; items[g].row[c] = 0; }
+    }
+  });
   CK(cudaMemcpyAsync(ctx->d_items, items, static_cast<size_t>(nitems) * sizeof(Item), cudaMemcpyHostToDevice, ctx->stream));
 
   scr::StepParams<T> p;
@@ -780,7 +803,8 @@ int ensure_stage(scr_ctx* ctx, size_t elems) {
 // ============================================================================================
 extern "C" {
 
-int scr_abi_version(void) { return 1; }
+int scr_abi_version(void) { return 2; }
+int scr_noise_stream_version(void) { return SCR_NOISE16 ? 2 : 1; }
 
 int scr_create(scr_ctx** out, int device_ordinal, int precision) {
   if (!out || (precision != SCR_F32 && precision != SCR_F64)) return fail(nullptr, SCR_E_ARG, "bad arguments");
@@ -949,6 +973,14 @@ int scr_debug_block_records(const scr_ctx* ctx, int32_t* records, int32_t max_re
   std::memcpy(records, ctx->h_tab.data(), static_cast<size_t>(o.nb) * 16);
   std::memcpy(list_bounds, ctx->h_tab.data() + scr::kRecBytes, static_cast<size_t>(o.wq + 1) * 4);
   return o.nb;
+}
+
+int scr_debug_gene_order(const scr_ctx* ctx, int32_t* perm_out, int32_t count) {
+  if (!ctx || !perm_out) return SCR_E_ARG;
+  if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
+  if (count != ctx->op.n_pad) return fail(ctx, SCR_E_ARG, "count must be n_pad");
+  for (int i = 0; i < count; ++i) perm_out[i] = ctx->op.perm[i];
+  return SCR_OK;
 }
 
 int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count) {

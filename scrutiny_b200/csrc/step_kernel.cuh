@@ -80,6 +80,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrival `seq` (0-based step index) of a barrier that `count` warps arrive on per step; with SCR_LAST_ARRIVER only the
+// warp that completes the count touches the mbarrier (acq_rel atomic: its arrival publishes the other warps' writes)
+#ifndef SCR_LAST_ARRIVER
+#define SCR_LAST_ARRIVER 0
+#endif
+__device__ __forceinline__ void group_arrive(uint64_t* bar, uint32_t* cnt, uint32_t seq, uint32_t count) {
+#if SCR_LAST_ARRIVER
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
+  if (old + 1u == (seq + 1u) * count) mbar_arrive(bar);
+#else
+  (void)cnt; (void)seq; (void)count;
+  mbar_arrive(bar);
+#endif
+}
 // 128-bit load from a shared-space address (LDS.128 with the table offset folded into the immediate)
 __device__ __forceinline__ int4 lds_i4(uint32_t addr) {
   int4 v;
@@ -189,6 +204,48 @@ __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float rscal
   n_sin = r * sn;
 }
 
+// ------------------------------------------------------------------------------------------
+// Noise stream v2 of the sparse stepper (SCR_NOISE16, default): ONE 32-bit Philox word yields two normals.  The top 16
+// bits k give the radius, u1 = 1 - k / 65536 in (0, 1] (largest radius sqrt(2 ln 65536) = 4.71 sigma), the low 16 bits
+// m the angle, theta = 2 pi (m + 1/2) / 65536 - pi.  Both are unpacked with one integer instruction each through the
+// 2^23 + x float trick (0x4b000000 | x is the float 2^23 + x for x < 2^23) and one exact FMA:
+//   u1    = fma(2^23 + k, -2^-16, 129)                        (exact: 129 - 128 - k / 65536)
+//   theta = fma(2^23 + m, 2 pi / 65536, -(2^23 * 2 pi / 65536) - pi + pi / 65536)
+// A Philox4x32-10 call therefore carries EIGHT normals: the four genes (j = 0..3) a lane owns in a 128-gene block for
+// one cell, for BOTH lanes of a lane pair.  Counter (16 * block + lane / 2, step, global cell id lo, hi); the lane whose
+// parity equals the parity of the global cell id takes words 0, 1, its partner words 2, 3; word 0 / 2 -> genes j = 0
+// (cos) and 1 (sin), word 1 / 3 -> genes j = 2, 3.  The stepper's fast path lets each lane compute the calls of the two
+// cells of its own parity (the host places even cell ids in slots 0, 1 and odd ones in slots 2, 3 of a group) and
+// passes the partner's half on with one shuffle per word: half the Philox work of stream v1 (4 words -> 4 normals).
+// Restated in oracle/philox_ref.py (box_muller16); scr_debug_noise dumps it.
+// ------------------------------------------------------------------------------------------
+#ifndef SCR_NOISE16
+#define SCR_NOISE16 1   // 0: stream v1 (one call per lane and cell, 23-bit radius / angle words) -- A/B builds only
+#endif
+constexpr float kBm16AngleScale = 9.58738019107841e-05f;           // float(2 pi / 65536)
+constexpr float kBm16AngleBias = -807.3892822265625f;              // float(-(2^23 * double(kBm16AngleScale)) - pi + pi / 65536)
+__device__ __forceinline__ void bm16_unpack(uint32_t w, float& u1, float& th) {
+  const float fk = __uint_as_float((w >> 16) + 0x4b000000u);
+  const float fm = __uint_as_float((w & 0xffffu) | 0x4b000000u);
+  u1 = fmaf(fk, -1.52587890625e-05f, 129.0f);
+  th = fmaf(fm, kBm16AngleScale, kBm16AngleBias);
+}
+// radius and (cos, sin) of one word; rscale = -2 ln(2) sigma^2
+__device__ __forceinline__ void box_muller16_polar(uint32_t w, float rscale, float& r, float& c, float& sn) {
+  float u1, th;
+  bm16_unpack(w, u1, th);
+  r = ptx_sqrt(fabsf(ptx_lg2(u1) * rscale));
+  c = ptx_cos(th);
+  sn = ptx_sin(th);
+}
+// two N(0, sigma^2) values from one word
+__device__ __forceinline__ void box_muller16(uint32_t w, float rscale, float& n_cos, float& n_sin) {
+  float r, c, sn;
+  box_muller16_polar(w, rscale, r, c, sn);
+  n_cos = r * c;
+  n_sin = r * sn;
+}
+
 // accurate tanh.  fp32: 1 - 2/(1+e^{2z}) with ex2/rcp approximations, evaluated on z itself (no |z| / copysign pair:
 // the form is exact in the limits -- ex2 -> +inf gives rcp -> 0 -> +1, ex2 -> 0 gives -1 -- and its absolute error is
 // ~2.5e-7 on either side, entering the state scaled by dt; DESIGN.md "Precision").  SCR_TANH_SYMMETRIC=1 restores the
@@ -252,6 +309,12 @@ __device__ __forceinline__ double add_supplied(double drive, double nz) { return
 // barrier (profiles/r1_final_step_kernel_ncu_summary.txt: 33 wake-ups per warp and step).
 #define SCR_EARLY_READ_ARRIVE 0
 #endif
+#ifndef SCR_LAST_ARRIVER
+// A/B candidate: the warps of a group count their step-barrier arrivals in a shared-memory word and only the LAST one
+// performs the mbarrier arrival (barrier count 1), so a group makes 3 mbarrier events per step instead of ~18 -- every
+// mbarrier arrival wakes all warps parked in a try_wait on the SM (profiles/r1_final_step_kernel_ncu_summary.txt).
+#define SCR_LAST_ARRIVER 0
+#endif
 #ifndef SCR_MERGE_RARE
 #define SCR_MERGE_RARE 1
 #endif
@@ -283,6 +346,20 @@ __device__ __forceinline__ void box_muller_polar2(uint32_t wa0, uint32_t wb0, ui
   c = pk2(ptx_cos(h0), ptx_cos(h1));
   sn = pk2(ptx_sin(h0), ptx_sin(h1));
 }
+// stream v2: the same word position of two cells at once -> radius pair and (cos, sin) pairs
+__device__ __forceinline__ void box_muller16_polar2(uint32_t w0, uint32_t w1, f32x2 rscale2, f32x2& r, f32x2& c, f32x2& sn) {
+  const f32x2 fk = pk2(__uint_as_float((w0 >> 16) + 0x4b000000u), __uint_as_float((w1 >> 16) + 0x4b000000u));
+  const f32x2 fm = pk2(__uint_as_float((w0 & 0xffffu) | 0x4b000000u), __uint_as_float((w1 & 0xffffu) | 0x4b000000u));
+  float u0, u1;
+  upk2(fma2(fk, pk2(-1.52587890625e-05f, -1.52587890625e-05f), pk2(129.0f, 129.0f)), u0, u1);   // 1 - k / 65536 in (0, 1]
+  float t0, t1;
+  upk2(mul2(pk2(ptx_lg2(u0), ptx_lg2(u1)), rscale2), t0, t1);
+  r = pk2(ptx_sqrt(fabsf(t0)), ptx_sqrt(fabsf(t1)));
+  float h0, h1;
+  upk2(fma2(fm, pk2(kBm16AngleScale, kBm16AngleScale), pk2(kBm16AngleBias, kBm16AngleBias)), h0, h1);
+  c = pk2(ptx_cos(h0), ptx_cos(h1));
+  sn = pk2(ptx_sin(h0), ptx_sin(h1));
+}
 // ------------------------------------------------------------------------------------------
 // types
 // ------------------------------------------------------------------------------------------
@@ -311,8 +388,10 @@ struct __align__(16) Item {   // one cell group
   uint32_t base[4];           // iterations already done (noise key)
   int row[4];                 // position in the caller's list (supplied noise / probe outputs)
   double scale;               // PROBE: multiplies W (1/alpha ladder, MatriSeq.py:461)
-  double pad_;
+  int flags;                  // kItemParity: slots 0, 1 hold even and slots 2, 3 odd GLOBAL cell ids (fp64: slot 0 / 1)
+  int pad_;
 };
+constexpr int kItemParity = 1;
 
 template <typename T> struct StepParams {
   // packed operator (global copies; staged to smem by the kernel)
@@ -349,7 +428,12 @@ template <typename T> struct StepParams {
 
 // element-wise update of one 128-gene block for a fully active group of 4 float cells, packed fp32x2: next_state()
 // on cell pairs, instruction for instruction (FFMA2 / FADD2 are per-lane IEEE, so the results are bit-identical)
-__device__ __forceinline__ void fast_update_f32x2(const uint32_t (&w)[4][4], float rscale, float dt, const float (&acc)[4][4],
+#if SCR_NOISE16
+constexpr int kWordsPerCell = 2;   // words a lane consumes per cell and 128-gene block
+#else
+constexpr int kWordsPerCell = 4;
+#endif
+__device__ __forceinline__ void fast_update_f32x2(const uint32_t (&w)[4][kWordsPerCell], float rscale, float dt, const float (&acc)[4][4],
                                                   Row<float> (&xo)[4], const float2 (&pcv)[4]) {
   const float omdt = 1.0f - dt, m2dt = -2.0f * dt;
   const f32x2 rscale2 = pk2(rscale, rscale), dt2 = pk2(dt, dt), omdt2 = pk2(omdt, omdt), m2dt2 = pk2(m2dt, m2dt);
@@ -360,7 +444,11 @@ __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&w)[4][4], flo
 #pragma unroll
     for (int h = 0; h < 2; ++h) {           // word pairs -> genes (2h, 2h+1)
       f32x2 r, cs, sn;
+#if SCR_NOISE16
+      box_muller16_polar2(w[c0][h], w[c1][h], rscale2, r, cs, sn);
+#else
       box_muller_polar2(w[c0][2 * h], w[c0][2 * h + 1], w[c1][2 * h], w[c1][2 * h + 1], rscale2, r, cs, sn);
+#endif
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = 2 * h + e;
@@ -375,7 +463,7 @@ __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&w)[4][4], flo
   }
 }
 // (double contexts never take this path; the overload only keeps the template well-formed)
-__device__ __forceinline__ void fast_update_f32x2(const uint32_t (&)[2][4], float, double, const double (&)[4][2],
+__device__ __forceinline__ void fast_update_f32x2(const uint32_t (&)[2][kWordsPerCell], float, double, const double (&)[4][2],
                                                   Row<double> (&)[4], const double2 (&)[4]) {}
 
 // Shared-memory layout of a CTA (byte offsets from the start of dynamic shared memory):
@@ -388,8 +476,8 @@ __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&)[2][4], floa
 constexpr int kMaxBlocks = 128;                 // n_pad <= 16384 (a cell group of that size cannot fit an SM anyway)
 constexpr int kRecBytes = kMaxBlocks * 16;
 constexpr int kFixedTab = kRecBytes + 128;
-constexpr int kGroupHdr = 384;                  // ctrl 16 | mbarriers 24 (+8 pad) | CellRound0 48 | steps 16 | cells 16 | probe partials 16 x 16
-constexpr int kHdrBar = 16, kHdrR0 = 48, kHdrSteps = 96, kHdrCells = 112, kHdrRed = 128;
+constexpr int kGroupHdr = 400;                  // ctrl 16 | mbarriers 24 (+8 pad) | CellRound0 48 | steps 16 | cells 16 | step bases 16 | probe partials 16 x 16
+constexpr int kHdrBar = 16, kHdrR0 = 48, kHdrSteps = 96, kHdrCells = 112, kHdrBase = 128, kHdrRed = 144;
 // block record flags
 constexpr int kBlkPP = 1, kBlkLong = 2, kBlkLastReg = 4, kBlkFirstPP = 8, kBlkBias = 16, kBlkFlagMask = 127;
 
@@ -427,9 +515,13 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   if (threadIdx.x == 0) mbar_init(s_mbar, 1);
   if (SCR_SPLIT_BARRIER && !PROBE && qtid == 0) {
     uint64_t* b0 = reinterpret_cast<uint64_t*>(ghdr + kHdrBar);
-    mbar_init(b0, p.wq);
-    mbar_init(b0 + 1, p.wq);
-    mbar_init(b0 + 2, (SCR_CHUNK_ARRIVE_ALL || SCR_CHUNK_SPREAD) ? p.wq : max(1, min(p.wq, p.nv_pad / 32)));   // bar_a: one arrival per chunk-evaluating warp
+    const int chunk_warps = (SCR_CHUNK_ARRIVE_ALL || SCR_CHUNK_SPREAD) ? p.wq : max(1, min(p.wq, p.nv_pad / 32));   // bar_a: one arrival per chunk-evaluating warp
+    mbar_init(b0, SCR_LAST_ARRIVER ? 1 : p.wq);
+    mbar_init(b0 + 1, SCR_LAST_ARRIVER ? 1 : p.wq);
+    mbar_init(b0 + 2, SCR_LAST_ARRIVER ? 1 : chunk_warps);
+    uint32_t* cnt0 = reinterpret_cast<uint32_t*>(b0 + 3);   // arrival counters of the three barriers (the third is ctrl word 2)
+    cnt0[0] = cnt0[1] = 0;
+    reinterpret_cast<volatile int*>(ghdr)[2] = 0;
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -498,11 +590,16 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(ghdr + kHdrBar);
   uint64_t* bar_r = bar_w + 1;
   uint64_t* bar_a = bar_w + 2;
+  uint32_t* cnt_w = reinterpret_cast<uint32_t*>(bar_w + 3);
+  uint32_t* cnt_r = cnt_w + 1;
+  uint32_t* cnt_a = reinterpret_cast<uint32_t*>(ghdr) + 2;
+  const uint32_t n_chunk_warps = (SCR_CHUNK_ARRIVE_ALL || SCR_CHUNK_SPREAD) ? p.wq : max(1, min(p.wq, p.nv_pad / 32));
   uint32_t* cell_r0 = reinterpret_cast<uint32_t*>(ghdr + kHdrR0);   // [3][4] words: CellRound0 per cell
   // per-cell step counts and local slots of the current group: read back where they are needed (ragged tail, write-back)
   // instead of being carried in registers through the block loop
   int* hsteps = reinterpret_cast<int*>(ghdr + kHdrSteps);
   int* hcells = reinterpret_cast<int*>(ghdr + kHdrCells);
+  uint32_t* hbase = reinterpret_cast<uint32_t*>(ghdr + kHdrBase);   // iterations done before this phase (Philox counter word c1 = base + s)
   RowT* red = reinterpret_cast<RowT*>(ghdr + kHdrRed);              // PROBE: per-warp partial sums of |dx|
   unsigned char* bufA = ghdr + kGroupHdr;
   unsigned char* bufB = bufA + static_cast<size_t>(p.n_pad) * 16;
@@ -534,6 +631,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         cell_r0[8 + c] = r0.c3_k1;
         hsteps[c] = it.steps[c];
         hcells[c] = it.cell[c];
+        hbase[c] = it.base[c];
       }
     }
 
@@ -577,9 +675,21 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
     }
     const T wscale = PROBE ? static_cast<T>(it.scale) : T(1);
 
+#if SCR_NOISE16
+    // stream v2: the fast path runs the Philox calls of the two cells of this lane's parity (slots 2q, 2q + 1) and gets
+    // the other two cells' words from its partner lane; it needs groups built with parity placement (Item::flags &
+    // kItemParity), which is how scr_run_phase builds every group of a free-running float32 phase -- the only launches
+    // that compile the fast path (kPacked)
+    constexpr bool canonical = true;
+    uint32_t sown[2];         // counter word c1 of the current step for the lane's own two cells
+    sown[0] = (lane & 1) ? it.base[(2 % CPG)] : it.base[0];
+    sown[1] = (lane & 1) ? it.base[(3 % CPG)] : it.base[1 % CPG];
+#else
+    constexpr bool canonical = true;
     uint32_t sctr[CPG];       // Philox counter word c1 of the current step: iterations done before this phase + s
 #pragma unroll
     for (int c = 0; c < CPG; ++c) sctr[c] = it.base[c];
+#endif
     for (int s = 0; s < smax; ++s) {
       if (kSplit && s > 0) mbar_wait(bar_w, (tg - 1u) & 1u);   // all of cur is in place
       // -------- phase A: chunks of rows longer than the cap --------
@@ -622,7 +732,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           // every arrival wakes the warps suspended in a try_wait
           if (SCR_CHUNK_ARRIVE_ALL || SCR_CHUNK_SPREAD || wq * 32 < p.nv_pad) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a);
+            if (lane == 0) group_arrive(bar_a, cnt_a, tg, n_chunk_warps);
           }
         } else {
           named_bar_sync(bar_id, qthreads);
@@ -630,7 +740,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       }
       if (kSplit && no_reg_blocks) {   // a warp without regulator blocks has nothing to publish
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_w);
+        if (lane == 0) group_arrive(bar_w, cnt_w, tg, p.wq);
       }
 
       T dsum[CPG];
@@ -707,30 +817,69 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         }
         if (kSplit && SCR_EARLY_READ_ARRIVE && bi + 1 == my_b1) {   // the warp's last read of cur in this step is behind it
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_r);
+          if (lane == 0) group_arrive(bar_r, cnt_r, tg, p.wq);
         }
+#if SCR_NOISE16
+        const uint32_t ctr0 = static_cast<uint32_t>(((rec.x >> 3) & ~15) | (lane >> 1));   // 16 * block + lane pair
+#else
         const uint32_t ctr0 = static_cast<uint32_t>(((rec.x >> 2) & ~31) | lane);   // 32 * block + lane
-        if (kPacked && all_active) {
-          uint32_t w[CPG][4];
+#endif
+        if (kPacked && all_active && canonical) {
+          uint32_t w[CPG][kWordsPerCell];
           const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * ctr0;
+#if SCR_NOISE16
+          const bool odd = (lane & 1) != 0;
+          const uint32_t* r0own = cell_r0 + (odd ? 2 : 0);
+          const uint2 hp = *reinterpret_cast<const uint2*>(r0own);
+          const uint2 lp = *reinterpret_cast<const uint2*>(r0own + 4);
+          const uint2 ck = *reinterpret_cast<const uint2*>(r0own + 8);
+          uint32_t own[2][4], got[2][2];
+          philox4x32_10_cell(p0, sown[0], hp.x, lp.x, ck.x, p.rk, own[0]);
+          philox4x32_10_cell(p0, sown[1], hp.y, lp.y, ck.y, p.rk, own[1]);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) got[e][h] = __shfl_xor_sync(0xffffffffu, own[e][2 + h], 1);
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              w[e % CPG][h] = odd ? got[e][h] : own[e][h];              // slots 0, 1: even cell ids
+              w[(2 + e) % CPG][h] = odd ? own[e][h] : got[e][h];        // slots 2, 3: odd cell ids
+            }
+          }
+#else
           uint32_t hp[4], lp[4], ck[4];
           *reinterpret_cast<uint4*>(hp) = *reinterpret_cast<const uint4*>(cell_r0);
           *reinterpret_cast<uint4*>(lp) = *reinterpret_cast<const uint4*>(cell_r0 + 4);
           *reinterpret_cast<uint4*>(ck) = *reinterpret_cast<const uint4*>(cell_r0 + 8);
 #pragma unroll
           for (int c = 0; c < CPG; ++c) philox4x32_10_cell(p0, sctr[c], hp[c % 4], lp[c % 4], ck[c % 4], p.rk, w[c]);
+#endif
           fast_update_f32x2(w, p.rscale, p.dt, acc, xo, pcv);
         } else if (all_active && !SUPPLIED) {
           uint32_t w[CPG][4];
           const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * ctr0;
 #pragma unroll
-          for (int c = 0; c < CPG; ++c)
+          for (int c = 0; c < CPG; ++c) {
+#if SCR_NOISE16
+            philox4x32_10_cell(p0, hbase[c] + static_cast<uint32_t>(s), cell_r0[c], cell_r0[4 + c], cell_r0[8 + c], p.rk, w[c]);
+            if ((lane ^ (static_cast<int>(p.cell_offset) + hcells[c])) & 1) { w[c][0] = w[c][2]; w[c][1] = w[c][3]; }   // partner half
+#else
             philox4x32_10_cell(p0, sctr[c], cell_r0[c], cell_r0[4 + c], cell_r0[8 + c], p.rk, w[c]);
+#endif
+          }
 #pragma unroll
           for (int c = 0; c < CPG; ++c) {
             float r0, c0, s0, r1, c1, s1;
+#if SCR_NOISE16
+            box_muller16_polar(w[c][0], p.rscale, r0, c0, s0);
+            box_muller16_polar(w[c][1], p.rscale, r1, c1, s1);
+#else
             box_muller_polar(w[c][0], w[c][1], p.rscale, r0, c0, s0);
             box_muller_polar(w[c][2], w[c][3], p.rscale, r1, c1, s1);
+#endif
             const float rr[4] = {r0, r0, r1, r1};
             const float uu[4] = {c0, s0, c1, s1};
 #pragma unroll
@@ -761,9 +910,17 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
                 for (int j = 0; j < 4; ++j) nz[j] = og[j] >= 0 ? p.noise[nbase + og[j]] : T(0);
               } else {
                 uint32_t w[4];
+#if SCR_NOISE16
+                philox4x32_10_cell(static_cast<uint64_t>(0xD2511F53u) * ctr0, hbase[c] + static_cast<uint32_t>(s), cell_r0[c], cell_r0[4 + c],
+                                   cell_r0[8 + c], p.rk, w);
+                const bool partner_half = ((lane ^ (static_cast<int>(p.cell_offset) + hcells[c])) & 1) != 0;
+                box_muller16_polar(partner_half ? w[2] : w[0], p.rscale, rr[0], uu[0], uu[1]);
+                box_muller16_polar(partner_half ? w[3] : w[1], p.rscale, rr[2], uu[2], uu[3]);
+#else
                 philox4x32_10_cell(static_cast<uint64_t>(0xD2511F53u) * ctr0, sctr[c], cell_r0[c], cell_r0[4 + c], cell_r0[8 + c], p.rk, w);
                 box_muller_polar(w[0], w[1], p.rscale, rr[0], uu[0], uu[1]);
                 box_muller_polar(w[2], w[3], p.rscale, rr[2], uu[2], uu[3]);
+#endif
                 rr[1] = rr[0];
                 rr[3] = rr[2];
               }
@@ -787,7 +944,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           *reinterpret_cast<RowT*>(dst + j * 512) = xo[j];
         if (kSplit && (bflags & kBlkLastReg)) {   // this warp's share of the next step's inputs is published
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_w);
+          if (lane == 0) group_arrive(bar_w, cnt_w, tg, p.wq);
         }
       }
 
@@ -807,15 +964,20 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       if (kSplit) {   // this warp no longer reads cur
         if (!SCR_EARLY_READ_ARRIVE || my_b0 >= my_b1) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_r);
+          if (lane == 0) group_arrive(bar_r, cnt_r, tg, p.wq);
         }
         ++tg;
       } else {
         named_bar_sync(bar_id, qthreads);   // end of step: every new value is in place
       }
       { unsigned char* t = cur; cur = oth; oth = t; }
+#if SCR_NOISE16
+      ++sown[0];
+      ++sown[1];
+#else
 #pragma unroll
       for (int c = 0; c < CPG; ++c) ++sctr[c];
+#endif
 
       if (PROBE) {
         if (qtid == 0) {
@@ -845,6 +1007,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
     if (kSplit && smax > 0) {   // both complete = full barrier: every value of the last step is visible
       mbar_wait(bar_w, (tg - 1u) & 1u);
       mbar_wait(bar_r, (tg - 1u) & 1u);
+      // with the early arrival a warp's in-place stores of its last (non-ping-ponged) block come after its arrival on
+      // bar_r and are covered by neither barrier: close the gap before other threads read those rows
+      if (SCR_EARLY_READ_ARRIVE) named_bar_sync(bar_id, qthreads);
     }
     if (PROBE) {
       if (qtid == 0) {

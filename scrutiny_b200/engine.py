@@ -91,6 +91,15 @@ class Engine:
         wq = self.layout()["warps_per_group"]
         return rec[:nb].copy(), bounds[:wq + 1].copy()
 
+    def gene_order(self):
+        """perm[i] = original gene at internal position i (-1 = padding)."""
+        perm = np.zeros(self.layout()["n_pad"], dtype=np.int32)
+        self._check(self._lib.scr_debug_gene_order(self._ctx, _ptr(perm, C.c_int32), len(perm)))
+        return perm
+
+    def noise_stream_version(self):
+        return int(self._lib.scr_noise_stream_version())
+
     def layout(self):
         out = np.zeros(16, dtype=np.int64)
         self._check(self._lib.scr_get_layout(self._ctx, _ptr(out, C.c_int64), 16))

@@ -146,13 +146,17 @@ class LineageSimulation:
             shift[order] = target
         return shift
 
-    def counts(self, cellRadiusDisp=0.14, expScale=1.0, out=None, out_device_ptr=None, **kw):
+    def counts(self, cellRadiusDisp=0.14, expScale=1.0, out=None, out_device_ptr=None, capture=None, **kw):
         """transformData (MS:816-891) for this rank's cells.  Returns (counts (cells_local, n) int32,
-        all cellSizeFactors)."""
+        all cellSizeFactors).  ``capture`` (dict, parity aid) receives ``lambda`` (n, cells_local) and ``shift``."""
         shift = self.gene_shift(expScale=expScale, **kw)
         size = np.random.normal(loc=1, scale=cellRadiusDisp, size=self.cells) ** 3   # MS:875-876
         got = self.eng.counts(shift, size[self.lo:self.hi], exp_scale=expScale, seed=self.seed,
-                              out=out, out_device_ptr=out_device_ptr)
+                              out=out, out_device_ptr=out_device_ptr, want_lambda=capture is not None)
+        if capture is not None:
+            got, lam = got
+            capture["lambda"] = np.ascontiguousarray(lam.T)
+            capture["shift"] = shift
         return got, size
 
     # =========================================================================================

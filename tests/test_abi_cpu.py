@@ -21,7 +21,7 @@ def test_exports_match_header():
     for name in declared:
         assert hasattr(lib, name), "library does not export " + name
     assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree"
-    assert lib.scr_abi_version() == 1
+    assert lib.scr_abi_version() == 2
 
 
 def test_no_cpu_fallback():
