@@ -41,6 +41,9 @@ enum {
 
 enum { SCR_F32 = 0, SCR_F64 = 1 };
 
+/* element type of the compact count output (scr_counts_compact) */
+enum { SCR_COUNT_I32 = 0, SCR_COUNT_U16 = 1, SCR_COUNT_U8 = 2 };
+
 /* RNG stream ids (mixed into the Philox key) */
 enum { SCR_STREAM_STEP = 0, SCR_STREAM_PROBE = 1, SCR_STREAM_COUNTS = 2, SCR_STREAM_ALPHA = 16 };
 
@@ -66,6 +69,10 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
                         const int32_t* col, const double* val);
 /* same from a dense row-major (n, n) float64 matrix (what the reference passes around) */
 int scr_set_network_dense(scr_ctx* ctx, int32_t n, const double* gc_rowmajor);
+/* Read-out context: n genes and NO network (transformData, MS:816-891, needs none).  Only the state and read-out entry
+ * points work afterwards (scr_alloc_cells, scr_set_states*, scr_get_states, scr_gene_sums, scr_counts*); scr_run_phase and
+ * scr_probe return SCR_E_STATE.  No on-chip budget applies: any n the count kernel's staging row holds (n <= 58 000). */
+int scr_set_genes(scr_ctx* ctx, int32_t n);
 
 /* Test hook, host only (no GPU work): y = W x computed by walking the SAME packed operator the
  * kernels read (internal order, tiles, chunks), so packing bugs show up in the CPU test-suite. */
@@ -128,6 +135,8 @@ int scr_gene_sums(scr_ctx* ctx, double* sums_out /* n */);
  *            else float64 (cells, n, draws_per_entry) consumed in order per entry.
  *   counts_out: int32 (cells, n) row-major, host or device memory (out_on_device);
  *   lambda_out: float64 (cells, n) HOST buffer or NULL (parity aid).
+ *   Rates above 2e9 (or +inf from an overflowing exp) are sampled as 2e9: counts are int32 across this ABI
+ *   (numpy returns int64 there; nothing in MatriSeq's parameter range comes near).
  *   With Philox uniforms and no lambda_out, entries with lambda < 10 are first screened in float32 with a guard band
  *   and redone by the float64 sampler when undecided: the integers are those of the float64 sampler in every case
  *   (environment SCR_COUNTS_EXACT=1 switches the screening off, for A/B tests). */
@@ -141,6 +150,17 @@ int scr_counts_range(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const
                      double exp_scale, const double* size_factors /* cell_count */, uint64_t seed,
                      const double* uniforms, int32_t draws_per_entry, int32_t* counts_out, int out_on_device,
                      double* lambda_out);
+
+/* Compact read-out (free-running Philox stream only): the same integers as scr_counts_range, stored as out_dtype
+ * (SCR_COUNT_U8 / SCR_COUNT_U16 / SCR_COUNT_I32), row-major (cell_count, n), host or device memory.  A count that does not
+ * fit below the type's largest value (255 / 65535) is stored AS that value (escape code) and listed in overflow_out as
+ * int64 triplets {row of this call's output, gene, count}, sorted by (row, gene); *overflow_count receives the number of
+ * such entries.  If it exceeds overflow_capacity the call fails with SCR_E_RESOURCE after setting *overflow_count (the
+ * count matrix itself is complete; call again with that capacity to get the list).  The reference stores float64
+ * (MS:891): at config c5 that is 24 GB per 10^6 cells against 3 GB here (mean rate ~2, MS:855-873 defaults). */
+int scr_counts_compact(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const double* shift /* n */, double exp_scale,
+                       const double* size_factors /* cell_count */, uint64_t seed, int out_dtype, void* counts_out,
+                       int out_on_device, int64_t* overflow_out, int64_t overflow_capacity, int64_t* overflow_count);
 
 /* ---- debugging / parity aids ------------------------------------------------------------------ */
 /* raw Philox4x32-10 words for counters (c0..c3)[count] under key (k0,k1): device generator check */

@@ -43,15 +43,23 @@ __global__ void broadcast_state_kernel(const double* __restrict__ x0, T* __restr
   for (int64_t c = blockIdx.y; c < cells; c += gridDim.y) state[c * ld + i] = v;
 }
 
-// sums[internal gene] += sum over this block's cells (float64 accumulation)
+// Per-gene sums over the context's cells in a FIXED order (run-to-run deterministic): block row y accumulates cells
+// y, y + gridDim.y, ... in float64 into partial[y][gene]; gene_sums_finish_kernel adds the partials in index order.
 template <typename T>
 __global__ void gene_sums_kernel(const T* __restrict__ state, int64_t ld, int64_t cells, int n_pad,
-                                 double* __restrict__ sums) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                 double* __restrict__ partial) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // internal gene
   if (i >= n_pad) return;
   double acc = 0.0;
   for (int64_t c = blockIdx.y; c < cells; c += gridDim.y) acc += static_cast<double>(state[c * ld + i]);
-  atomicAdd(&sums[i], acc);
+  partial[static_cast<int64_t>(blockIdx.y) * n_pad + i] = acc;
+}
+__global__ void gene_sums_finish_kernel(const double* __restrict__ partial, int rows, int n_pad, double* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  double acc = 0.0;
+  for (int y = 0; y < rows; ++y) acc += partial[static_cast<int64_t>(y) * n_pad + i];
+  sums[i] = acc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -91,6 +99,7 @@ struct UniformSource {
 
 __device__ inline int poisson_draw(double lam, UniformSource& u) {
   if (!(lam > 0.0)) return 0;
+  if (lam > 2.0e9) lam = 2.0e9;   // counts are int32 across the ABI: rates beyond 2e9 (or +inf from an overflowing exp) saturate there
   if (lam < 10.0) {
     const double enlam = exp(-lam);
     double prod = 1.0;
@@ -156,13 +165,22 @@ __device__ __forceinline__ int poisson_small_f32(float lam_f, uint32_t gene, uin
 #ifndef SCR_COUNTS_CTAS_PER_SM
 #define SCR_COUNTS_CTAS_PER_SM 4   // 64 registers: the sampler is latency-bound (dependent FP64 chains), more warps pay (2 / 3 / 4 CTAs: 28.8 / 22.5 / 21.5 ms at 400k cells)
 #endif
-template <typename T, bool FAST>
+// OUT = int32_t, or a compact type (uint16_t / uint8_t): a count that does not fit below the type's largest value is
+// stored as that value (the escape code) and appended as {local cell, gene, count} to the overflow list (capacity
+// ovf_cap triplets; *ovf_count keeps counting beyond it so the host can tell).  Mean lambda of the read-out is ~2
+// (MatriSeq.py:855-873 defaults), so a byte per entry holds all but a handful of the 3e9 entries of config c5.
+template <typename OUT> struct CountLimit { static constexpr int kEscape = 0x7fffffff; };
+template <> struct CountLimit<uint16_t> { static constexpr int kEscape = 0xffff; };
+template <> struct CountLimit<uint8_t> { static constexpr int kEscape = 0xff; };
+
+template <typename T, bool FAST, typename OUT>
 __global__ void __launch_bounds__(256, SCR_COUNTS_CTAS_PER_SM)
 counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ inv,
                               const int* __restrict__ order, int n, int64_t cell0, const double* __restrict__ shift,
                               double exp_scale, const double* __restrict__ sizef, const RoundKeys rk,
                               int64_t cell_offset, const double* __restrict__ uniforms, int draws,
-                              int32_t* __restrict__ out, double* __restrict__ lam_out, int* err) {
+                              OUT* __restrict__ out, double* __restrict__ lam_out, int* err,
+                              int32_t* __restrict__ ovf, unsigned long long ovf_cap, unsigned long long* __restrict__ ovf_count) {
   extern __shared__ int32_t s_counts[];
   const int64_t c = cell0 + blockIdx.x;   // local slot
   const uint64_t gid = static_cast<uint64_t>(cell_offset + c);
@@ -201,8 +219,22 @@ counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ i
     s_counts[o] = cnt;
   }
   __syncthreads();
-  int32_t* orow = out + static_cast<int64_t>(blockIdx.x) * n;
-  for (int o = threadIdx.x; o < n; o += blockDim.x) orow[o] = s_counts[o];
+  OUT* orow = out + static_cast<int64_t>(blockIdx.x) * n;
+  constexpr int kEscape = CountLimit<OUT>::kEscape;
+  for (int o = threadIdx.x; o < n; o += blockDim.x) {
+    const int32_t v = s_counts[o];
+    if (sizeof(OUT) < 4 && v >= kEscape) {
+      const unsigned long long k = atomicAdd(ovf_count, 1ULL);
+      if (k < ovf_cap) {
+        ovf[3 * k] = static_cast<int32_t>(c);
+        ovf[3 * k + 1] = o;
+        ovf[3 * k + 2] = v;
+      }
+      orow[o] = static_cast<OUT>(kEscape);
+    } else {
+      orow[o] = static_cast<OUT>(v);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -49,8 +49,9 @@ inline int env_int(const char* name, int dflt) {
 // Cost of the quarter-warp read sets of a gene order under the LDS.128 bank model.  A read set is the (up to) eight
 // state rows the lanes of one quarter warp gather in the same slot: rows 8m .. 8m+7 of the order at tile entry k, or
 // eight consecutive chunks of long rows at chunk entry k.  Its cost is the largest number of DISTINCT positions that
-// share a bank group (position mod 8); lanes without an entry read position 0.  The stepper's gathers are 30 % bank
-// conflicts on the bench network (profiles/r1_final_step_kernel_ncu_summary.txt).
+// share a bank group (position mod 8); lanes without an entry read the row a real lane of their set reads (a broadcast,
+// free) -- position 0 only when the whole set is padding.  The stepper's gathers were 30 % bank conflicts on the bench
+// network before this model was used (profiles/r1_final_step_kernel_ncu_summary.txt).
 struct BankModel {
   int n = 0, cap = 0, lv = 0;
   const int32_t* rowptr = nullptr;
@@ -62,7 +63,7 @@ struct BankModel {
   int cost(int s) const {
     int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int seen[8][8];
-    if (pad[s] > 0) { seen[0][0] = 0; cnt[0] = 1; }
+    if (pad[s] > 0 && sets[s].empty()) { seen[0][0] = 0; cnt[0] = 1; }
     for (int g : sets[s]) {
       const int p = pos[g], b = p & 7;
       bool dup = false;
@@ -113,7 +114,7 @@ struct BankModel {
   }
 };
 
-// SCR_BANK_OPT=1 (opt-in, measured lead for the next round): genes are exchanged inside aligned groups of 8 positions
+// SCR_BANK_OPT (default 6 passes, 0 = off; +5.8 % on the bench network, profiles/r2_stepper_ab.txt): genes are exchanged inside aligned groups of 8 positions
 // -- which keeps every block's row set, the class prefixes and the rows of each quarter warp, and only changes the bank
 // group a gene's state row falls into -- whenever that lowers the modelled wavefront count.  Long rows stay where they
 // are (their order numbers the chunks, i.e. decides which chunks share a quarter warp), so every read set keeps its
@@ -196,11 +197,12 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
     int nlong = 0;
     std::vector<int> klass(n);
     for (int g = 0; g < n; ++g) { klass[g] = cls(g); nlong += klass[g] == 0; }
-    if (env_int("SCR_BANK_OPT", 0)) {
+    const int bank_passes = env_int("SCR_BANK_OPT", 6);
+    if (bank_passes > 0) {
       // the rows of a quarter warp are the members of its 8-group whatever their order inside it, but WHICH slot a
       // row's k-th entry shares with its neighbours' k-th entries is fixed: rebuild the read sets after the exchange
       bm.build(order, indeg, nlong);
-      bank_optimize(bm, order, klass, 6);
+      bank_optimize(bm, order, klass, bank_passes == 1 ? 6 : bank_passes);
     }
     bm.build(order, indeg, nlong);
     op.gather_wavefronts = bm.total();
@@ -272,6 +274,27 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
       }
     }
     op.rowsum[i] = sum;
+  }
+  // padding lanes gather the row a real lane of their quarter warp gathers in the same slot (same address: a broadcast,
+  // no extra shared-memory wavefront) instead of row 0, which could collide with a real entry of bank group 0
+  {
+    std::vector<char> real_tile(nslots, 0), real_chunk(op.chunk_val.size(), 0);
+    for (int i = 0; i < n; ++i) {
+      const int r = op.perm[i];
+      const int blk = i / 128, j = (i % 128) / 32, lane = i % 32;
+      for (int k = 0; k < indeg[r]; ++k) {
+        if (k < cap) real_tile[op.slice_off[blk] + (4 * k + j) * 32 + lane] = 1;
+        else real_chunk[static_cast<size_t>((k - cap) % op.lv) * op.nv_pad + op.ovf_start[i] + (k - cap) / op.lv] = 1;
+      }
+    }
+    auto fix = [](std::vector<int>& colv, const std::vector<char>& real, size_t base) {   // one aligned group of 8 lanes
+      int donor = -1;
+      for (size_t l = 0; l < 8; ++l) if (real[base + l]) { donor = colv[base + l]; break; }
+      if (donor < 0) return;
+      for (size_t l = 0; l < 8; ++l) if (!real[base + l]) colv[base + l] = donor;
+    };
+    for (size_t base = 0; base + 8 <= static_cast<size_t>(nslots); base += 8) fix(op.tile_col, real_tile, base);
+    for (size_t base = 0; base + 8 <= op.chunk_col.size(); base += 8) fix(op.chunk_col, real_chunk, base);
   }
   // every column any row reads must live in the ping-ponged prefix
   for (int slot = 0; slot < nslots; ++slot)

@@ -76,6 +76,11 @@ struct scr_ctx {
   int* d_corder = nullptr;
   int32_t* d_cbuf[2] = {nullptr, nullptr};
   size_t cshift_cap = 0, csize_cap = 0, corder_cap = 0, cbuf_cap[2] = {0, 0};
+  int32_t* d_covf = nullptr;                 // compact read-out: overflow triplets {local cell, gene, count}
+  unsigned long long* d_covf_count = nullptr;
+  size_t covf_cap = 0;
+  bool counts_smem_optin = false;
+  bool readout_only = false;                 // scr_set_genes: no network, only the state / read-out entry points work
 
   // RegNetInference front end
   double rank_kernel_ms = 0.0;
@@ -784,8 +789,10 @@ int ensure_buf(scr_ctx* ctx, P*& ptr, size_t& cap, size_t elems) {
 }
 void free_counts_scratch(scr_ctx* ctx) {
   cudaFree(ctx->d_cshift); cudaFree(ctx->d_csize); cudaFree(ctx->d_corder); cudaFree(ctx->d_cbuf[0]); cudaFree(ctx->d_cbuf[1]);
+  cudaFree(ctx->d_covf); cudaFree(ctx->d_covf_count);
   ctx->d_cshift = ctx->d_csize = nullptr; ctx->d_corder = nullptr; ctx->d_cbuf[0] = ctx->d_cbuf[1] = nullptr;
-  ctx->cshift_cap = ctx->csize_cap = ctx->corder_cap = ctx->cbuf_cap[0] = ctx->cbuf_cap[1] = 0;
+  ctx->d_covf = nullptr; ctx->d_covf_count = nullptr;
+  ctx->cshift_cap = ctx->csize_cap = ctx->corder_cap = ctx->cbuf_cap[0] = ctx->cbuf_cap[1] = ctx->covf_cap = 0;
 }
 
 int ensure_stage(scr_ctx* ctx, size_t elems) {
@@ -940,6 +947,32 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
     }
   }
   ctx->dense_mode = dense;
+  ctx->readout_only = false;
+  ctx->has_net = true;
+  return SCR_OK;
+}
+
+int scr_set_genes(scr_ctx* ctx, int32_t n) {
+  if (!ctx || n <= 0) return fail(ctx, SCR_E_ARG, "bad arguments");
+  if (ctx->cells > 0) return fail(ctx, SCR_E_STATE, "cells are already allocated");
+  PackedOperator op;
+  std::string err;
+  std::vector<int32_t> rowptr(static_cast<size_t>(n) + 1, 0);
+  if (!scr::pack_operator(n, 0, rowptr.data(), nullptr, nullptr, op, err, true, 128)) return fail(ctx, SCR_E_ARG, err);
+  ctx->op = std::move(op);
+  ctx->has_net = false;
+  ctx->dense_mode = false;
+  ctx->tab_bytes = ctx->w_bytes = 0;
+  if (!ctx->host_only) {
+    CK(cudaSetDevice(ctx->device));
+    free_network(ctx);
+    const PackedOperator& o = ctx->op;
+    CK(cudaMalloc(&ctx->d_perm, o.n_pad * sizeof(int)));
+    CK(cudaMalloc(&ctx->d_inv, o.n * sizeof(int)));
+    CK(cudaMemcpy(ctx->d_perm, o.perm.data(), o.n_pad * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_inv, o.inv.data(), o.n * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  ctx->readout_only = true;
   ctx->has_net = true;
   return SCR_OK;
 }
@@ -1085,6 +1118,7 @@ int scr_run_phase(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_
   NEED_GPU();
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (m < 0 || (m > 0 && (!cell_ids || !steps)) || !proj || !cnst) return fail(ctx, SCR_E_ARG, "bad arguments");
+  if (ctx->readout_only) return fail(ctx, SCR_E_STATE, "read-out context (scr_set_genes): no network to step with");
   if (m == 0) return SCR_OK;
   if (ctx->dense_mode)
     return run_phase_dense(ctx, m, cell_ids, steps, step_base, proj, cnst, dt, sigma, mu, seed, noise, noise_steps);
@@ -1100,6 +1134,7 @@ int scr_probe(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* 
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (k <= 0 || !sample_ids || !proj || !cnst || !iters_out || max_iter <= 0 || avg_num <= 0)
     return fail(ctx, SCR_E_ARG, "bad arguments");
+  if (ctx->readout_only) return fail(ctx, SCR_E_STATE, "read-out context (scr_set_genes): no network to step with");
   if (ctx->dense_mode && scr::env_int("SCR_DENSE_PROBE", 1))
     return probe_dense(ctx, k, sample_ids, w_div, proj, cnst, dt, sigma, mu, thresh, max_iter, avg_num, seed, stream, noise, iters_out, normdiff_out);
   if (ctx->prec == SCR_F64)
@@ -1112,16 +1147,19 @@ int scr_gene_sums(scr_ctx* ctx, double* sums_out) {
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (!sums_out) return fail(ctx, SCR_E_ARG, "null output");
   const int n = ctx->op.n, n_pad = ctx->op.n_pad;
-  int rc = ensure_stage(ctx, n_pad);
+  const int rows = static_cast<int>(std::min<int64_t>(ctx->cells, 256));
+  int rc = ensure_stage(ctx, static_cast<size_t>(rows + 1) * n_pad);   // [0, n_pad): sums; then rows x n_pad partials
   if (rc) return rc;
-  CK(cudaMemsetAsync(ctx->d_stage, 0, n_pad * sizeof(double), ctx->stream));
-  dim3 grid((n_pad + 127) / 128, static_cast<unsigned>(std::min<int64_t>(ctx->cells, 2048)));
+  double* d_partial = ctx->d_stage + n_pad;
+  dim3 grid((n_pad + 127) / 128, static_cast<unsigned>(rows));
   if (ctx->prec == SCR_F64)
-    scr::gene_sums_kernel<double><<<grid, 128, 0, ctx->stream>>>(static_cast<const double*>(ctx->d_state), n_pad, ctx->cells, n_pad, ctx->d_stage);
+    scr::gene_sums_kernel<double><<<grid, 128, 0, ctx->stream>>>(static_cast<const double*>(ctx->d_state), n_pad, ctx->cells, n_pad, d_partial);
   else
-    scr::gene_sums_kernel<float><<<grid, 128, 0, ctx->stream>>>(static_cast<const float*>(ctx->d_state), n_pad, ctx->cells, n_pad, ctx->d_stage);
+    scr::gene_sums_kernel<float><<<grid, 128, 0, ctx->stream>>>(static_cast<const float*>(ctx->d_state), n_pad, ctx->cells, n_pad, d_partial);
   CK(cudaGetLastError());
-  ctx->launches++;
+  scr::gene_sums_finish_kernel<<<(n_pad + 127) / 128, 128, 0, ctx->stream>>>(d_partial, rows, n_pad, ctx->d_stage);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
   std::vector<double> h(n_pad);
   CK(cudaMemcpyAsync(h.data(), ctx->d_stage, n_pad * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1129,15 +1167,21 @@ int scr_gene_sums(scr_ctx* ctx, double* sums_out) {
   return SCR_OK;
 }
 
-int scr_counts_range(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const double* shift, double exp_scale,
-                     const double* size_factors, uint64_t seed, const double* uniforms, int32_t draws_per_entry,
-                     int32_t* counts_out, int out_on_device, double* lambda_out) {
+namespace {
+// shared body of scr_counts_range / scr_counts_compact.  out_dtype: SCR_COUNT_I32 / _U16 / _U8 (bytes per entry 4 / 2 / 1)
+int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const double* shift, double exp_scale,
+                const double* size_factors, uint64_t seed, const double* uniforms, int32_t draws_per_entry,
+                void* counts_out, int out_on_device, double* lambda_out, int out_dtype, int64_t* ovf_out,
+                int64_t ovf_cap, int64_t* ovf_count_out) {
   NEED_GPU();
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (!shift || !size_factors || !counts_out) return fail(ctx, SCR_E_ARG, "bad arguments");
+  if (out_dtype != SCR_COUNT_I32 && out_dtype != SCR_COUNT_U16 && out_dtype != SCR_COUNT_U8) return fail(ctx, SCR_E_ARG, "bad count dtype");
   if (cell_begin < 0 || cell_count < 0 || cell_begin + cell_count > ctx->cells) return fail(ctx, SCR_E_ARG, "cell range out of bounds");
+  if (ovf_count_out) *ovf_count_out = 0;
   if (cell_count == 0) return SCR_OK;
   const int n = ctx->op.n;
+  const size_t esz = out_dtype == SCR_COUNT_I32 ? 4 : (out_dtype == SCR_COUNT_U16 ? 2 : 1);
   const int64_t cells = cell_count;   // rows of this call: local slots [cell_begin, cell_begin + cells)
   double *d_uni = nullptr, *d_lam = nullptr;   // parity / debug inputs only: allocated per call
   int rc = SCR_OK;
@@ -1149,14 +1193,28 @@ int scr_counts_range(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const
   if ((rc = ensure_buf(ctx, ctx->d_corder, ctx->corder_cap, static_cast<size_t>(n)))) return rc;
   if ((rc = ensure_buf(ctx, ctx->d_cshift, ctx->cshift_cap, static_cast<size_t>(n)))) return rc;
   if ((rc = ensure_buf(ctx, ctx->d_csize, ctx->csize_cap, static_cast<size_t>(cells)))) return rc;
+  const unsigned long long dev_ovf_cap = esz < 4 ? static_cast<unsigned long long>(std::max<int64_t>(ovf_cap, 0)) : 0ULL;
+  if (esz < 4) {
+    if ((rc = ensure_buf(ctx, ctx->d_covf, ctx->covf_cap, static_cast<size_t>(3 * dev_ovf_cap + 3)))) return rc;
+    if (!ctx->d_covf_count) CK(cudaMalloc(&ctx->d_covf_count, sizeof(unsigned long long)));
+  }
   double *d_shift = ctx->d_cshift, *d_size = ctx->d_csize;
   int* d_order = ctx->d_corder;
-  int32_t** d_buf = ctx->d_cbuf;
 #define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
+  if (n * sizeof(int32_t) > 48 * 1024 && !ctx->counts_smem_optin) {   // staging row beyond the default 48 KB of dynamic shared memory
+    if (n * sizeof(int32_t) > static_cast<size_t>(ctx->smem_optin)) return fail(ctx, SCR_E_RESOURCE, "count read-out: n too large for the per-cell staging row");
+#define SCR_OPTIN(T, FAST, OUT) CKC(cudaFuncSetAttribute(scr::counts_kernel<T, FAST, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin))
+#define SCR_OPTIN_ALL(OUT) SCR_OPTIN(float, true, OUT); SCR_OPTIN(float, false, OUT); SCR_OPTIN(double, true, OUT); SCR_OPTIN(double, false, OUT)
+    SCR_OPTIN_ALL(int32_t); SCR_OPTIN_ALL(uint16_t); SCR_OPTIN_ALL(uint8_t);
+#undef SCR_OPTIN_ALL
+#undef SCR_OPTIN
+    ctx->counts_smem_optin = true;
+  }
   CKC(cudaMemcpyAsync(d_order, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemcpyAsync(d_shift, shift, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemcpyAsync(d_size, size_factors, cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));   // entry r <-> slot cell_begin + r
   CKC(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+  if (esz < 4) CKC(cudaMemsetAsync(ctx->d_covf_count, 0, sizeof(unsigned long long), ctx->stream));
   if (uniforms) {
     const size_t cnt = static_cast<size_t>(cells) * n * draws_per_entry;
     CKC(cudaMalloc(&d_uni, cnt * sizeof(double)));
@@ -1170,35 +1228,44 @@ int scr_counts_range(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const
   // free-running stream without a lambda dump: float32 screening of the lambda < 10 sampler (identical integers,
   // aux_kernels.cuh); SCR_COUNTS_EXACT=1 forces the float64 sampler for every entry (A/B tests)
   const bool fast = !uniforms && !lambda_out && scr::env_int("SCR_COUNTS_EXACT", 0) == 0;
-  auto launch = [&](int64_t c0, int64_t cnt, int32_t* out, double* lam) -> cudaError_t {
+  auto launch = [&](int64_t c0, int64_t cnt, void* out, double* lam) -> cudaError_t {
     const double* uni_by_slot = d_uni ? d_uni - cell_begin * n * static_cast<int64_t>(draws_per_entry) : nullptr;
-#define SCR_LAUNCH_COUNTS(T, FAST) \
-    scr::counts_kernel<T, FAST><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>( \
+#define SCR_LAUNCH_COUNTS(T, FAST, OUT) \
+    scr::counts_kernel<T, FAST, OUT><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>( \
         static_cast<const T*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, cell_begin + c0, d_shift, exp_scale, \
-        size_by_slot, crk, ctx->cell_offset, uni_by_slot, draws_per_entry, out, lam, ctx->d_err)
-    if (ctx->prec == SCR_F64) { if (fast) SCR_LAUNCH_COUNTS(double, true); else SCR_LAUNCH_COUNTS(double, false); }
-    else                      { if (fast) SCR_LAUNCH_COUNTS(float, true);  else SCR_LAUNCH_COUNTS(float, false); }
+        size_by_slot, crk, ctx->cell_offset, uni_by_slot, draws_per_entry, static_cast<OUT*>(out), lam, ctx->d_err, \
+        ctx->d_covf, dev_ovf_cap, ctx->d_covf_count)
+#define SCR_LAUNCH_PREC(OUT) \
+    if (ctx->prec == SCR_F64) { if (fast) SCR_LAUNCH_COUNTS(double, true, OUT); else SCR_LAUNCH_COUNTS(double, false, OUT); } \
+    else                      { if (fast) SCR_LAUNCH_COUNTS(float, true, OUT);  else SCR_LAUNCH_COUNTS(float, false, OUT); }
+    if (out_dtype == SCR_COUNT_I32) { SCR_LAUNCH_PREC(int32_t) }
+    else if (out_dtype == SCR_COUNT_U16) { SCR_LAUNCH_PREC(uint16_t) }
+    else { SCR_LAUNCH_PREC(uint8_t) }
+#undef SCR_LAUNCH_PREC
 #undef SCR_LAUNCH_COUNTS
     ctx->launches++;
     return cudaGetLastError();
   };
+  unsigned char* out_bytes = static_cast<unsigned char*>(counts_out);
   if (out_on_device) {
     CKC(launch(0, cells, counts_out, d_lam));
   } else {
     // double-buffered: the Poisson kernel of chunk i+1 overlaps the D2H copy of chunk i
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(cells, (256LL << 20) / (static_cast<int64_t>(n) * 4)));
-    if ((rc = ensure_buf(ctx, ctx->d_cbuf[0], ctx->cbuf_cap[0], static_cast<size_t>(chunk) * n))) { cleanup(); return rc; }
-    if (cells > chunk && (rc = ensure_buf(ctx, ctx->d_cbuf[1], ctx->cbuf_cap[1], static_cast<size_t>(chunk) * n))) { cleanup(); return rc; }
+    const size_t words = (static_cast<size_t>(chunk) * n * esz + 3) / 4;
+    if ((rc = ensure_buf(ctx, ctx->d_cbuf[0], ctx->cbuf_cap[0], words))) { cleanup(); return rc; }
+    if (cells > chunk && (rc = ensure_buf(ctx, ctx->d_cbuf[1], ctx->cbuf_cap[1], words))) { cleanup(); return rc; }
     int used[2] = {0, 0};
     int64_t ci = 0;
     for (int64_t c0 = 0; c0 < cells; c0 += chunk, ++ci) {
       const int b = static_cast<int>(ci & 1);
       const int64_t cnt = std::min(chunk, cells - c0);
       if (used[b]) CKC(cudaStreamWaitEvent(ctx->stream, ctx->ev_c[b], 0));
-      CKC(launch(c0, cnt, d_buf[b], d_lam ? d_lam + c0 * n : nullptr));
+      CKC(launch(c0, cnt, ctx->d_cbuf[b], d_lam ? d_lam + c0 * n : nullptr));
       CKC(cudaEventRecord(ctx->ev_k[b], ctx->stream));
       CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[b], 0));
-      CKC(cudaMemcpyAsync(counts_out + c0 * n, d_buf[b], static_cast<size_t>(cnt) * n * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      CKC(cudaMemcpyAsync(out_bytes + static_cast<size_t>(c0) * n * esz, ctx->d_cbuf[b], static_cast<size_t>(cnt) * n * esz,
+                          cudaMemcpyDeviceToHost, ctx->copy_stream));
       CKC(cudaEventRecord(ctx->ev_c[b], ctx->copy_stream));
       used[b] = 1;
     }
@@ -1208,10 +1275,47 @@ int scr_counts_range(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const
   if (lambda_out) CKC(cudaMemcpy(lambda_out, d_lam, static_cast<size_t>(cells) * n * sizeof(double), cudaMemcpyDeviceToHost));
   int herr = 0;
   CKC(cudaMemcpy(&herr, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  unsigned long long novf = 0;
+  if (esz < 4) {
+    CKC(cudaMemcpy(&novf, ctx->d_covf_count, sizeof(novf), cudaMemcpyDeviceToHost));
+    const unsigned long long take = std::min(novf, dev_ovf_cap);
+    if (take > 0 && ovf_out) {
+      std::vector<int32_t> h(3 * take);
+      CKC(cudaMemcpy(h.data(), ctx->d_covf, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      // the kernel appends in arrival order: sort by (cell, gene) so that the list is deterministic
+      std::vector<size_t> idx(take);
+      for (size_t i = 0; i < take; ++i) idx[i] = i;
+      std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) {
+        return h[3 * a] != h[3 * b] ? h[3 * a] < h[3 * b] : h[3 * a + 1] < h[3 * b + 1];
+      });
+      for (size_t i = 0; i < take; ++i) {
+        ovf_out[3 * i] = static_cast<int64_t>(h[3 * idx[i]]) - cell_begin;   // row of THIS call's output
+        ovf_out[3 * i + 1] = h[3 * idx[i] + 1];
+        ovf_out[3 * i + 2] = h[3 * idx[i] + 2];
+      }
+    }
+    if (ovf_count_out) *ovf_count_out = static_cast<int64_t>(novf);
+  }
 #undef CKC
   cleanup();
   if (herr) return fail(ctx, SCR_E_DRAWS, "supplied uniforms exhausted (raise draws_per_entry)");
+  if (novf > dev_ovf_cap) return fail(ctx, SCR_E_RESOURCE, "overflow list too small: " + std::to_string(novf) + " counts reach the escape code (call again with that capacity)");
   return rc;
+}
+}  // namespace
+
+int scr_counts_range(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const double* shift, double exp_scale,
+                     const double* size_factors, uint64_t seed, const double* uniforms, int32_t draws_per_entry,
+                     int32_t* counts_out, int out_on_device, double* lambda_out) {
+  return counts_impl(ctx, cell_begin, cell_count, shift, exp_scale, size_factors, seed, uniforms, draws_per_entry, counts_out,
+                     out_on_device, lambda_out, SCR_COUNT_I32, nullptr, 0, nullptr);
+}
+
+int scr_counts_compact(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const double* shift, double exp_scale,
+                       const double* size_factors, uint64_t seed, int out_dtype, void* counts_out, int out_on_device,
+                       int64_t* overflow_out, int64_t overflow_capacity, int64_t* overflow_count) {
+  return counts_impl(ctx, cell_begin, cell_count, shift, exp_scale, size_factors, seed, nullptr, 0, counts_out, out_on_device,
+                     nullptr, out_dtype, overflow_out, overflow_capacity, overflow_count);
 }
 
 int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double* size_factors, uint64_t seed,

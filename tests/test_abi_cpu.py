@@ -67,18 +67,18 @@ def test_packed_operator_matches_dense(n, seed, heavy, prec):
 
 @pytest.mark.parametrize("n,seed,heavy", [(129, 3, 2), (1000, 5, 0), (3000, 6, 2)])
 def test_bank_aware_gene_order_is_a_valid_packing(n, seed, heavy):
-    """SCR_BANK_OPT=1 (opt-in): genes exchanged inside aligned groups of 8 positions to lower the modelled shared-memory
-    bank conflicts of the gather.  The packed operator must still be W exactly, with the same block structure, and the
-    model must not get worse."""
+    """The default gene order exchanges genes inside aligned groups of 8 positions to lower the modelled shared-memory
+    bank conflicts of the gather (SCR_BANK_OPT=0 switches that off).  The packed operator must still be W exactly, with
+    the same block structure, and the model must not get worse."""
     W = power_law_like(n, seed, heavy)
-    base = engine.Engine(device=-1)
-    base.set_network(W)
-    os.environ["SCR_BANK_OPT"] = "1"
+    os.environ["SCR_BANK_OPT"] = "0"
     try:
-        eng = engine.Engine(device=-1)
-        eng.set_network(W)
+        base = engine.Engine(device=-1)
+        base.set_network(W)
     finally:
         del os.environ["SCR_BANK_OPT"]
+    eng = engine.Engine(device=-1)
+    eng.set_network(W)
     x = np.random.RandomState(7).randn(n)
     ref = W @ x
     assert np.allclose(eng.host_matvec(x), ref, rtol=1e-12, atol=1e-12 * max(1.0, np.abs(ref).max()))

@@ -58,7 +58,8 @@ def engine_on(net, prec):
     e.set_network(net["gc"])
     e.alloc_cells(CELLS, 2 ** 32 + 3)                        # odd offset: parity placement must use GLOBAL ids
     lay = e.layout()
-    assert lay["groups_per_cta"] == 2 and not lay["operator_in_smem"] and lay["operator_prefix_bytes"] > 0
+    if prec == "f32":   # two cell groups per CTA and a partly resident operator, as in bench.py (float64 rows leave room for one group)
+        assert lay["groups_per_cta"] == 2 and not lay["operator_in_smem"] and lay["operator_prefix_bytes"] > 0
     if net["exponent"] == 2.05:
         assert lay["chunks"] > 300                           # max in-degree ~300: many long-row chunks
     return e
