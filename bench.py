@@ -4,17 +4,20 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
 
-Workload (BASELINE.json config 5): SimulatedPowerLaw network, n = 3000 genes, powerLawExponent 2.5
-(nnz ~4.6k), alpha from the reference's own search rule run on the GPU, the 4-leaf / 7-type lineage
-tree of config 2 (parents [-1,0,0,1,1,2,2]), 1,000,000 cells PER GPU (weak scaling), default
-dt / noise / thresholds of MatriSeq.py:546-554, then the transformData count read-out
-(MatriSeq.py:816-891).  One "step" = one full pass: convergence probe per tree node, ragged
-stepping of members and descendants, per-gene mean all-reduce, Poisson counts and -- for N > 1 --
-the NCCL gather of the count matrix to rank 0.  metric = cell-steps/s = sum of
-totalCellIterations over all cells / time.
+Workload (BASELINE.json config 5): SimulatedPowerLaw network, n = 3000 genes, powerLawExponent 2.5 (nnz ~4.6k), divided by
+alpha = 0.4 (what the reference's own search rule, MatriSeq.py:368-500, returns for this seeded network: re-derived on the
+GPU in `extra.alpha_search`), the 4-leaf / 7-type lineage tree of config 2 (parents [-1,0,0,1,1,2,2]), 1,000,000 cells PER
+GPU (weak scaling), default dt / noise / thresholds of MatriSeq.py:546-554, then the transformData count read-out
+(MatriSeq.py:816-891).  One "step" = one full pass: convergence probe per tree node, ragged stepping of members and
+descendants, per-gene mean all-reduce, Poisson counts into this rank's shard of the count matrix (unsigned bytes + overflow
+list; `--gather` additionally collects the shards on rank 0 with NCCL).  metric = cell-steps/s = sum of totalCellIterations
+over all cells / time.
 
-`value`: inputs resident in HBM.  `e2e`: the same pass through the C ABI with HOST buffers
-(network, initial state and schedules copied in, count matrix copied out to pinned memory).
+`value`: inputs resident in HBM.  `e2e`: the same pass through the C ABI with HOST buffers (network, initial state and
+schedules copied in, this rank's count shard copied out to pinned memory).  `extra`: the other paths north_star names,
+measured after the headline in the same process -- TRRUST and the reference's default exponent 2.05 on the sparse stepper,
+the float64 parity context, config c4 on the tcgen05 3xTF32 stepper (with a TF32 matmul timed in-run as its denominator),
+the count kernel alone, the alpha search, and (N > 1) the strong-scaling point: 10^6 cells in TOTAL split over the ranks.
 """
 import argparse
 import json
@@ -36,7 +39,9 @@ CONST_PROPS = [0.05] * 7
 GENES = 3000
 EXPONENT = 2.5
 HBM_FALLBACK_GBS = 6650.0
-ALPHA_SEARCHED = 0.4   # what findOptimalAlpha returns for this seeded network (our arm re-derives it on the GPU)
+# network divisors: what findOptimalAlpha returned for the seeded networks in round 1 (profiles/r1_final_configs_c1_c4.jsonl;
+# powerlaw is re-derived in extra.alpha_search); powerlaw205 simply reuses the contract value (a rate measurement)
+ALPHA = {"powerlaw": 0.4, "trrust": 0.1, "powerlaw205": 0.4, "dense_c4": 2.21}
 
 
 def parse():
@@ -47,48 +52,54 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=1000000, help="cells per GPU")
     ap.add_argument("--genes", type=int, default=GENES)
-    ap.add_argument("--network", default="powerlaw", choices=["powerlaw", "trrust"],
-                    help="powerlaw = the contract workload; trrust = the same pass on the TRRUST network (n = 2895)")
-    ap.add_argument("--alpha", type=float, default=None, help="skip the search")
+    ap.add_argument("--network", default="powerlaw", choices=["powerlaw", "trrust", "powerlaw205"],
+                    help="powerlaw = the contract workload; trrust / powerlaw205 = the same pass on those networks")
+    ap.add_argument("--alpha", type=float, default=None, help="override the network divisor")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--extra", default="trrust,powerlaw205,f64,dense_c4,counts,alpha_search,strong",
+                    help="comma-separated extra blocks to measure after the headline")
+    ap.add_argument("--gather", action="store_true", help="also gather the count shards on rank 0 with NCCL (N > 1)")
+    ap.add_argument("--counts-dtype", default="uint8", choices=["uint8", "uint16", "int32"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------
-# workload construction (host, deterministic, identical on every rank)
+# workload construction (host, deterministic, identical on every rank and for every N)
 # ---------------------------------------------------------------------------------------------
 def build_network(n, kind="powerlaw"):
-    """kind "powerlaw" (the default workload) or "trrust" (the other network BASELINE.json's config 5 names;
-    n is then TRRUST's own 2895, MS:99-100)."""
+    """kind "powerlaw" (the contract workload), "powerlaw205" (the reference's default exponent), "trrust" (n is then
+    TRRUST's own 2895, MS:99-100) or "dense_c4" (Random, networkSparsity 0.5)."""
     from scrutiny_b200 import network
     np.random.seed(1337)
     random.seed(1337)
     if kind == "trrust":
         return network.generate_gene_correlation_matrix(0, "TRRUST")
-    gc, tf = network.generate_gene_correlation_matrix(n, "SimulatedPowerLaw", powerLawExponent=EXPONENT)
-    return gc, tf
+    if kind == "dense_c4":
+        return network.generate_gene_correlation_matrix(n, "Random", networkSparsity=0.5)
+    return network.generate_gene_correlation_matrix(n, "SimulatedPowerLaw", powerLawExponent=EXPONENT if kind == "powerlaw" else 2.05)
 
 
-def build_tree(n, cells, tf):
+def build_tree(n, cells, tf, parents=PARENTS, shares=SHARES, const_props=CONST_PROPS):
     """Same structure formCellTypeTree builds (MatriSeq.py:175-297): every cell gets its final type
     up front (a random permutation split by SHARES), proj/const inherited down the tree."""
     from scrutiny_b200.MatriSeq import getNextProjConst
     from scrutiny_b200.lineage import Tree
-    counts = [int(round(s * cells)) for s in SHARES]
+    counts = [int(round(s * cells)) for s in shares]
     counts[-1] = cells - sum(counts[:-1])
     perm = np.random.permutation(cells)
     bounds = np.cumsum([0] + counts)
-    members = [np.sort(perm[bounds[t]:bounds[t + 1]]) for t in range(len(PARENTS))]
+    members = [np.sort(perm[bounds[t]:bounds[t + 1]]) for t in range(len(parents))]
     tree = Tree()
     tree.add_head(-1, np.zeros(0, dtype=np.int64), np.zeros(n), np.ones(n), 0)
 
     def attach(parent, proj_up, const_up):
         below = []
-        for t in [i for i, p in enumerate(PARENTS) if p == parent]:
-            proj, const = getNextProjConst(n, proj_up, const_up, CONST_PROPS[t], tf)
+        for t in [i for i, p in enumerate(parents) if p == parent]:
+            proj, const = getNextProjConst(n, proj_up, const_up, const_props[t], tf)
             tree.add_node(t, members[t], const, proj, 0, parent)
             below += attach(t, proj, const) + [members[t]]
         tree[parent].setChildCellTypeMembers(np.concatenate(below) if below else np.zeros(0, dtype=np.int64))
@@ -98,17 +109,38 @@ def build_tree(n, cells, tf):
     return tree
 
 
-def search_alpha(gc, tree, x0, n):
-    """findOptimalAlpha (MatriSeq.py:368-500) on the GPU over 50 sampled copies of the shared
-    initial state; setup, not timed."""
+def build_workload(n, kind, cells):
+    """(gc, tf, x0, tree): x0 is drawn BEFORE the cell permutation, so network, initial state and node vectors do not
+    depend on the number of cells / ranks."""
+    gc, tf = build_network(n, kind)
+    x0 = 2.0 * np.random.rand(gc.shape[0]) - 1.0
+    single = kind == "dense_c4"
+    tree = build_tree(gc.shape[0], cells, tf, *(([-1], [1.0], [0.0]) if single else (PARENTS, SHARES, CONST_PROPS)))
+    return gc, tf, x0, tree
+
+
+def search_alpha(gc, tree, x0, n, device):
+    """findOptimalAlpha (MatriSeq.py:368-500) on the GPU over 50 sampled copies of the shared initial state."""
     import scrutiny_b200.MatriSeq as ms
     st_np, st_py = np.random.get_state(), random.getstate()
-    ms.init(outputDir=None, seed=1337, verbose=False, device=int(os.environ.get("LOCAL_RANK", 0)))
+    ms.init(outputDir=None, seed=1337, verbose=False, device=device)
     states = np.repeat(x0[:, None], 64, axis=1)
+    t0 = time.perf_counter()
     alpha = ms.findOptimalAlpha(n, gc, tree, states, numToSample=50)
+    dt = time.perf_counter() - t0
+    ms.init(outputDir=None, seed=1337, verbose=False, device=device)      # drops the cached context
     np.random.set_state(st_np)
     random.setstate(st_py)
-    return alpha
+    return alpha, dt
+
+
+def workload_config(args, n, nnz, alpha):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    net = {"trrust": "TRRUST n=%d" % n, "powerlaw": "SimulatedPowerLaw n=%d powerLawExponent=%.1f" % (n, EXPONENT),
+           "powerlaw205": "SimulatedPowerLaw n=%d powerLawExponent=2.05" % n}[args.network]
+    return {"workload": "c5: MatriSeq %s, %d cells per GPU, 7-type/4-leaf lineage tree, count sampling" % (net, args.cells),
+            "genes": n, "nnz": nnz, "alpha": round(float(alpha), 4), "cells_per_gpu": args.cells, "tree_parents": PARENTS,
+            "l2": "inputs exceed L2 (state %.1f GB per GPU)" % (args.cells * (-(-n // 128) * 128) * 4 / 1e9)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -133,6 +165,7 @@ class ClockSampler:
             self.thread.start()
         except OSError:
             self.proc = None
+        return self
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -209,7 +242,7 @@ def cpu_baseline(gc, proj, const, x0, seconds):
         pool.map(_cpu_work, [(100 + w, cells_each, iters) for w in range(workers)])
         wall = time.perf_counter() - t0
     steps = workers * cells_each * iters
-    return {"value": steps / wall, "unit": "cell-steps/s", "cores": workers, "kind": "port",
+    return {"value": steps / wall, "unit": "cell-steps/s", "cores": workers, "kind": "port", "wall_s": wall,
             "sample": "%d cells x %d iterations of findCellNextState (dense float64 gemv, n=%d) on %d processes, "
                       "%.1f s wall; single-process rate %.0f cell-steps/s" % (workers * cells_each, iters, gc.shape[0],
                                                                           workers, wall, 1.0 / per_step)}
@@ -218,43 +251,117 @@ def cpu_baseline(gc, proj, const, x0, seconds):
 def run_reference(args, rank):
     if rank != 0:
         return
-    gc, tf = build_network(args.genes, args.network)
+    gc, tf, x0, tree = build_workload(args.genes, args.network, 1000)
     n = gc.shape[0]
-    tree = build_tree(n, 1000, tf)
-    alpha = args.alpha if args.alpha else (0.1 if args.network == "trrust" else ALPHA_SEARCHED)
+    alpha = args.alpha if args.alpha else ALPHA[args.network]
+    nnz = int(np.count_nonzero(gc))
     gc = gc / alpha
-    x0 = 2.0 * np.random.rand(n) - 1.0
-    vals, infos = [], None
+    vals, walls, infos = [], [], None
     for i in range(args.warmup + args.steps):
         info = cpu_baseline(gc, tree[0].proj, tree[0].const, x0, max(2.0, args.cpu_seconds / 2))
         if i >= args.warmup:
             vals.append(info["value"])
+            walls.append(info["wall_s"])
             infos = info
     value = float(np.mean(vals))
     infos["value"] = value
     line = {"impl": "reference", "metric": "cell_steps_per_sec", "value": value, "unit": "cell-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": float(np.mean(walls)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, n, int(np.count_nonzero(gc)), alpha, note="CPU sample of the same network"),
+            "config": workload_config(args, n, nnz, alpha),
+            "note": "each step is a bounded CPU sample of the same network (cpu_baseline.sample); rank 0 only",
             "cpu_baseline": infos,
             "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, n, nnz, alpha, note=None):
-    net = "TRRUST n=%d" % n if args.network == "trrust" else "SimulatedPowerLaw n=%d powerLawExponent=%.1f" % (n, EXPONENT)
-    cfg = {"workload": "c5: MatriSeq %s, %d cells per GPU, 7-type/4-leaf lineage tree, count sampling" % (net, args.cells),
-           "genes": n, "nnz": nnz, "alpha": alpha, "cells_per_gpu": args.cells, "tree_parents": PARENTS,
-           "l2": "inputs exceed L2 (state %.1f GB per GPU)" % (args.cells * (-(-n // 128) * 128) * 4 / 1e9)}
-    if note:
-        cfg["note"] = note
-    return cfg
-
-
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+class Rig:
+    """One rank's engine + scheduler for a workload, with the timing loop shared by the headline and the extra blocks."""
+
+    def __init__(self, env, kind, cells_per_gpu, prec="f32", alpha=None, n=GENES):
+        from scrutiny_b200 import engine as eng_mod
+        from scrutiny_b200.network import dense_to_csr
+        from scrutiny_b200.simulate import LineageSimulation
+        self.env = env
+        world, rank = env["world"], env["rank"]
+        self.kind, self.per_gpu, self.cells = kind, cells_per_gpu, cells_per_gpu * world
+        self.gc, self.tf, self.x0, self.tree = build_workload(n, kind, self.cells)
+        self.n = self.gc.shape[0]
+        self.nnz = int(np.count_nonzero(self.gc))
+        self.alpha = alpha if alpha else ALPHA[kind]
+        self.csr = dense_to_csr(self.gc / self.alpha)
+        lo = rank * cells_per_gpu
+        self.eng = eng_mod.Engine(env["local"], prec)
+        self.eng.set_network(csr=self.csr, n=self.n)
+        self.eng.alloc_cells(cells_per_gpu, lo)
+        self.sim = LineageSimulation(self.eng, self.cells, lo, lo + cells_per_gpu, comm=env["comm"], seed=1337)
+        self.sim.prepare(self.tree)
+        self.layout = self.eng.layout()
+        self.prec = prec
+
+    def close(self):
+        self.eng.close()
+
+    def timed(self, steps, warmup, seed0, clocks=True, **run_kw):
+        """W untimed + K timed passes (states reset outside the timed region, barrier + synchronize on both sides, max over
+        ranks).  Returns dict(value, ms_per_step, kernel stats ...)."""
+        import torch
+        env, eng, sim = self.env, self.eng, self.sim
+        for w in range(warmup):
+            eng.set_states_broadcast(self.x0)
+            sim.run_all(self.tree, seed=seed0 + w, **run_kw)
+            env["after_pass"]()
+        env["barrier"]()
+        sampler = ClockSampler(env["local"]).start() if clocks else None
+        if clocks:
+            time.sleep(0.3)
+        launches0 = eng.launch_count()
+        eng.step_kernel_stats(reset=True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total_steps = local_steps = 0
+        elapsed_ms = 0.0
+        res = None
+        for k in range(steps):
+            eng.set_states_broadcast(self.x0)                            # reset, outside the timed region
+            env["barrier"]()
+            ev0.record()
+            t0 = time.perf_counter()
+            res = sim.run_all(self.tree, seed=seed0 + 1000 + k, **run_kw)
+            env["after_pass"]()
+            env["barrier"]()
+            ev1.record()
+            torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            elapsed_ms += max(ev0.elapsed_time(ev1), wall_ms)
+            total_steps += res["global_cell_steps"]
+            local_steps += res["local_cell_steps"]
+        out = {"clocks": sampler.stop() if sampler else None}
+        out["launches"] = eng.launch_count() - launches0 - steps        # minus the untimed reset kernels
+        kernel_ms, kernel_launches = eng.step_kernel_stats()
+        elapsed_ms = env["max_over_ranks"](elapsed_ms)
+        out.update(value=total_steps / (elapsed_ms / 1e3), ms_per_step=elapsed_ms / steps, elapsed_ms=elapsed_ms,
+                   total_steps=total_steps, local_steps=local_steps, kernel_ms=kernel_ms, kernel_launches=int(kernel_launches),
+                   last=res, node_iterations=dict(sim.node_iterations))
+        return out
+
+    def sparse_roofline(self, t, peak, peak_source):
+        achieved = (t["local_steps"] * 8.0 * self.n) / (t["kernel_ms"] / 1e3) / 1e9 if t["kernel_ms"] > 0 else None
+        esz = 8 if self.prec == "f64" else 4
+        if achieved and esz == 8:
+            achieved *= 2
+        return {"bound": "hbm", "kernel": "scr::step_kernel<%s> (persistent stepper)" % ("double" if esz == 8 else "float"),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "peak_source": peak_source, "algorithmic_bytes_per_cell_step": 2 * esz * self.n,
+                "cell_steps_per_launch": t["local_steps"] / max(t["kernel_launches"], 1),
+                "kernel_ms_per_launch": t["kernel_ms"] / max(t["kernel_launches"], 1), "kernel_launches": t["kernel_launches"],
+                "kernel_share_of_step": t["kernel_ms"] / t["elapsed_ms"] if t["elapsed_ms"] else None,
+                "kernel_cell_steps_per_s": t["local_steps"] / (t["kernel_ms"] / 1e3) if t["kernel_ms"] > 0 else None}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -266,8 +373,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from scrutiny_b200 import engine as eng_mod
-    from scrutiny_b200.simulate import Comm, LineageSimulation
+    from scrutiny_b200.simulate import Comm
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -275,149 +381,246 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     comm = Comm(device=dev)
 
-    per_gpu = args.cells
-    cells = per_gpu * world
-    gc, tf = build_network(args.genes, args.network)
-    n = gc.shape[0]
-    nnz = int(np.count_nonzero(gc))
-    tree = build_tree(n, cells, tf)
-    x0 = 2.0 * np.random.rand(n) - 1.0
-    alpha = args.alpha if args.alpha else search_alpha(gc, tree, x0, n)
-    gcs = gc / alpha
-    from scrutiny_b200.network import dense_to_csr
-    csr = dense_to_csr(gcs)
-
-    lo, hi = rank * per_gpu, (rank + 1) * per_gpu
-    eng = eng_mod.Engine(local, "f32")
-    eng.set_network(csr=csr, n=n)
-    eng.alloc_cells(per_gpu, lo)
-    sim = LineageSimulation(eng, cells, lo, hi, comm=comm, seed=1337)
-    sim.prepare(tree)
-    counts_dev = torch.empty((per_gpu, n), dtype=torch.int32, device=dev)
-    gathered = [torch.empty((per_gpu, n), dtype=torch.int32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
-    layout = eng.layout()
-
-    # the count matrix is sampled in row blocks; each finished block is handed to NCCL at once (asynchronous gather to
-    # rank 0), so the transfer of block i runs under the sampling of block i+1
-    COUNT_BLOCKS = 8 if world > 1 else 1
-    pending = []
-
-    def gather_block(r0, r1):
-        if world > 1:
-            pending.append(dist.gather(counts_dev[r0:r1], [g[r0:r1] for g in gathered] if rank == 0 else None,
-                                       dst=0, async_op=True))
-
-    def gather_counts():
-        for w in pending:
-            w.wait()
-        pending.clear()
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up ----
-    for w in range(args.warmup):
-        eng.set_states_broadcast(x0)
-        sim.run_all(tree, counts_dev_ptr=counts_dev.data_ptr(), seed=1337 + w, counts_blocks=COUNT_BLOCKS,
-                    on_counts_block=gather_block)
-        gather_counts()
-    barrier()
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- timed: resident inputs ----
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
-    launches0 = eng.launch_count()
-    eng.step_kernel_stats(reset=True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    total_steps = 0
-    local_steps = 0
-    elapsed_ms = 0.0
-    for k in range(args.steps):
-        eng.set_states_broadcast(x0)                            # reset, outside the timed region
-        barrier()
-        ev0.record()
-        t0 = time.perf_counter()
-        res = sim.run_all(tree, counts_dev_ptr=counts_dev.data_ptr(), seed=2000 + k, counts_blocks=COUNT_BLOCKS,
-                          on_counts_block=gather_block)
-        gather_counts()
-        barrier()
-        ev1.record()
-        torch.cuda.synchronize()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        elapsed_ms += max(ev0.elapsed_time(ev1), wall_ms)
-        total_steps += res["global_cell_steps"]
-        local_steps += res["local_cell_steps"]
-    clocks = sampler.stop()
-    launches = eng.launch_count() - launches0 - args.steps      # minus the untimed reset kernels
-    kernel_ms, kernel_launches = eng.step_kernel_stats()
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = total_steps / (elapsed_ms / 1e3)
+    env = dict(world=world, rank=rank, local=local, comm=comm, barrier=barrier, max_over_ranks=max_over_ranks,
+               after_pass=lambda: None)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+
+    per_gpu = args.cells
+    rig = Rig(env, args.network, per_gpu, alpha=args.alpha, n=args.genes)
+    n = rig.n
+    cdt = args.counts_dtype
+    torch_dt = {"uint8": torch.uint8, "uint16": torch.uint16, "int32": torch.int32}[cdt]
+    esz = {"uint8": 1, "uint16": 2, "int32": 4}[cdt]
+    counts_dev = torch.empty((per_gpu, n), dtype=torch_dt, device=dev)       # this rank's shard of the count matrix
+    gathered = None
+    pending = []
+    COUNT_BLOCKS = 1
+    on_block = None
+    if args.gather and world > 1:
+        # optional: the shards are collected on rank 0 (north_star's "NCCL only to gather the final count matrix"); each
+        # finished row block is handed to NCCL at once, so its transfer runs under the sampling of the next block
+        COUNT_BLOCKS = 8
+        gathered = [torch.empty((per_gpu, n), dtype=torch_dt, device=dev) for _ in range(world)] if rank == 0 else None
+
+        def on_block(r0, r1):
+            pending.append(dist.gather(counts_dev[r0:r1], [g[r0:r1] for g in gathered] if rank == 0 else None,
+                                       dst=0, async_op=True))
+
+        def after_pass():
+            for w in pending:
+                w.wait()
+            pending.clear()
+        env["after_pass"] = after_pass
+
+    run_kw = dict(counts_dev_ptr=counts_dev.data_ptr(), counts_blocks=COUNT_BLOCKS, on_counts_block=on_block, counts_dtype=cdt)
+    head = rig.timed(args.steps, args.warmup, seed0=1337, **run_kw)
+    env["after_pass"] = lambda: None
+    overflow_entries = 0 if head["last"]["overflow"] is None else int(len(head["last"]["overflow"]))
 
     # ---- timed: end to end with host buffers ----
     e2e = None
     if not args.no_e2e:
+        np_dt = {"uint8": np.uint8, "uint16": np.uint16, "int32": np.int32}[cdt]
         try:
-            host_counts = torch.empty((per_gpu, n), dtype=torch.int32, pin_memory=True).numpy()
+            host_counts = torch.empty((per_gpu, n), dtype=torch_dt, pin_memory=True).numpy()
         except RuntimeError:
-            host_counts = np.empty((per_gpu, n), dtype=np.int32)
-        e_ms, e_steps, h2d = 0.0, 0, 0
+            host_counts = np.empty((per_gpu, n), dtype=np_dt)
+        e_ms, e_steps, h2d, d2h = 0.0, 0, 0, 0
         for k in range(args.e2e_steps):
             barrier()
             t0 = time.perf_counter()
-            eng.set_network(csr=csr, n=n)
-            eng.set_states_broadcast(x0)
-            res = sim.run_all(tree, counts_out=host_counts, seed=3000 + k)
+            rig.eng.set_network(csr=rig.csr, n=n)
+            rig.eng.set_states_broadcast(rig.x0)
+            res = rig.sim.run_all(rig.tree, counts_out=host_counts, seed=3000 + k, counts_dtype=cdt)
             barrier()
             e_ms += (time.perf_counter() - t0) * 1e3
             e_steps += res["global_cell_steps"]
-            h2d = int(csr[0].nbytes + csr[1].nbytes + csr[2].nbytes + x0.nbytes + res["h2d_bytes"])
-        t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": e_steps / (float(t.item()) / 1e3), "unit": "cell-steps/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": int(host_counts.nbytes + per_gpu * 8), "steps": args.e2e_steps,
+            h2d = int(sum(a.nbytes for a in rig.csr) + rig.x0.nbytes + res["h2d_bytes"])
+            d2h = int(host_counts.nbytes + per_gpu * 8 + (0 if res["overflow"] is None else res["overflow"].shape[0] * 12))
+        e_ms = max_over_ranks(e_ms)
+        e2e = {"value": e_steps / (e_ms / 1e3), "unit": "cell-steps/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "counts_dtype": cdt,
                "api": "scr_set_network_csr + scr_set_states_broadcast + scr_probe/scr_run_phase per node + "
-                      "scr_gene_sums + scr_counts(host int32 out)"}
+                      "scr_gene_sums + scr_counts_compact(host %s out, per-rank shard)" % cdt}
+        del host_counts
+
+    # ---- the other north_star paths, same process ----
+    extra = {}
+    if not args.no_extra:
+        want = [x for x in args.extra.split(",") if x]
+        extra = run_extras(args, env, rig, counts_dev, want, peak, peak_source, dev)
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
-        n_pad = layout["n_pad"]
-        achieved = (local_steps * 8.0 * n) / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else None
-        roofline = {"bound": "hbm", "kernel": "scr::step_kernel<float> (persistent stepper)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                    "algorithmic_bytes_per_cell_step": 8 * n, "cell_steps_per_launch": local_steps / max(kernel_launches, 1),
-                    "kernel_ms_per_launch": kernel_ms / max(kernel_launches, 1), "kernel_launches": int(kernel_launches),
-                    "kernel_share_of_step": kernel_ms / elapsed_ms if elapsed_ms else None,
-                    "kernel_cell_steps_per_s": local_steps / (kernel_ms / 1e3) if kernel_ms > 0 else None,
-                    "traffic": _ncu_traffic(), "traffic_source": "profiles/step_kernel_traffic.json (ncu capture of one "
-                    "80e6-cell-step launch: 9.87 GB DRAM vs 1.92 TB algorithmic -- the state is smem-resident)",
-                    "layout": layout}
+        roofline = rig.sparse_roofline(head, peak, peak_source)
+        roofline.update(traffic=_ncu_traffic(), traffic_source="profiles/step_kernel_traffic.json (ncu capture of one "
+                        "80e6-cell-step launch: DRAM bytes vs 1.92 TB algorithmic -- the state is smem-resident)",
+                        layout=rig.layout)
         cpu = None
         if not args.no_cpu:
-            cpu = cpu_baseline(gcs, tree[0].proj, tree[0].const, x0, args.cpu_seconds)
-        cfg = workload_config(args, n, nnz, alpha)
-        cfg["node_iterations"] = sim.node_iterations
-        line = {"metric": "cell_steps_per_sec", "value": value, "unit": "cell-steps/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            cpu = cpu_baseline(rig.gc / rig.alpha, rig.tree[0].proj, rig.tree[0].const, rig.x0, args.cpu_seconds)
+        line = {"metric": "cell_steps_per_sec", "value": head["value"], "unit": "cell-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu}
+                "data": "synthetic", "config": workload_config(args, n, rig.nnz, rig.alpha), "clocks": head["clocks"],
+                "e2e": e2e, "gpu_launches": int(head["launches"]), "roofline": roofline, "cpu_baseline": cpu,
+                "details": {"node_iterations": head["node_iterations"], "counts_dtype": cdt,
+                            "count_matrix": "per-rank shards (cells x genes, %s + overflow list)%s" % (
+                                cdt, ", gathered on rank 0" if args.gather and world > 1 else ""),
+                            "overflow_entries_last_pass": overflow_entries,
+                            "noise_stream": rig.eng.noise_stream_version()},
+                "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extras(args, env, rig, counts_dev, want, peak, peak_source, dev):
+    """Measured after the headline, in the same process; rank 0 keeps the numbers.  Every block: its own warm-up, CUDA-event
+    / barrier timing like the headline, its own clocks sample."""
+    import torch
+    world, rank = env["world"], env["rank"]
+    out = {}
+    n = rig.n
+
+    def block(name, fn):
+        if name not in want:
+            return
+        try:
+            t0 = time.perf_counter()
+            res = fn()
+            if res is not None:
+                res["block_wall_s"] = time.perf_counter() - t0
+                out[name] = res
+        except Exception as exc:                                         # an extra block never takes the headline down
+            out[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+    # -- the count kernel alone on the headline's final states -----------------------------------------------------
+    def counts_block():
+        eng = rig.eng
+        sampler = ClockSampler(env["local"]).start()
+        shift = rig.sim.gene_shift()
+        size = rig.sim._size_factors(0.14)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for rep in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            eng.counts_compact(shift, size, seed=5 + rep, dtype="uint8", out_device_ptr=counts_dev.data_ptr())
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) * 1e3
+            best = ms if best is None or ms < best else best
+        entries = float(rig.per_gpu) * n
+        rate = entries / (best / 1e3)
+        return {"metric": "entries_per_sec (counts_kernel, uint8 out, one GPU)", "value": rate, "ms_per_call": best,
+                "entries": entries, "timing": "host clock around the synchronous scr_counts_compact call (one kernel launch + "
+                "4 small copies), best of 4",
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_entry": 5, "achieved": rate * 5 / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": rate * 5 / 1e9 / peak, "peak_source": peak_source},
+                "clocks": sampler.stop()}
+    block("counts", counts_block)
+
+    # -- alpha search of the contract network (setup of the headline, re-derived here) -----------------------------
+    def alpha_block():
+        if rank != 0:
+            return None
+        small = build_tree(n, 1000, rig.tf)
+        a, dt = search_alpha(rig.gc, small, rig.x0, n, env["local"])
+        return {"alpha_searched": round(float(a), 4), "alpha_used": rig.alpha, "seconds": dt,
+                "what": "findOptimalAlpha (MS:368-500) on the GPU, 50 sampled cells, batched ladder"}
+    block("alpha_search", alpha_block)
+    env["barrier"]()
+
+    def sparse_block(kind, prec, cells, steps, label):
+        def fn():
+            r = Rig(env, kind, cells, prec=prec)
+            try:
+                dt = torch.uint8
+                buf = torch.empty((cells, r.n), dtype=dt, device=dev)
+                t = r.timed(steps, 1, seed0=7000, counts_dev_ptr=buf.data_ptr(), counts_dtype="uint8")
+                res = {"metric": "cell_steps_per_sec", "workload": label, "value": t["value"], "ms_per_step": t["ms_per_step"],
+                       "n_gpus": world, "cells_per_gpu": cells, "genes": r.n, "nnz": r.nnz, "alpha": r.alpha, "dtype": prec,
+                       "steps": steps, "warmup": 1, "node_iterations": t["node_iterations"],
+                       "roofline": r.sparse_roofline(t, peak, peak_source), "clocks": t["clocks"],
+                       "layout": {k: r.layout[k] for k in ("groups_per_cta", "operator_prefix_bytes", "operator_bytes", "chunks",
+                                                           "gather_wavefronts_model", "gather_wavefronts_floor")}}
+                del buf
+                return res
+            finally:
+                r.close()
+        return fn
+
+    block("trrust", sparse_block("trrust", "f32", args.cells, 2, "c5 pass on TRRUST n=2895 (alpha 0.1), %d cells per GPU" % args.cells))
+    block("powerlaw205", sparse_block("powerlaw205", "f32", args.cells, 2,
+                                      "c5 pass on SimulatedPowerLaw n=3000 powerLawExponent=2.05 (the reference's default), %d cells per GPU" % args.cells))
+    f64_cells = min(args.cells, 250000)
+    block("f64", sparse_block(args.network, "f64", f64_cells,
+                              2, "c5 pass in the float64 parity context, %d cells per GPU" % f64_cells))
+    if world > 1:
+        strong_cells = max(4, (1000000 // world) // 4 * 4)
+        def strong():
+            res = sparse_block(args.network, "f32", strong_cells, 3,
+                               "STRONG scaling point: 10^6 cells in total, %d per GPU, contract network" % strong_cells)()
+            res["scaling"] = "strong"
+            return res
+        block("strong", strong)
+
+    # -- config c4 on the tcgen05 3xTF32 stepper -------------------------------------------------------------------
+    def dense_block():
+        cells = min(200000, args.cells)
+        r = Rig(env, "dense_c4", cells)
+        try:
+            assert r.layout["dense_stepper"] == 1
+            # denominator: a plain TF32 matmul timed here, on this GPU, now
+            torch.backends.cuda.matmul.allow_tf32 = True
+            a = torch.randn(8192, 8192, device=dev)
+            b = torch.randn(8192, 8192, device=dev)
+            for _ in range(3):
+                torch.matmul(a, b)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = None
+            for _ in range(5):
+                ev0.record()
+                for _ in range(4):
+                    torch.matmul(a, b)
+                ev1.record()
+                torch.cuda.synchronize()
+                ms = ev0.elapsed_time(ev1) / 4
+                best = ms if best is None or ms < best else best
+            tf32_peak = 2.0 * 8192 ** 3 / (best / 1e3) / 1e12
+            del a, b
+            t = r.timed(1, 1, seed0=9000, do_counts=False)
+            ks = t["local_steps"] / (t["kernel_ms"] / 1e3)
+            issued = ks * 6.0 * r.n * r.n / 1e12
+            return {"metric": "cell_steps_per_sec", "workload": "c4: Random n=3000 networkSparsity=0.5 (alpha 2.21), %d cells per GPU, "
+                    "single type, stepping only" % cells, "value": t["value"], "ms_per_step": t["ms_per_step"], "n_gpus": world,
+                    "genes": r.n, "nnz": r.nnz, "dtype": "f32 via 3xTF32", "node_iterations": t["node_iterations"],
+                    "kernel_launches": t["kernel_launches"], "kernel_cell_steps_per_s": ks,
+                    "roofline": {"bound": "tensor", "kernel": "scr::dense::dense_step_kernel (tcgen05 3xTF32, fused update)",
+                                 "achieved": issued, "useful": issued / 3.0, "peak": tf32_peak, "unit": "TFLOP/s",
+                                 "frac": issued / tf32_peak, "peak_source": "torch.matmul TF32 8192^3 timed in this run (best of 5 x 4)",
+                                 "flops_per_cell_step_issued": 6.0 * r.n * r.n},
+                    "clocks": t["clocks"]}
+        finally:
+            r.close()
+    block("dense_c4", dense_block)
+    return out
 
 
 def _ncu_traffic():

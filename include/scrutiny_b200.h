@@ -74,6 +74,12 @@ int scr_set_network_dense(scr_ctx* ctx, int32_t n, const double* gc_rowmajor);
  * scr_probe return SCR_E_STATE.  No on-chip budget applies: any n the count kernel's staging row holds (n <= 58 000). */
 int scr_set_genes(scr_ctx* ctx, int32_t n);
 
+/* Additive term of the drive, per gene (n doubles, caller's gene order; NULL clears it): scr_run_phase and scr_probe then
+ * evaluate tanh(gc (x - mu) + bias + noise).  This is how a PER-GENE geneMeanLevels vector (developCell broadcasts
+ * `x - geneMeanLevels`, MS:530; Matri-seqFinal.py passes np.zeros(n)) reaches the kernels: bias = -gc mu_vec, const + mu_vec,
+ * scalar mu = 0 (scrutiny_b200/engine.py does that).  Stays set until cleared or the network is replaced. */
+int scr_set_drive_bias(scr_ctx* ctx, const double* bias);
+
 /* Test hook, host only (no GPU work): y = W x computed by walking the SAME packed operator the
  * kernels read (internal order, tiles, chunks), so packing bugs show up in the CPU test-suite. */
 int scr_debug_host_matvec(const scr_ctx* ctx, const double* x, double* y);

@@ -27,14 +27,17 @@ Deliberate differences (DESIGN.md "Reference quirks"):
   * keyword arguments of ``findAllNextStates`` ARE forwarded to child nodes (the reference drops
     them at MS:611-612); pass ``reference_compat=True`` to reproduce the reference's behaviour.
   * ``rangeTransformation`` exists (the packaged reference forgot it: NameError at MS:336).
-  * extra keyword-only arguments: ``precision`` ("f32" default, "f64" parity path), ``alpha=`` on
-    ``generateGeneCorrelationMatrix`` (skip the search), ``device``.
+  * extra trailing arguments with defaults: ``precision`` ("f32" default, "f64" parity path), ``alpha=`` on
+    ``generateGeneCorrelationMatrix`` (skip the search), ``device``, ``compact=`` / ``capture=`` on ``transformData``.
+  * the CUDA context holding the packed network is cached between calls (keyed on the ``gc`` buffer and its contents), so
+    per-cell calls of ``developCell`` / ``findCellNextState`` do not rebuild the operator; ``init`` drops it.
 """
 import os
 import random
 
 import numpy as np
 
+from . import artefacts as _artefacts
 from . import network as _network
 from .engine import STREAM_ALPHA, Engine
 from .lineage import Tree
@@ -61,6 +64,7 @@ def init(outputDir='./scRutiNy/MatriSeq', seed=1337, verbose=True, device=0, pre
     __device = device
     __precision = precision
     __call_counter = 0
+    _drop_engines()
 
 
 def _next_seed():
@@ -149,17 +153,49 @@ def generateInitialStates(n, cells, sameInitialCell=True, geneMeanLevels=0):
 # ------------------------------------------------------------------------------------------
 # GPU-backed hot path
 # ------------------------------------------------------------------------------------------
+_engine_cache = {}        # (device, precision) -> [fingerprint of gc, Engine]: one context per device and precision is kept
+
+
+def _fingerprint(gc):
+    """Cheap identity of a dense network argument: buffer address and shape plus two content checks that any rescaling
+    or edit of the matrix changes (full sum, bytes of a strided sample) -- a few ms at n = 3000 against the ~0.5 s of
+    converting, packing and uploading the operator again."""
+    gc = np.asarray(gc)
+    flat = gc.reshape(-1)
+    return (gc.__array_interface__["data"][0], gc.shape, gc.dtype.str, float(flat.sum()),
+            hash(flat[::max(1, flat.size // 65536)].tobytes()))
+
+
 def _engine_for(gc, cells, states=None, precision=None, device=None):
-    eng = Engine(__device if device is None else device, precision or __precision)
-    eng.set_network(gc)
-    eng.alloc_cells(cells)
+    """The context holding ``gc``: developCell / findCellNextState / findOptimalIterations are called once per cell or
+    per node by user code (MS:503-537, 683-736), so the packed operator is kept between calls and only rebuilt when the
+    matrix changes (VERDICT r1 weak #8)."""
+    dev = __device if device is None else device
+    key = (dev, precision or __precision)
+    fp = _fingerprint(gc)
+    slot = _engine_cache.get(key)
+    if slot is None or slot[0] != fp:
+        if slot is not None:
+            slot[1].close()
+        eng = Engine(dev, key[1])
+        eng.set_network(gc)
+        _engine_cache[key] = slot = [fp, eng]
+    eng = slot[1]
+    if eng.cells != cells:
+        eng.alloc_cells(cells)
     if states is not None:
         eng.set_states(states)
     return eng
 
 
+def _drop_engines():
+    for slot in _engine_cache.values():
+        slot[1].close()
+    _engine_cache.clear()
+
+
 def developCell(n, gc, timeStep, initialState, proj, const, noiseDisp, geneMeanLevels, precision=None):
-    """MS:503-537: one step of one cell."""
+    """MS:503-537: one step of one cell.  ``geneMeanLevels``: scalar or per-gene vector, like the reference's broadcast."""
     return findCellNextState(gc, n, timeStep, 0, proj, const, initialState, 1, noiseDisp, geneMeanLevels, False,
                              precision=precision)
 
@@ -219,9 +255,7 @@ def findOptimalAlpha(n, gc, cellTypeTree, currentStates, numToSample, timeStep=0
         for _ in range(batch):
             a = a + step
             ladder.append(a)
-        eng = Engine(__device, precision or __precision)
-        eng.set_network(gc)
-        eng.alloc_cells(per * batch)
+        eng = _engine_for(gc, per * batch, precision=precision)
         block = np.zeros((n, per * batch))
         for j in range(batch):
             block[:, j * per:j * per + numToSample] = currentStates[:, samples[rung + j]]
@@ -231,7 +265,6 @@ def findOptimalAlpha(n, gc, cellTypeTree, currentStates, numToSample, timeStep=0
         it = eng.probe(np.arange(per * batch), proj, const, dt=timeStep, sigma=noiseDisp, mu=geneMeanLevels,
                        thresh=convergenceThreshold, max_iter=maxNumIterations, avg_num=convDistAvgNum, seed=seed,
                        stream=STREAM_ALPHA + rung, w_div=np.repeat(ladder, per)).reshape(batch, per)[:, :numToSample]
-        eng.close()
         rates = (it != maxNumIterations).sum(axis=1) / numToSample               # MS:480-481, 489
         done = False
         for j in range(batch):
@@ -273,23 +306,32 @@ def findAllNextStates(gc, cellTypeNode, cellTypeTree, currentStates, cellTypesRe
         eng.get_states(out=currentStates)
     else:
         currentStates[...] = eng.get_states()
-    eng.close()
 
 
 def transformData(n, cells, finalCellStates, dropoutProportion=0.0, cellRadiusDisp=0.14, geneScale=0.0, expScale=1.0,
-                  expLambda=0.0, shape=0.35, rate=0.19, gammaDistMean=True, precision=None, capture=None):
+                  expLambda=0.0, shape=0.35, rate=0.19, gammaDistMean=True, precision=None, capture=None, compact=None):
     """MS:816-891 -> (counts (n, cells) float64 holding integers, cellSizeFactors).
     ``dropoutProportion`` is accepted and unused, exactly like the reference (MS:819).
+    ``compact`` (extension): False -> always the reference's dense float64 array; True -> an
+    ``artefacts.CountMatrix`` (unsigned bytes + overflow list on the host, 1/8 of the bytes, reads like the reference's
+    array); None (default) -> dense up to ``artefacts.DENSE_LIMIT`` bytes (2 GiB), compact above.
     ``capture`` (extension, parity aid): a dict that receives the Poisson rate matrix ``lambda`` (n, cells) and the
     per-gene ``shift`` the read-out used."""
-    eng = _engine_for(np.zeros((n, n)), cells, finalCellStates, precision)
+    eng = Engine(__device, precision or __precision)
     try:
+        eng.set_genes(n)                                                         # the read-out needs no network
+        eng.alloc_cells(cells)
+        eng.set_states(finalCellStates)
         sim = LineageSimulation(eng, cells, seed=_next_seed())
+        dense = compact is False or (compact is None and 8 * n * cells <= _artefacts.DENSE_LIMIT) or capture is not None
         counts, size = sim.counts(cellRadiusDisp=cellRadiusDisp, expScale=expScale, shape=shape, rate=rate,
-                                  geneScale=geneScale, expLambda=expLambda, gammaDistMean=gammaDistMean, capture=capture)
+                                  geneScale=geneScale, expLambda=expLambda, gammaDistMean=gammaDistMean, capture=capture,
+                                  dtype="int32" if dense else "uint8")
     finally:
         eng.close()
-    return np.ascontiguousarray(counts.T, dtype=np.float64), size
+    if dense:
+        return np.ascontiguousarray(counts.T, dtype=np.float64), size
+    return _artefacts.CountMatrix([counts[0]], [counts[1]], n), size
 
 
 # ------------------------------------------------------------------------------------------
@@ -306,6 +348,14 @@ def saveData(synthscRNAseq, cellTypesRecord, gc, projMatrix, constMatrix, cellSi
     from .rdata import write_rdata
     for name, value in zip(ARTEFACTS, (synthscRNAseq, cellTypesRecord, gc, projMatrix, constMatrix,
                                        cellSizeFactors, synthPseudotimes)):
+        if isinstance(value, _artefacts.CountMatrix):
+            # compact counts: shards + manifest always; the reference's dense float64 twins only while they stay small
+            for r, (blk, ovf) in enumerate(zip(value.blocks, value.overflows)):
+                _artefacts.save_shard(__outputDir, np.asarray(blk), ovf, r)
+            _artefacts.write_manifest(__outputDir, value.genes, [b.shape[0] for b in value.blocks], value.blocks[0].dtype)
+            if 8 * value.genes * value.cells > _artefacts.DENSE_LIMIT:
+                continue
+            value = np.asarray(value)
         np.save(os.path.join(__outputDir, name), value)
         write_rdata(os.path.join(__outputDir, name + ".gzip"), name, np.asarray(value))
 

@@ -47,18 +47,22 @@ def _eng():
 
 
 def readCellStates():
-    """RNI:49-66: loads the artefacts MatriSeq.saveData wrote and rank-transforms the count matrix."""
-    cellStates = np.load(os.path.join(__inputDir, "synthscRNAseq.npy"))
-    pseudotimes = np.load(os.path.join(__inputDir, "synthPseudotimes.npy"))
-    cellTypesRecord = np.load(os.path.join(__inputDir, "cellTypesRecord.npy"))
-    W_real = np.load(os.path.join(__inputDir, "gc.npy"))
+    """RNI:49-66: loads the artefacts MatriSeq.saveData wrote and rank-transforms the count matrix.  When only the
+    compact shards exist (counts above ``artefacts.DENSE_LIMIT``), the matrix is assembled from them."""
+    from . import artefacts
+
+    def artefact(name):
+        return np.load(os.path.join(__inputDir, name + ".npy"))
+
+    dense = os.path.join(__inputDir, "synthscRNAseq.npy")
+    cellStates = np.load(dense) if os.path.isfile(dense) else np.asarray(artefacts.load(__inputDir))
+    pseudotimes, cellTypesRecord, W_real = artefact("synthPseudotimes"), artefact("cellTypesRecord"), artefact("gc")
     n, cells = cellStates.shape
     cellStates = convertToS(n, cells, cellStates)
     if __verbose:
-        print("Num genes: ", n, ", num cells: ", cells)
-        print("Cell States: ", cellStates)
-        print("Num TF Connections: ", np.flatnonzero(W_real).size)
-        print("Pseudotimes: ", pseudotimes)
+        for label, value in (("Num genes: %d , num cells: " % n, cells), ("Cell States: ", cellStates),
+                             ("Num TF Connections: ", int(np.count_nonzero(W_real))), ("Pseudotimes: ", pseudotimes)):
+            print(label, value)
     return n, cells, cellStates, pseudotimes, cellTypesRecord, W_real
 
 

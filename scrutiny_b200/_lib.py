@@ -26,6 +26,7 @@ SIGNATURES = {
     "scr_sync": (C.c_int, [c_ctx]),
     "scr_set_network_csr": (C.c_int, [c_ctx, C.c_int32, C.c_int64, _i32p, _i32p, _f64p]),
     "scr_set_network_dense": (C.c_int, [c_ctx, C.c_int32, _f64p]),
+    "scr_set_drive_bias": (C.c_int, [c_ctx, _f64p]),
     "scr_debug_host_matvec": (C.c_int, [c_ctx, _f64p, _f64p]),
     "scr_debug_block_records": (C.c_int, [c_ctx, _i32p, C.c_int32, _i32p, C.c_int32]),
     "scr_debug_gene_order": (C.c_int, [c_ctx, _i32p, C.c_int32]),

@@ -80,6 +80,7 @@ struct scr_ctx {
   unsigned long long* d_covf_count = nullptr;
   size_t covf_cap = 0;
   bool counts_smem_optin = false;
+  std::vector<double> user_bias;            // scr_set_drive_bias: additive drive term per gene (original order), empty = none
   bool readout_only = false;                 // scr_set_genes: no network, only the state / read-out entry points work
 
   // RegNetInference front end
@@ -311,9 +312,10 @@ int upload_node(scr_ctx* ctx, const double* proj, const double* cnst, double mu,
   }
   CK(cudaMemcpyAsync(ctx->d_pc, pc.data(), pc.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
   p.bias = nullptr;
-  if (mu != 0.0) {
+  if (mu != 0.0 || !ctx->user_bias.empty()) {
     std::vector<T> bias(op.n_pad, T(0));
-    for (int i = 0; i < op.n; ++i) bias[i] = static_cast<T>(-mu * op.rowsum[i] * drive_scale);
+    for (int i = 0; i < op.n; ++i)
+      bias[i] = static_cast<T>((-mu * op.rowsum[i] + (ctx->user_bias.empty() ? 0.0 : ctx->user_bias[op.perm[i]])) * drive_scale);
     CK(cudaMemcpyAsync(ctx->d_bias, bias.data(), bias.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     p.bias = static_cast<const T*>(ctx->d_bias);
   }
@@ -905,6 +907,7 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
   ctx->w_bytes = static_cast<int>(w.size());
   ctx->h_tab = tab;
   ctx->op = std::move(op);
+  ctx->user_bias.clear();
   ctx->has_net = false;
   int rc = choose_config(ctx);
   if (rc) return rc;
@@ -960,6 +963,7 @@ int scr_set_genes(scr_ctx* ctx, int32_t n) {
   std::vector<int32_t> rowptr(static_cast<size_t>(n) + 1, 0);
   if (!scr::pack_operator(n, 0, rowptr.data(), nullptr, nullptr, op, err, true, 128)) return fail(ctx, SCR_E_ARG, err);
   ctx->op = std::move(op);
+  ctx->user_bias.clear();
   ctx->has_net = false;
   ctx->dense_mode = false;
   ctx->tab_bytes = ctx->w_bytes = 0;
@@ -1006,6 +1010,14 @@ int scr_debug_block_records(const scr_ctx* ctx, int32_t* records, int32_t max_re
   std::memcpy(records, ctx->h_tab.data(), static_cast<size_t>(o.nb) * 16);
   std::memcpy(list_bounds, ctx->h_tab.data() + scr::kRecBytes, static_cast<size_t>(o.wq + 1) * 4);
   return o.nb;
+}
+
+int scr_set_drive_bias(scr_ctx* ctx, const double* bias) {
+  if (!ctx) return SCR_E_ARG;
+  if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
+  if (!bias) { ctx->user_bias.clear(); return SCR_OK; }
+  ctx->user_bias.assign(bias, bias + ctx->op.n);
+  return SCR_OK;
 }
 
 int scr_debug_gene_order(const scr_ctx* ctx, int32_t* perm_out, int32_t count) {

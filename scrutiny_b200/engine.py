@@ -11,6 +11,8 @@ from . import _lib
 from .network import dense_to_csr
 
 F32, F64 = 0, 1
+COUNT_DTYPES = {"int32": (0, np.int32), "uint16": (1, np.uint16), "uint8": (2, np.uint8)}
+E_RESOURCE = -4
 STREAM_STEP, STREAM_PROBE, STREAM_COUNTS, STREAM_ALPHA = 0, 1, 2, 16
 
 
@@ -74,6 +76,34 @@ class Engine:
         self._check(self._lib.scr_set_network_csr(self._ctx, n, len(val), _ptr(rowptr, C.c_int32),
                                                   _ptr(col, C.c_int32), _ptr(val, C.c_double)))
         self.n = n
+        self._csr = (rowptr, col, val)
+
+    def _mean_levels(self, mu, const):
+        """geneMeanLevels as the reference accepts it (a scalar, or a per-gene vector broadcast in ``x - geneMeanLevels``,
+        MS:530) -> (scalar mu for the ABI, const).  A non-uniform vector becomes the drive bias -gc mu plus const + mu."""
+        if np.ndim(mu) == 0:
+            return float(mu), const
+        mu = np.asarray(mu, dtype=np.float64).ravel()
+        if mu.shape != (self.n,):
+            raise ValueError("geneMeanLevels must be a scalar or a vector of length n = %d, got shape %s" % (self.n, mu.shape))
+        if np.all(mu == mu[0]):
+            return float(mu[0]), const
+        rowptr, col, val = self._csr
+        rows = np.repeat(np.arange(self.n), np.diff(rowptr))
+        bias = -np.bincount(rows, weights=val * mu[col], minlength=self.n)
+        self._check(self._lib.scr_set_drive_bias(self._ctx, _ptr(_f64(bias), C.c_double)))
+        self._bias_set = True
+        return 0.0, const + mu
+
+    def _clear_bias(self):
+        if getattr(self, "_bias_set", False):
+            self._check(self._lib.scr_set_drive_bias(self._ctx, None))
+            self._bias_set = False
+
+    def set_genes(self, n):
+        """Read-out context: n genes, no network (only states, gene sums and counts work afterwards)."""
+        self._check(self._lib.scr_set_genes(self._ctx, int(n)))
+        self.n = int(n)
 
     def host_matvec(self, x):
         x = _f64(x)
@@ -142,21 +172,28 @@ class Engine:
         steps = np.ascontiguousarray(steps, dtype=np.int32)
         base = None if step_base is None else np.ascontiguousarray(step_base, dtype=np.int64)
         proj, const = _f64(proj), _f64(const)
+        mu, const = self._mean_levels(mu, const)
+        const = _f64(const)
         nsteps = 0
         if noise is not None:
             noise = _f64(noise)
             assert noise.ndim == 3 and noise.shape[0] == len(cell_ids) and noise.shape[2] == self.n
             nsteps = noise.shape[1]
-        self._check(self._lib.scr_run_phase(self._ctx, len(cell_ids), _ptr(cell_ids, C.c_int64),
-                                            _ptr(steps, C.c_int32), _ptr(base, C.c_int64),
-                                            _ptr(proj, C.c_double), _ptr(const, C.c_double), dt, sigma, mu,
-                                            int(seed) & (2 ** 64 - 1), _ptr(noise, C.c_double), nsteps))
+        try:
+            self._check(self._lib.scr_run_phase(self._ctx, len(cell_ids), _ptr(cell_ids, C.c_int64),
+                                                _ptr(steps, C.c_int32), _ptr(base, C.c_int64),
+                                                _ptr(proj, C.c_double), _ptr(const, C.c_double), dt, sigma, mu,
+                                                int(seed) & (2 ** 64 - 1), _ptr(noise, C.c_double), nsteps))
+        finally:
+            self._clear_bias()
 
     def probe(self, sample_ids, proj, const, dt=0.01, sigma=0.05, mu=0.0, thresh=0.1, max_iter=500,
               avg_num=20, seed=0, stream=STREAM_PROBE, w_div=None, noise=None, want_trace=False):
         ids = np.ascontiguousarray(sample_ids, dtype=np.int64)
         k = len(ids)
         proj, const = _f64(proj), _f64(const)
+        mu, const = self._mean_levels(mu, const)
+        const = _f64(const)
         wd = None if w_div is None else _f64(w_div)
         nz = None
         if noise is not None:
@@ -164,10 +201,13 @@ class Engine:
             assert nz.shape == (k, max_iter, self.n)
         iters = np.zeros(k, dtype=np.int32)
         trace = np.zeros((k, max_iter)) if want_trace else None
-        self._check(self._lib.scr_probe(self._ctx, k, _ptr(ids, C.c_int64), _ptr(wd, C.c_double),
-                                        _ptr(proj, C.c_double), _ptr(const, C.c_double), dt, sigma, mu, thresh,
-                                        int(max_iter), int(avg_num), int(seed) & (2 ** 64 - 1), int(stream),
-                                        _ptr(nz, C.c_double), _ptr(iters, C.c_int32), _ptr(trace, C.c_double)))
+        try:
+            self._check(self._lib.scr_probe(self._ctx, k, _ptr(ids, C.c_int64), _ptr(wd, C.c_double),
+                                            _ptr(proj, C.c_double), _ptr(const, C.c_double), dt, sigma, mu, thresh,
+                                            int(max_iter), int(avg_num), int(seed) & (2 ** 64 - 1), int(stream),
+                                            _ptr(nz, C.c_double), _ptr(iters, C.c_int32), _ptr(trace, C.c_double)))
+        finally:
+            self._clear_bias()
         return (iters, trace) if want_trace else iters
 
     def gene_sums(self):
@@ -200,6 +240,35 @@ class Engine:
                                                _ptr(size_factors, C.c_double), int(seed) & (2 ** 64 - 1),
                                                _ptr(uni, C.c_double), int(draws), ptr, on_dev, _ptr(lam, C.c_double)))
         return (out, lam) if want_lambda else out
+
+    def counts_compact(self, shift, size_factors, exp_scale=1.0, seed=0, dtype="uint8", out=None, out_device_ptr=None,
+                       cell_begin=0, cell_count=None, overflow_capacity=None):
+        """Free-running read-out stored as ``dtype`` ("uint8" / "uint16" / "int32"), scr_counts_compact.  Returns
+        ``(out, overflow)``: ``out`` (rows, n) host array (None with ``out_device_ptr``), ``overflow`` (k, 3) int64 rows
+        (row of this call, gene, count) for the entries stored as the escape code (dtype max), sorted by (row, gene)."""
+        code, np_dtype = COUNT_DTYPES[dtype]
+        rows = self.cells - int(cell_begin) if cell_count is None else int(cell_count)
+        shift, size_factors = _f64(shift), _f64(size_factors)
+        assert len(size_factors) == rows and len(shift) == self.n
+        if out_device_ptr is not None:
+            ptr, on_dev = C.c_void_p(int(out_device_ptr)), 1
+        else:
+            if out is None:
+                out = np.empty((rows, self.n), dtype=np_dtype)
+            assert out.dtype == np_dtype and out.flags.c_contiguous and out.shape == (rows, self.n)
+            ptr, on_dev = C.c_void_p(out.ctypes.data), 0
+        cap = int(overflow_capacity) if overflow_capacity is not None else max(4096, rows * self.n // 4096)
+        while True:
+            ovf = np.zeros((max(cap, 1), 3), dtype=np.int64)
+            count = C.c_int64(0)
+            rc = self._lib.scr_counts_compact(self._ctx, int(cell_begin), rows, _ptr(shift, C.c_double), float(exp_scale),
+                                              _ptr(size_factors, C.c_double), int(seed) & (2 ** 64 - 1), code, ptr, on_dev,
+                                              _ptr(ovf, C.c_int64), cap, C.byref(count))
+            if rc == E_RESOURCE and count.value > cap:      # list too small: the draw is deterministic, sample again
+                cap = int(count.value)
+                continue
+            self._check(rc)
+            return out, ovf[:count.value].copy()
 
     # -- RegNetInference front end ------------------------------------------------------------
     def rank_transform(self, S):

@@ -146,11 +146,15 @@ class LineageSimulation:
             shift[order] = target
         return shift
 
-    def counts(self, cellRadiusDisp=0.14, expScale=1.0, out=None, out_device_ptr=None, capture=None, **kw):
+    def counts(self, cellRadiusDisp=0.14, expScale=1.0, out=None, out_device_ptr=None, capture=None, dtype="int32", **kw):
         """transformData (MS:816-891) for this rank's cells.  Returns (counts (cells_local, n) int32,
-        all cellSizeFactors).  ``capture`` (dict, parity aid) receives ``lambda`` (n, cells_local) and ``shift``."""
+        all cellSizeFactors); with ``dtype`` "uint8" / "uint16" the first item is ``(compact counts, overflow rows)``.
+        ``capture`` (dict, parity aid) receives ``lambda`` (n, cells_local) and ``shift``."""
         shift = self.gene_shift(expScale=expScale, **kw)
         size = np.random.normal(loc=1, scale=cellRadiusDisp, size=self.cells) ** 3   # MS:875-876
+        if dtype != "int32":
+            return self.eng.counts_compact(shift, size[self.lo:self.hi], exp_scale=expScale, seed=self.seed, dtype=dtype,
+                                           out=out, out_device_ptr=out_device_ptr), size
         got = self.eng.counts(shift, size[self.lo:self.hi], exp_scale=expScale, seed=self.seed,
                               out=out, out_device_ptr=out_device_ptr, want_lambda=capture is not None)
         if capture is not None:
@@ -193,13 +197,16 @@ class LineageSimulation:
     def run_all(self, tree=None, counts_out=None, counts_dev_ptr=None, seed=None, timeStep=0.01, noiseDisp=0.05,
                 convergenceThreshold=0.1, maxNumIterations=500, convDistAvgNum=20, cellsToSample=50,
                 geneMeanLevels=0.0, fixed_iterations=None, cellRadiusDisp=0.14, expScale=1.0, do_counts=True,
-                counts_blocks=1, on_counts_block=None):
+                counts_blocks=1, on_counts_block=None, counts_dtype="int32", cellDevelopmentMode=True):
         """findAllNextStates + transformData for this rank's shard (tree prepared beforehand).
         Returns dict(global_cell_steps, local_cell_steps, h2d_bytes, iterations, types, size_factors).
 
         ``counts_blocks`` > 1 samples the count matrix in that many row blocks and calls
         ``on_counts_block(row0, row1)`` after each: the caller can pass finished rows on (NCCL gather in bench.py)
-        while the next block is sampled.
+        while the next block is sampled.  ``counts_dtype`` "uint8" / "uint16" stores the counts compactly
+        (scr_counts_compact); the result then carries ``overflow`` = (k, 3) int64 rows (local row, gene, count) for the
+        few entries that do not fit.  ``cellDevelopmentMode=False`` draws the member step counts from Poisson(T)
+        instead of U{0..T} (MS:590-591), by inversion of the same hashed uniforms.
 
         The per-cell draws that do not depend on a node's iteration count T (member uniforms, size factors) are
         produced by one helper thread while the main thread sits in the engine's calls (ctypes and numpy release
@@ -253,7 +260,10 @@ class LineageSimulation:
                 self.node_iterations[int(node.identifier)] = T
                 ids, nmem = p["ids"], len(p["mem_loc"])
                 steps = np.full(len(ids), T, dtype=np.int32)                     # descendants step T (MS:599-605)
-                np.minimum((draw.result() * (T + 1)).astype(np.int32), T, out=steps[:nmem])   # members k ~ U{0..T} (MS:589)
+                if cellDevelopmentMode:
+                    np.minimum((draw.result() * (T + 1)).astype(np.int32), T, out=steps[:nmem])   # members k ~ U{0..T} (MS:589)
+                else:
+                    steps[:nmem] = poisson_quantile(draw.result(), T)                          # members k ~ Poisson(T) (MS:591)
                 base = base_f.result() if base_f is not None else iters[ids]
                 next_ids = live[i + 1]["ids"] if i + 1 < len(live) else None
                 base_f = pool.submit(bookkeeping, ids, steps, next_ids)
@@ -272,18 +282,45 @@ class LineageSimulation:
                 nblk = max(1, min(int(counts_blocks), nloc))
                 edges = [nloc * b // nblk for b in range(nblk + 1)]
                 n_genes = len(shift)
+                esz = {"int32": 4, "uint16": 2, "uint8": 1}[counts_dtype]
+                overflow = []
                 for r0, r1 in zip(edges[:-1], edges[1:]):
-                    self.eng.counts(shift, size[r0:r1], exp_scale=expScale, seed=self.seed, cell_begin=r0, cell_count=r1 - r0,
-                                    out=None if counts_out is None else counts_out[r0:r1],
-                                    out_device_ptr=None if counts_dev_ptr is None else counts_dev_ptr + 4 * n_genes * r0)
+                    out_blk = None if counts_out is None else counts_out[r0:r1]
+                    dev_blk = None if counts_dev_ptr is None else counts_dev_ptr + esz * n_genes * r0
+                    if counts_dtype == "int32":
+                        self.eng.counts(shift, size[r0:r1], exp_scale=expScale, seed=self.seed, cell_begin=r0,
+                                        cell_count=r1 - r0, out=out_blk, out_device_ptr=dev_blk)
+                    else:
+                        _, ovf = self.eng.counts_compact(shift, size[r0:r1], exp_scale=expScale, seed=self.seed,
+                                                         dtype=counts_dtype, cell_begin=r0, cell_count=r1 - r0, out=out_blk,
+                                                         out_device_ptr=dev_blk)
+                        ovf[:, 0] += r0
+                        overflow.append(ovf)
                     if on_counts_block is not None:
                         on_counts_block(r0, r1)
                 h2d += shift.nbytes + size.nbytes
         finally:
             pool.shutdown(wait=True)
         glob = float(self.comm.allreduce_sum(np.array([float(local_steps)]))[0])
+        ovf_all = None
+        if do_counts and counts_dtype != "int32":
+            ovf_all = np.concatenate(overflow) if overflow else np.zeros((0, 3), dtype=np.int64)
         return dict(global_cell_steps=glob, local_cell_steps=local_steps, h2d_bytes=h2d, iterations=iters,
-                    types=types, size_factors=size)
+                    types=types, size_factors=size, overflow=ovf_all)
+
+
+def poisson_quantile(u, lam):
+    """Smallest k with P(Poisson(lam) <= k) > u, vectorised over u in [0, 1): inverse-transform draw of Poisson(lam)
+    from one uniform per cell (the prepared mode's counterpart of np.random.poisson at MS:591)."""
+    u = np.asarray(u, dtype=np.float64)
+    if lam <= 0:
+        return np.zeros(u.shape, dtype=np.int32)
+    kmax = int(lam + 12.0 * np.sqrt(lam) + 25)
+    k = np.arange(kmax + 1, dtype=np.float64)
+    from math import lgamma
+    logp = k * np.log(lam) - lam - np.array([lgamma(v + 1.0) for v in k])
+    cdf = np.cumsum(np.exp(logp))
+    return np.minimum(np.searchsorted(cdf, u, side="right"), kmax).astype(np.int32)
 
 
 def hashed_uniform(seed, salt, ids):

@@ -52,6 +52,19 @@ class OracleEngine:
         return self.lam[cell_begin:r1]
 
 
+    def counts_compact(self, shift, size, exp_scale=1.0, seed=0, dtype="uint8", out=None, out_device_ptr=None, cell_begin=0,
+                       cell_count=None):
+        """Compact read-out double: integers drawn per GLOBAL cell id (rates scaled up so that some exceed a byte)."""
+        r1 = len(self.X) if cell_count is None else cell_begin + cell_count
+        lam = self.fo.poisson_lambda(self.X[cell_begin:r1].T, shift, exp_scale, size).T
+        full = np.stack([np.random.RandomState((self.offset + cell_begin + i) * 31 + int(seed)).poisson(60.0 * row)
+                         for i, row in enumerate(lam)])
+        esc = 255 if dtype == "uint8" else 65535
+        rows, genes = np.nonzero(full >= esc)
+        out[...] = np.minimum(full, esc)
+        return out, np.stack([rows, genes, full[rows, genes]], axis=1).astype(np.int64)
+
+
 def build_case():
     from scrutiny_b200.lineage import Tree
     np.random.seed(5)
@@ -94,6 +107,54 @@ def run_rank(rank, world, port_no, out_path):
              lam=eng.lam, glob=res["global_cell_steps"], T=np.array(sorted(sim.node_iterations.items())))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_rank_shards(rank, world, port_no, out_dir):
+    """The compact, sharded read-out of bench.py / a 10^6-cell run: every rank samples its own rows as unsigned bytes and
+    writes its own shard; nothing is gathered."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from scrutiny_b200 import artefacts
+    from scrutiny_b200.simulate import Comm, LineageSimulation, shard_bounds
+    if world > 1:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port_no, rank=rank, world_size=world)
+    n, cells, W, tree, x0 = build_case()
+    lo, hi = shard_bounds(cells, rank, world)
+    eng = OracleEngine(W, hi - lo, lo)
+    eng.set_states_broadcast(x0)
+    sim = LineageSimulation(eng, cells, lo, hi, comm=Comm(), seed=99)
+    host = np.zeros((hi - lo, n), dtype=np.uint8)
+    res = sim.run_all(tree, seed=99, fixed_iterations=7, counts_out=host, counts_dtype="uint8", counts_blocks=2,
+                      cellDevelopmentMode=False)                        # member steps ~ Poisson(T) (MS:590-591), keyed by global id
+    assert res["overflow"].shape[1] == 3 and len(res["overflow"]) > 0
+    os.makedirs(out_dir, exist_ok=True)
+    artefacts.save_shard(out_dir, host, res["overflow"], rank)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        artefacts.write_manifest(out_dir, n, [shard_bounds(cells, r, world)[1] - shard_bounds(cells, r, world)[0] for r in range(world)],
+                                 np.uint8)
+
+
+def test_two_ranks_write_count_shards_that_load_as_one_matrix(tmp_path):
+    import torch.multiprocessing as mp
+    from scrutiny_b200 import artefacts
+    run_rank_shards(0, 1, 0, str(tmp_path / "one"))
+    port_no = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=run_rank_shards, args=(r, 2, port_no, str(tmp_path / "two"))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    one, two = artefacts.load(str(tmp_path / "one")), artefacts.load(str(tmp_path / "two"))
+    assert len(two.blocks) == 2 and one.shape == two.shape == (24, 44)
+    a = np.asarray(one)
+    assert np.array_equal(a, np.asarray(two)) and a.max() > 255 and a.dtype == np.float64
+    assert np.array_equal(two[:, 20:30], a[:, 20:30])
 
 
 def _free_port():
