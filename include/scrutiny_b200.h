@@ -168,6 +168,21 @@ int scr_counts_compact(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, con
                        const double* size_factors /* cell_count */, uint64_t seed, int out_dtype, void* counts_out,
                        int out_on_device, int64_t* overflow_out, int64_t overflow_capacity, int64_t* overflow_count);
 
+/* EXTENSIONS of the read-out, default off (north_star (4); the reference has only np.random.poisson, MS:884, and a
+ * commented-out dropout, MS:887-889).  With nb_dispersion = dropout_p = 0 this is scr_counts_range / scr_counts_compact.
+ *   nb_dispersion phi > 0: counts ~ negative binomial with mean lambda and variance lambda + phi lambda^2, drawn as
+ *       Poisson(lambda G), G ~ Gamma(1/phi, phi) by Marsaglia-Tsang;
+ *   dropout_p in (0, 1]: every entry is independently set to 0 with that probability (the parallel form of the reference's
+ *       commented-out "zero a random share of each gene's cells");
+ *   per entry the uniforms (supplied, or the Philox stream of scr_counts) are consumed in the order dropout, Gamma, Poisson:
+ *   restated in oracle/poisson_oracle.c (oracle_counts_ext_batch), bit-exact given the same uniforms.
+ * uniforms / lambda_out as in scr_counts_range (lambda_out receives the rate BEFORE the Gamma factor); out_dtype, overflow_*
+ * as in scr_counts_compact (overflow_out may be NULL for SCR_COUNT_I32). */
+int scr_counts_ext(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const double* shift /* n */, double exp_scale,
+                   const double* size_factors /* cell_count */, uint64_t seed, double nb_dispersion, double dropout_p,
+                   const double* uniforms, int32_t draws_per_entry, int out_dtype, void* counts_out, int out_on_device,
+                   double* lambda_out, int64_t* overflow_out, int64_t overflow_capacity, int64_t* overflow_count);
+
 /* ---- debugging / parity aids ------------------------------------------------------------------ */
 /* raw Philox4x32-10 words for counters (c0..c3)[count] under key (k0,k1): device generator check */
 int scr_debug_philox(scr_ctx* ctx, int64_t count, const uint32_t* ctr4, uint32_t k0, uint32_t k1,

@@ -84,3 +84,62 @@ long oracle_poisson_stream(long entries, const double* lam, const double* u, lon
   }
   return pos;
 }
+
+/* ---- extensions of the read-out (north_star (4): negative-binomial draws and dropout; DEFAULT OFF, not in the
+ * reference, which only has np.random.poisson at MatriSeq.py:884 and a commented-out dropout at MatriSeq.py:887-889).
+ * Own oracle, same contract: explicit uniforms consumed in a fixed order per entry --
+ *   1. dropout_p > 0:  one uniform d; the entry is dropped (count 0) when d < dropout_p, AFTER all its draws were made
+ *      (so the stream position does not depend on the outcome);
+ *   2. nb_phi > 0:     G ~ Gamma(shape 1/phi, scale phi) (mean 1, variance phi) by Marsaglia & Tsang (ACM TOMS 26, 2000):
+ *      shape < 1 -> one uniform for the boost U^(1/shape), shape += 1; then per attempt two uniforms for a Box-Muller normal
+ *      (cos branch) and one for the acceptance test; the rate becomes lam * G (count ~ NB with mean lam, var lam + phi lam^2);
+ *   3. the Poisson sampler above on what is left of the uniforms.
+ * CUDA counterpart: counts_kernel's extension path (scr_counts_ext). */
+static double gamma_mt(double shape, double scale, const double* u, int avail, int* p_io, int* ok) {
+  int p = *p_io;
+  double boost = 1.0;
+  *ok = 1;
+  if (shape < 1.0) {
+    if (p >= avail) { *ok = 0; return 0.0; }
+    boost = pow(u[p++], 1.0 / shape);
+    shape += 1.0;
+  }
+  {
+    const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (;;) {
+      double z, v, U;
+      if (p + 3 > avail) { *ok = 0; *p_io = p; return 0.0; }
+      z = sqrt(-2.0 * log(u[p])) * cos(6.283185307179586 * u[p + 1]);
+      U = u[p + 2];
+      p += 3;
+      v = 1.0 + c * z;
+      if (v <= 0.0) continue;
+      v = v * v * v;
+      if (U < 1.0 - 0.0331 * (z * z) * (z * z) || log(U) < 0.5 * z * z + d * (1.0 - v + log(v))) {
+        *p_io = p;
+        return boost * d * v * scale;
+      }
+    }
+  }
+}
+
+long oracle_counts_ext_batch(long entries, const double* lam, const double* u, int draws, double nb_phi, double dropout_p,
+                             int32_t* counts, int32_t* used_out) {
+  long bad = 0;
+  for (long i = 0; i < entries; ++i) {
+    const double* ui = u + (size_t)i * draws;
+    int p = 0, used = 0, ok = 1, drop = 0;
+    double rate = lam[i];
+    long k;
+    if (dropout_p > 0.0) {
+      if (p >= draws) ok = 0; else drop = ui[p++] < dropout_p;
+    }
+    if (ok && nb_phi > 0.0 && rate > 0.0) rate *= gamma_mt(1.0 / nb_phi, nb_phi, ui, draws, &p, &ok);
+    k = ok ? poisson_one(rate, ui + p, draws - p, &used) : -1;
+    if (k >= 0 && drop) k = 0;
+    counts[i] = (int32_t)k;
+    if (used_out) used_out[i] = p + used;
+    if (k < 0) bad++;
+  }
+  return bad;
+}

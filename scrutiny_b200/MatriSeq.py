@@ -309,9 +309,13 @@ def findAllNextStates(gc, cellTypeNode, cellTypeTree, currentStates, cellTypesRe
 
 
 def transformData(n, cells, finalCellStates, dropoutProportion=0.0, cellRadiusDisp=0.14, geneScale=0.0, expScale=1.0,
-                  expLambda=0.0, shape=0.35, rate=0.19, gammaDistMean=True, precision=None, capture=None, compact=None):
+                  expLambda=0.0, shape=0.35, rate=0.19, gammaDistMean=True, precision=None, capture=None, compact=None,
+                  applyDropout=False, nbDispersion=0.0):
     """MS:816-891 -> (counts (n, cells) float64 holding integers, cellSizeFactors).
     ``dropoutProportion`` is accepted and unused, exactly like the reference (MS:819).
+    ``applyDropout=True`` (extension, default off): every entry is independently zeroed with probability
+    ``dropoutProportion`` -- the parallel form of the reference's commented-out dropout (MS:887-889); ``nbDispersion`` phi > 0
+    (extension, default off): negative-binomial counts with mean lambda and variance lambda + phi lambda^2 instead of Poisson.
     ``compact`` (extension): False -> always the reference's dense float64 array; True -> an
     ``artefacts.CountMatrix`` (unsigned bytes + overflow list on the host, 1/8 of the bytes, reads like the reference's
     array); None (default) -> dense up to ``artefacts.DENSE_LIMIT`` bytes (2 GiB), compact above.
@@ -323,10 +327,12 @@ def transformData(n, cells, finalCellStates, dropoutProportion=0.0, cellRadiusDi
         eng.alloc_cells(cells)
         eng.set_states(finalCellStates)
         sim = LineageSimulation(eng, cells, seed=_next_seed())
-        dense = compact is False or (compact is None and 8 * n * cells <= _artefacts.DENSE_LIMIT) or capture is not None
+        ext = dict(nb_dispersion=float(nbDispersion), dropout=float(dropoutProportion) if applyDropout else 0.0)
+        dense = (compact is False or (compact is None and 8 * n * cells <= _artefacts.DENSE_LIMIT) or capture is not None
+                 or ext["nb_dispersion"] > 0 or ext["dropout"] > 0)
         counts, size = sim.counts(cellRadiusDisp=cellRadiusDisp, expScale=expScale, shape=shape, rate=rate,
                                   geneScale=geneScale, expLambda=expLambda, gammaDistMean=gammaDistMean, capture=capture,
-                                  dtype="int32" if dense else "uint8")
+                                  dtype="int32" if dense else "uint8", **ext)
     finally:
         eng.close()
     if dense:

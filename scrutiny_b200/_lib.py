@@ -47,6 +47,8 @@ SIGNATURES = {
                                    C.c_void_p, C.c_int, _f64p]),
     "scr_counts_compact": (C.c_int, [c_ctx, C.c_int64, C.c_int64, _f64p, C.c_double, _f64p, C.c_uint64, C.c_int, C.c_void_p,
                                      C.c_int, _i64p, C.c_int64, _i64p]),
+    "scr_counts_ext": (C.c_int, [c_ctx, C.c_int64, C.c_int64, _f64p, C.c_double, _f64p, C.c_uint64, C.c_double, C.c_double,
+                                 _f64p, C.c_int32, C.c_int, C.c_void_p, C.c_int, _f64p, _i64p, C.c_int64, _i64p]),
     "scr_set_genes": (C.c_int, [c_ctx, C.c_int32]),
     "scr_debug_philox": (C.c_int, [c_ctx, C.c_int64, _u32p, C.c_uint32, C.c_uint32, _u32p]),
     "scr_debug_noise": (C.c_int, [c_ctx, C.c_int64, C.c_uint32, C.c_double, C.c_uint64, C.c_uint32, _f64p]),

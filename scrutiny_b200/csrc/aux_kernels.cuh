@@ -128,6 +128,27 @@ __device__ inline int poisson_draw(double lam, UniformSource& u) {
   return static_cast<int>(lam);
 }
 
+// Extension of the read-out (north_star (4), default off; restated in oracle/poisson_oracle.c gamma_mt): G ~ Gamma(shape,
+// scale) by Marsaglia & Tsang (ACM TOMS 26, 2000) over the entry's uniform stream -- shape < 1: one uniform for the boost
+// U^(1/shape); per attempt two uniforms for a Box-Muller normal (cos branch) and one for the acceptance test.
+__device__ inline double gamma_mt(double shape, double scale, UniformSource& u) {
+  double boost = 1.0;
+  if (shape < 1.0) {
+    boost = pow(u.next(), 1.0 / shape);
+    shape += 1.0;
+  }
+  const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (int guard = 0; guard < 1000; ++guard) {
+    const double u1 = u.next(), u2 = u.next(), U = u.next();
+    const double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+    double v = 1.0 + c * z;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    if (U < 1.0 - 0.0331 * (z * z) * (z * z) || log(U) < 0.5 * z * z + d * (1.0 - v + log(v))) return boost * d * v * scale;
+  }
+  return shape * scale;   // unreachable unless the uniforms are degenerate
+}
+
 // Float32 screening of the multiplication method (lambda < 10), EXACT by construction: the same Philox words, the same
 // draw order, but product and threshold carried in float32 with a guard band.  With eps = 2^-24:
 //   lambda_f = ex2(t2) * size  (t2 = log2(e) * expScale * (x + shift) rounded to float32, |t2| < 64, size in [0.05, 8]):
@@ -156,12 +177,86 @@ __device__ __forceinline__ int poisson_small_f32(float lam_f, uint32_t gene, uin
   return -1;
 }
 
+// Float32 screening of Hoermann's PTRS sampler (10 < lambda < kPtrsLamMax), EXACT by construction like poisson_small_f32:
+// the same Philox words in the same order -- uniforms 2i, 2i+1 are (U, V) of draw i -- every quantity the float64 sampler
+// compares is formed in float32 and a decision is only taken when it clears a guard band wider than the float32 error;
+// anything closer, and any draw that needs more than 16 pairs, returns -1 and the caller runs the float64 sampler from the
+// first uniform again.  With eps = 2^-24 and lam_f within 1e-6 lambda of the float64 rate (see poisson_small_f32):
+//   b_f, a_f, vr_f, invalpha_f: relative error <= 1e-6 (sqrt.approx 1 ulp, FMAs), a_f absolute <= 2e-6;
+//   u_f, V_f (one I2F + one FMA): absolute <= 6e-8, so us_f = 0.5 - |u_f - 0.5| absolute <= 1.2e-7;
+//   q = 2 a / us (rcp.approx 1 ulp): relative <= 1e-5 + 1.2e-7 / us;
+//   x = (q + b) U + lambda + 0.43: absolute <= 1e-6 lambda + 1.2e-4 + q (5e-6 + 6e-8 / us)
+//       -> floor(x) is trusted when frac(x) is further than g = 2e-6 lambda + 3e-4 + q (1e-5 + 2e-7 / us) from 0 and 1;
+//   "us >= 0.07", "us < 0.013": decided outside +-1e-6;  "V <= vr": outside +-2e-6;  "V > us": outside +-1e-6;
+//   full test ln V + ln invalpha - ln(a / us^2 + b) <= -lambda + k ln lambda - lgamma(k + 1) (lg2.approx absolute 2.4e-7,
+//   lgamma from a float32 table of the exact values, cancellation at magnitude <= 8200 -> ulp 4.9e-4): both sides together
+//   within 1.5e-3 + 2e-6 k + 1e-7 / V + 5e-7 / us; decided outside G = 3e-3 + 4e-6 k + 2e-7 / V + 1e-6 / us.
+// tests/test_counts_guard.py replays this arithmetic on the host against the C oracle; the GPU suite compares both device
+// paths entry for entry (3e8 entries in test_count_readout_moments_at_scale).
+constexpr float kPtrsLamMax = 1000.0f;
+constexpr int kLgamTable = 2048;                     // lgamma(k + 1), k < 2048 (lambda + 10 sqrt(lambda) < 1320)
+__device__ __forceinline__ int poisson_ptrs_f32(float lam, uint32_t gene, uint64_t gid, const RoundKeys& rk,
+                                                const float* __restrict__ lgam) {
+  const float slam = ptx_sqrt(lam);
+  const float b = fmaf(2.53f, slam, 0.931f);
+  const float a = fmaf(0.02483f, b, -0.059f);
+  const float vr = fmaf(-3.6224f, ptx_rcp(b - 2.0f), 0.9277f);
+  const float g0 = fmaf(2e-6f, lam, 3e-4f);
+  const float a2 = a + a;
+  for (uint32_t call = 0; call < 8; ++call) {
+    uint32_t w[4];
+    philox4x32_10_rk(gene, call, static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), rk, w);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u = fmaf(__uint2float_rn(w[2 * h]), 2.3283064365386963e-10f, 1.16415321826934814e-10f);
+      const float V = fmaf(__uint2float_rn(w[2 * h + 1]), 2.3283064365386963e-10f, 1.16415321826934814e-10f);
+      const float U = u - 0.5f;
+      const float us = 0.5f - fabsf(U);
+      if (fabsf(us - 0.07f) < 1e-6f || fabsf(us - 0.013f) < 1e-6f) return -1;
+      const float rus = ptx_rcp(us);
+      const float q = a2 * rus;
+      const float x = fmaf(q + b, U, lam + 0.43f);
+      const float g = fmaf(q, fmaf(2e-7f, rus, 1e-5f), g0);
+      const float kf = floorf(x);
+      const float fr = x - kf;
+      const bool k_exact = fr > g && fr < 1.0f - g;
+      if (us > 0.07f) {
+        if (V < vr - 2e-6f) return k_exact ? static_cast<int>(kf) : -1;
+        if (V < vr + 2e-6f) return -1;
+      }
+      if (x < g) {                       // kf < 0 -> next draw (only the sign matters here)
+        if (x < -g) continue;
+        return -1;
+      }
+      if (us < 0.013f) {                 // squeeze: V > us -> next draw
+        if (V > us + 1e-6f) continue;
+        if (V > us - 1e-6f) return -1;
+      }
+      if (!k_exact || kf >= static_cast<float>(kLgamTable)) return -1;
+      const float lhs = (ptx_lg2(V) + ptx_lg2(fmaf(1.1328f, ptx_rcp(b - 3.4f), 1.1239f)) - ptx_lg2(fmaf(a, rus * rus, b))) * 0.69314718055994531f;
+      const float rhs = fmaf(kf, ptx_lg2(lam) * 0.69314718055994531f, -lam) - lgam[static_cast<int>(kf)];
+      const float G = fmaf(4e-6f, kf, 3e-3f) + 2e-7f * ptx_rcp(V) + 1e-6f * rus;
+      if (lhs < rhs - G) return static_cast<int>(kf);
+      if (lhs > rhs + G) continue;
+      return -1;
+    }
+  }
+  return -1;
+}
+
+// one gene of the read-out, in the order the kernel walks them (sorted by shift): one 16-byte load per entry instead of
+// the chain order -> inverse permutation -> shift
+struct __align__(16) CountGene { int gene; int state_idx; double shift; };
+
 // one CTA per cell of the chunk.  Thread t handles gene `order[t]`, where `order` sorts the genes by
 // their shift (the dominant term of log lambda): the 32 lanes of a warp then see similar lambda and leave
 // the sampler's loops together instead of waiting for the largest one.  Counts are staged in shared
 // memory and written as one coalesced int32 row in the caller's gene order.
 // FAST (free-running Philox stream, no lambda dump): entries with lambda < 10 go through poisson_small_f32 first and
 // fall back to the float64 sampler only when it declines; results are identical to FAST = false.
+#ifndef SCR_COUNTS_PTRS_F32
+#define SCR_COUNTS_PTRS_F32 1   // 0: lambda >= 10 always through the float64 sampler (A/B builds)
+#endif
 #ifndef SCR_COUNTS_CTAS_PER_SM
 #define SCR_COUNTS_CTAS_PER_SM 4   // 64 registers: the sampler is latency-bound (dependent FP64 chains), more warps pay (2 / 3 / 4 CTAs: 28.8 / 22.5 / 21.5 ms at 400k cells)
 #endif
@@ -175,12 +270,13 @@ template <> struct CountLimit<uint8_t> { static constexpr int kEscape = 0xff; };
 
 template <typename T, bool FAST, typename OUT>
 __global__ void __launch_bounds__(256, SCR_COUNTS_CTAS_PER_SM)
-counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ inv,
-                              const int* __restrict__ order, int n, int64_t cell0, const double* __restrict__ shift,
+counts_kernel(const T* __restrict__ state, int64_t ld, const CountGene* __restrict__ genes, const float* __restrict__ lgam,
+                              int n, int64_t cell0,
                               double exp_scale, const double* __restrict__ sizef, const RoundKeys rk,
                               int64_t cell_offset, const double* __restrict__ uniforms, int draws,
                               OUT* __restrict__ out, double* __restrict__ lam_out, int* err,
-                              int32_t* __restrict__ ovf, unsigned long long ovf_cap, unsigned long long* __restrict__ ovf_count) {
+                              int32_t* __restrict__ ovf, unsigned long long ovf_cap, unsigned long long* __restrict__ ovf_count,
+                              double nb_phi, double dropout_p) {
   extern __shared__ int32_t s_counts[];
   const int64_t c = cell0 + blockIdx.x;   // local slot
   const uint64_t gid = static_cast<uint64_t>(cell_offset + c);
@@ -190,18 +286,22 @@ counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ i
   const float sf_f = static_cast<float>(sf);
   const double esl = exp_scale * 1.4426950408889634;
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    const int o = order[t];
-    const double x = static_cast<double>(row[inv[o]]);
+    const CountGene cg = genes[t];
+    const int o = cg.gene;
+    const double x = static_cast<double>(row[cg.state_idx]);
     int cnt = -1;
     if (FAST && sf_ok) {
-      const float t2 = static_cast<float>((x + shift[o]) * esl);
-      if (t2 > -64.0f && t2 < 8.0f) {
+      const float t2 = static_cast<float>((x + cg.shift) * esl);
+      if (t2 > -64.0f && t2 < 12.0f) {
         const float lam_f = ptx_ex2(t2) * sf_f;
         if (lam_f < 9.999f) cnt = poisson_small_f32(lam_f, static_cast<uint32_t>(o), gid, rk);
+#if SCR_COUNTS_PTRS_F32
+        else if (lam_f > 10.001f && lam_f < kPtrsLamMax) cnt = poisson_ptrs_f32(lam_f, static_cast<uint32_t>(o), gid, rk, lgam);
+#endif
       }
     }
     if (cnt < 0) {
-      double lam = exp(exp_scale * (x + shift[o])) * sf;
+      double lam = exp(exp_scale * (x + cg.shift)) * sf;
       if (lam < 0.0) lam = 0.0;
       UniformSource u;
       u.supplied = uniforms;
@@ -213,8 +313,14 @@ counts_kernel(const T* __restrict__ state, int64_t ld, const int* __restrict__ i
       u.c3 = static_cast<uint32_t>(gid >> 32);
       u.rk = &rk; u.call = 0; u.have = 0; u.err = err;
       u.w0 = u.w1 = u.w2 = u.w3 = 0;
-      cnt = poisson_draw(lam, u);
       if (lam_out) lam_out[static_cast<int64_t>(blockIdx.x) * n + o] = lam;
+      // extensions, default off (FAST launches never have them): dropout uniform first, then the Gamma factor of the
+      // negative-binomial draw, then the Poisson sampler -- the order oracle_counts_ext_batch consumes uniforms in
+      bool drop = false;
+      if (dropout_p > 0.0) drop = u.next() < dropout_p;
+      if (nb_phi > 0.0 && lam > 0.0) lam *= gamma_mt(1.0 / nb_phi, nb_phi, u);
+      cnt = poisson_draw(lam, u);
+      if (drop) cnt = 0;
     }
     s_counts[o] = cnt;
   }

@@ -72,10 +72,11 @@ struct scr_ctx {
   size_t stage_elems = 0;
   // read-out scratch, kept between scr_counts calls (cudaMalloc / cudaFree of the 256 MB staging buffers
   // synchronise the device and cost more than the kernel itself)
-  double *d_cshift = nullptr, *d_csize = nullptr;
-  int* d_corder = nullptr;
+  double* d_csize = nullptr;
+  scr::CountGene* d_ctab = nullptr;          // genes of the read-out sorted by shift: {gene, state index, shift}
+  float* d_lgam = nullptr;                   // lgamma(k + 1), k < scr::kLgamTable (float32 PTRS screening)
   int32_t* d_cbuf[2] = {nullptr, nullptr};
-  size_t cshift_cap = 0, csize_cap = 0, corder_cap = 0, cbuf_cap[2] = {0, 0};
+  size_t ctab_cap = 0, csize_cap = 0, cbuf_cap[2] = {0, 0};
   int32_t* d_covf = nullptr;                 // compact read-out: overflow triplets {local cell, gene, count}
   unsigned long long* d_covf_count = nullptr;
   size_t covf_cap = 0;
@@ -790,11 +791,11 @@ int ensure_buf(scr_ctx* ctx, P*& ptr, size_t& cap, size_t elems) {
   return SCR_OK;
 }
 void free_counts_scratch(scr_ctx* ctx) {
-  cudaFree(ctx->d_cshift); cudaFree(ctx->d_csize); cudaFree(ctx->d_corder); cudaFree(ctx->d_cbuf[0]); cudaFree(ctx->d_cbuf[1]);
+  cudaFree(ctx->d_ctab); cudaFree(ctx->d_csize); cudaFree(ctx->d_lgam); cudaFree(ctx->d_cbuf[0]); cudaFree(ctx->d_cbuf[1]);
   cudaFree(ctx->d_covf); cudaFree(ctx->d_covf_count);
-  ctx->d_cshift = ctx->d_csize = nullptr; ctx->d_corder = nullptr; ctx->d_cbuf[0] = ctx->d_cbuf[1] = nullptr;
+  ctx->d_ctab = nullptr; ctx->d_csize = nullptr; ctx->d_lgam = nullptr; ctx->d_cbuf[0] = ctx->d_cbuf[1] = nullptr;
   ctx->d_covf = nullptr; ctx->d_covf_count = nullptr;
-  ctx->cshift_cap = ctx->csize_cap = ctx->corder_cap = ctx->cbuf_cap[0] = ctx->cbuf_cap[1] = ctx->covf_cap = 0;
+  ctx->ctab_cap = ctx->csize_cap = ctx->cbuf_cap[0] = ctx->cbuf_cap[1] = ctx->covf_cap = 0;
 }
 
 int ensure_stage(scr_ctx* ctx, size_t elems) {
@@ -1184,8 +1185,9 @@ namespace {
 int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const double* shift, double exp_scale,
                 const double* size_factors, uint64_t seed, const double* uniforms, int32_t draws_per_entry,
                 void* counts_out, int out_on_device, double* lambda_out, int out_dtype, int64_t* ovf_out,
-                int64_t ovf_cap, int64_t* ovf_count_out) {
+                int64_t ovf_cap, int64_t* ovf_count_out, double nb_phi = 0.0, double dropout_p = 0.0) {
   NEED_GPU();
+  if (!(nb_phi >= 0.0) || !(dropout_p >= 0.0) || dropout_p > 1.0) return fail(ctx, SCR_E_ARG, "bad extension parameters");
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (!shift || !size_factors || !counts_out) return fail(ctx, SCR_E_ARG, "bad arguments");
   if (out_dtype != SCR_COUNT_I32 && out_dtype != SCR_COUNT_U16 && out_dtype != SCR_COUNT_U8) return fail(ctx, SCR_E_ARG, "bad count dtype");
@@ -1202,16 +1204,22 @@ int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const doub
   std::vector<int> order(n);
   for (int i = 0; i < n; ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return shift[a] < shift[b]; });
-  if ((rc = ensure_buf(ctx, ctx->d_corder, ctx->corder_cap, static_cast<size_t>(n)))) return rc;
-  if ((rc = ensure_buf(ctx, ctx->d_cshift, ctx->cshift_cap, static_cast<size_t>(n)))) return rc;
+  std::vector<scr::CountGene> tab(n);
+  for (int t = 0; t < n; ++t) tab[t] = scr::CountGene{order[t], ctx->op.inv[order[t]], shift[order[t]]};
+  if ((rc = ensure_buf(ctx, ctx->d_ctab, ctx->ctab_cap, static_cast<size_t>(n)))) return rc;
   if ((rc = ensure_buf(ctx, ctx->d_csize, ctx->csize_cap, static_cast<size_t>(cells)))) return rc;
+  if (!ctx->d_lgam) {
+    std::vector<float> lg(scr::kLgamTable);
+    for (int k = 0; k < scr::kLgamTable; ++k) lg[k] = static_cast<float>(std::lgamma(static_cast<double>(k) + 1.0));
+    CK(cudaMalloc(&ctx->d_lgam, lg.size() * sizeof(float)));
+    CK(cudaMemcpy(ctx->d_lgam, lg.data(), lg.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   const unsigned long long dev_ovf_cap = esz < 4 ? static_cast<unsigned long long>(std::max<int64_t>(ovf_cap, 0)) : 0ULL;
   if (esz < 4) {
     if ((rc = ensure_buf(ctx, ctx->d_covf, ctx->covf_cap, static_cast<size_t>(3 * dev_ovf_cap + 3)))) return rc;
     if (!ctx->d_covf_count) CK(cudaMalloc(&ctx->d_covf_count, sizeof(unsigned long long)));
   }
-  double *d_shift = ctx->d_cshift, *d_size = ctx->d_csize;
-  int* d_order = ctx->d_corder;
+  double* d_size = ctx->d_csize;
 #define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
   if (n * sizeof(int32_t) > 48 * 1024 && !ctx->counts_smem_optin) {   // staging row beyond the default 48 KB of dynamic shared memory
     if (n * sizeof(int32_t) > static_cast<size_t>(ctx->smem_optin)) return fail(ctx, SCR_E_RESOURCE, "count read-out: n too large for the per-cell staging row");
@@ -1222,8 +1230,7 @@ int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const doub
 #undef SCR_OPTIN
     ctx->counts_smem_optin = true;
   }
-  CKC(cudaMemcpyAsync(d_order, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CKC(cudaMemcpyAsync(d_shift, shift, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemcpyAsync(ctx->d_ctab, tab.data(), n * sizeof(scr::CountGene), cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemcpyAsync(d_size, size_factors, cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));   // entry r <-> slot cell_begin + r
   CKC(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
   if (esz < 4) CKC(cudaMemsetAsync(ctx->d_covf_count, 0, sizeof(unsigned long long), ctx->stream));
@@ -1239,14 +1246,14 @@ int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const doub
   const double* size_by_slot = d_size - cell_begin;
   // free-running stream without a lambda dump: float32 screening of the lambda < 10 sampler (identical integers,
   // aux_kernels.cuh); SCR_COUNTS_EXACT=1 forces the float64 sampler for every entry (A/B tests)
-  const bool fast = !uniforms && !lambda_out && scr::env_int("SCR_COUNTS_EXACT", 0) == 0;
+  const bool fast = !uniforms && !lambda_out && nb_phi == 0.0 && dropout_p == 0.0 && scr::env_int("SCR_COUNTS_EXACT", 0) == 0;
   auto launch = [&](int64_t c0, int64_t cnt, void* out, double* lam) -> cudaError_t {
     const double* uni_by_slot = d_uni ? d_uni - cell_begin * n * static_cast<int64_t>(draws_per_entry) : nullptr;
 #define SCR_LAUNCH_COUNTS(T, FAST, OUT) \
     scr::counts_kernel<T, FAST, OUT><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>( \
-        static_cast<const T*>(ctx->d_state), ctx->op.n_pad, ctx->d_inv, d_order, n, cell_begin + c0, d_shift, exp_scale, \
+        static_cast<const T*>(ctx->d_state), ctx->op.n_pad, ctx->d_ctab, ctx->d_lgam, n, cell_begin + c0, exp_scale, \
         size_by_slot, crk, ctx->cell_offset, uni_by_slot, draws_per_entry, static_cast<OUT*>(out), lam, ctx->d_err, \
-        ctx->d_covf, dev_ovf_cap, ctx->d_covf_count)
+        ctx->d_covf, dev_ovf_cap, ctx->d_covf_count, nb_phi, dropout_p)
 #define SCR_LAUNCH_PREC(OUT) \
     if (ctx->prec == SCR_F64) { if (fast) SCR_LAUNCH_COUNTS(double, true, OUT); else SCR_LAUNCH_COUNTS(double, false, OUT); } \
     else                      { if (fast) SCR_LAUNCH_COUNTS(float, true, OUT);  else SCR_LAUNCH_COUNTS(float, false, OUT); }
@@ -1328,6 +1335,14 @@ int scr_counts_compact(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, con
                        int64_t* overflow_out, int64_t overflow_capacity, int64_t* overflow_count) {
   return counts_impl(ctx, cell_begin, cell_count, shift, exp_scale, size_factors, seed, nullptr, 0, counts_out, out_on_device,
                      nullptr, out_dtype, overflow_out, overflow_capacity, overflow_count);
+}
+
+int scr_counts_ext(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const double* shift, double exp_scale,
+                   const double* size_factors, uint64_t seed, double nb_dispersion, double dropout_p, const double* uniforms,
+                   int32_t draws_per_entry, int out_dtype, void* counts_out, int out_on_device, double* lambda_out,
+                   int64_t* overflow_out, int64_t overflow_capacity, int64_t* overflow_count) {
+  return counts_impl(ctx, cell_begin, cell_count, shift, exp_scale, size_factors, seed, uniforms, draws_per_entry, counts_out,
+                     out_on_device, lambda_out, out_dtype, overflow_out, overflow_capacity, overflow_count, nb_dispersion, dropout_p);
 }
 
 int scr_counts(scr_ctx* ctx, const double* shift, double exp_scale, const double* size_factors, uint64_t seed,

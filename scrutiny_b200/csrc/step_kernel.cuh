@@ -476,8 +476,12 @@ __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&)[2][kWordsPe
 constexpr int kMaxBlocks = 128;                 // n_pad <= 16384 (a cell group of that size cannot fit an SM anyway)
 constexpr int kRecBytes = kMaxBlocks * 16;
 constexpr int kFixedTab = kRecBytes + 128;
-constexpr int kGroupHdr = 400;                  // ctrl 16 | mbarriers 24 (+8 pad) | CellRound0 48 | steps 16 | cells 16 | step bases 16 | probe partials 16 x 16
-constexpr int kHdrBar = 16, kHdrR0 = 48, kHdrSteps = 96, kHdrCells = 112, kHdrBase = 128, kHdrRed = 144;
+// ctrl 16 | mbarriers 24 (+8 pad) | CellRound0 48 | steps 16 | cells 16 | step bases 16 | caller rows 16 | probe partials 16 x 16 |
+// probe window: the last kProbeRing values of mean|dx|/dt per cell (float64)
+constexpr int kProbeRing = 32;
+constexpr int kHdrBar = 16, kHdrR0 = 48, kHdrSteps = 96, kHdrCells = 112, kHdrBase = 128, kHdrRows = 144, kHdrRed = 160,
+              kHdrRing = kHdrRed + 256;
+constexpr int kGroupHdr = kHdrRing + 4 * kProbeRing * 8;
 // block record flags
 constexpr int kBlkPP = 1, kBlkLong = 2, kBlkLastReg = 4, kBlkFirstPP = 8, kBlkBias = 16, kBlkFlagMask = 127;
 
@@ -600,7 +604,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   int* hsteps = reinterpret_cast<int*>(ghdr + kHdrSteps);
   int* hcells = reinterpret_cast<int*>(ghdr + kHdrCells);
   uint32_t* hbase = reinterpret_cast<uint32_t*>(ghdr + kHdrBase);   // iterations done before this phase (Philox counter word c1 = base + s)
+  int* hrows = reinterpret_cast<int*>(ghdr + kHdrRows);             // position of each cell in the caller's list
   RowT* red = reinterpret_cast<RowT*>(ghdr + kHdrRed);              // PROBE: per-warp partial sums of |dx|
+  double* ring = reinterpret_cast<double*>(ghdr + kHdrRing);        // PROBE: [cell][kProbeRing] window of the convergence trace
   unsigned char* bufA = ghdr + kGroupHdr;
   unsigned char* bufB = bufA + static_cast<size_t>(p.n_pad) * 16;
   RowT* ovf = reinterpret_cast<RowT*>(bufB + static_cast<size_t>(p.npp) * 16);
@@ -632,6 +638,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         hsteps[c] = it.steps[c];
         hcells[c] = it.cell[c];
         hbase[c] = it.base[c];
+        hrows[c] = it.row[c];
       }
     }
 
@@ -667,11 +674,11 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
     for (int c = 0; c < CPG; ++c) smin = min(smin, it.steps[c]);
     constexpr uint32_t full_mask = (1u << CPG) - 1u;
     uint32_t alive = 0;       // PROBE: bit c set while cell c is still iterating
-    int iters[CPG];
+    int my_iters = 0;         // PROBE: iterations of cell `lane` (lanes 0 .. CPG-1 of the group's first warp keep the books)
     if (PROBE) {
       smax = p.max_iter;
 #pragma unroll
-      for (int c = 0; c < CPG; ++c) { iters[c] = 0; if (it.cell[c] >= 0) alive |= 1u << c; }
+      for (int c = 0; c < CPG; ++c) { if (it.cell[c] >= 0) alive |= 1u << c; }
     }
     const T wscale = PROBE ? static_cast<T>(it.scale) : T(1);
 
@@ -980,23 +987,32 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
 #endif
 
       if (PROBE) {
-        if (qtid == 0) {
-#pragma unroll
-          for (int c = 0; c < CPG; ++c) {
-            if ((alive >> c) & 1u) {
-              double tot = 0.0;
-              for (int w = 0; w < p.wq; ++w) tot += static_cast<double>(red[w].v[c]);
-              double* trace = p.nd + static_cast<int64_t>(it.row[c]) * p.max_iter;
-              trace[s] = tot / (static_cast<double>(p.n) * static_cast<double>(p.dt));
-              iters[c] = s + 1;
-              if (s >= p.avg_num - 1) {
-                double acc = 0.0;
+        // stopping rule of MatriSeq.py:657-668, one lane per cell: mean of the last avg_num values of mean|dx|/dt, summed in
+        // index order from a shared-memory window (the global trace is only written, for the caller)
+        if (wq == 0) {
+          bool still = false;
+          if (lane < CPG && ((alive >> lane) & 1u)) {
+            double tot = 0.0;
+            for (int w = 0; w < p.wq; ++w) tot += static_cast<double>(red[w].v[lane]);
+            double* trace = p.nd + static_cast<int64_t>(hrows[lane]) * p.max_iter;
+            const double val = tot / (static_cast<double>(p.n) * static_cast<double>(p.dt));
+            trace[s] = val;
+            double* win = ring + lane * kProbeRing;
+            win[s & (kProbeRing - 1)] = val;
+            my_iters = s + 1;
+            still = true;
+            if (s >= p.avg_num - 1) {
+              double acc = 0.0;
+              if (p.avg_num <= kProbeRing) {
+                for (int i = s - p.avg_num + 1; i <= s; ++i) acc += win[i & (kProbeRing - 1)];
+              } else {
                 for (int i = s - p.avg_num + 1; i <= s; ++i) acc += trace[i];
-                if (acc / p.avg_num <= p.thresh) alive &= ~(1u << c);
               }
+              if (acc / p.avg_num <= p.thresh) still = false;
             }
           }
-          ctrl[1] = static_cast<int>(alive);
+          const uint32_t m = __ballot_sync(0xffffffffu, still);
+          if (lane == 0) ctrl[1] = static_cast<int>(m);
         }
         named_bar_sync(bar_id, qthreads);
         alive = static_cast<uint32_t>(ctrl[1]);
@@ -1012,11 +1028,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
       if (SCR_EARLY_READ_ARRIVE) named_bar_sync(bar_id, qthreads);
     }
     if (PROBE) {
-      if (qtid == 0) {
-#pragma unroll
-        for (int c = 0; c < CPG; ++c)
-          if (it.cell[c] >= 0) p.iters_out[it.row[c]] = iters[c];
-      }
+      if (wq == 0 && lane < CPG && hcells[lane] >= 0) p.iters_out[hrows[lane]] = my_iters;
     } else {
       // ---- write the group back: interleaved -> CPG cell rows ----
       for (int g0 = qtid * CPG; g0 < p.n_pad; g0 += qthreads * CPG) {

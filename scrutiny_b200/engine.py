@@ -241,6 +241,26 @@ class Engine:
                                                _ptr(uni, C.c_double), int(draws), ptr, on_dev, _ptr(lam, C.c_double)))
         return (out, lam) if want_lambda else out
 
+    def counts_ext(self, shift, size_factors, nb_dispersion=0.0, dropout=0.0, exp_scale=1.0, seed=0, uniforms=None,
+                   want_lambda=False, cell_begin=0, cell_count=None):
+        """Read-out with the default-off extensions (scr_counts_ext): negative-binomial draws with dispersion
+        ``nb_dispersion`` (variance lambda + phi lambda^2) and Bernoulli ``dropout``.  int32 (rows, n) host result."""
+        rows = self.cells - int(cell_begin) if cell_count is None else int(cell_count)
+        shift, size_factors = _f64(shift), _f64(size_factors)
+        assert len(size_factors) == rows and len(shift) == self.n
+        uni, draws = None, 0
+        if uniforms is not None:
+            uni = _f64(uniforms)
+            assert uni.shape[:2] == (rows, self.n)
+            draws = uni.shape[2]
+        lam = np.zeros((rows, self.n)) if want_lambda else None
+        out = np.empty((rows, self.n), dtype=np.int32)
+        self._check(self._lib.scr_counts_ext(self._ctx, int(cell_begin), rows, _ptr(shift, C.c_double), float(exp_scale),
+                                             _ptr(size_factors, C.c_double), int(seed) & (2 ** 64 - 1), float(nb_dispersion),
+                                             float(dropout), _ptr(uni, C.c_double), int(draws), 0, C.c_void_p(out.ctypes.data), 0,
+                                             _ptr(lam, C.c_double), None, 0, None))
+        return (out, lam) if want_lambda else out
+
     def counts_compact(self, shift, size_factors, exp_scale=1.0, seed=0, dtype="uint8", out=None, out_device_ptr=None,
                        cell_begin=0, cell_count=None, overflow_capacity=None):
         """Free-running read-out stored as ``dtype`` ("uint8" / "uint16" / "int32"), scr_counts_compact.  Returns

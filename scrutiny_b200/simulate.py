@@ -146,12 +146,21 @@ class LineageSimulation:
             shift[order] = target
         return shift
 
-    def counts(self, cellRadiusDisp=0.14, expScale=1.0, out=None, out_device_ptr=None, capture=None, dtype="int32", **kw):
+    def counts(self, cellRadiusDisp=0.14, expScale=1.0, out=None, out_device_ptr=None, capture=None, dtype="int32",
+               nb_dispersion=0.0, dropout=0.0, **kw):
         """transformData (MS:816-891) for this rank's cells.  Returns (counts (cells_local, n) int32,
         all cellSizeFactors); with ``dtype`` "uint8" / "uint16" the first item is ``(compact counts, overflow rows)``.
         ``capture`` (dict, parity aid) receives ``lambda`` (n, cells_local) and ``shift``."""
         shift = self.gene_shift(expScale=expScale, **kw)
         size = np.random.normal(loc=1, scale=cellRadiusDisp, size=self.cells) ** 3   # MS:875-876
+        if nb_dispersion or dropout:                                             # default-off extensions (scr_counts_ext)
+            got = self.eng.counts_ext(shift, size[self.lo:self.hi], nb_dispersion=nb_dispersion, dropout=dropout,
+                                      exp_scale=expScale, seed=self.seed, want_lambda=capture is not None)
+            if capture is not None:
+                got, lam = got
+                capture["lambda"] = np.ascontiguousarray(lam.T)
+                capture["shift"] = shift
+            return got, size
         if dtype != "int32":
             return self.eng.counts_compact(shift, size[self.lo:self.hi], exp_scale=expScale, seed=self.seed, dtype=dtype,
                                            out=out, out_device_ptr=out_device_ptr), size

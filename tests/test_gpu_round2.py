@@ -218,3 +218,65 @@ def test_prepared_mode_with_poisson_member_steps():
     assert abs(k.mean() - T) < 4 * np.sqrt(T / len(root)) and abs(k.var() / T - 1) < 0.15 and k.max() > T
     leaf = np.asarray(tree[3].cellTypeMembers)                            # root T + type-1 T + own Poisson(T)
     assert abs(res["iterations"][leaf].mean() - 3 * T) < 0.5
+
+
+# ---------------------------------------------------------------------------------------------
+# default-off extensions of the read-out: negative-binomial draws, dropout
+# ---------------------------------------------------------------------------------------------
+def test_extension_draws_bit_exact_given_uniforms_and_default_off():
+    """scr_counts_ext against its own C oracle (oracle_counts_ext_batch) on the same uniforms: identical integers for NB
+    (dispersion below and above 1), dropout and both; with both switches at 0 it returns scr_counts_range's integers."""
+    from oracle import poisson_ref
+    n, cells = 96, 60
+    rng = np.random.RandomState(51)
+    e = engine(sparse_net(n, 4), cells, "f64", offset=123)
+    S = np.tanh(rng.randn(n, cells))
+    e.set_states(S)
+    shift = rng.normal(0.6, 1.6, size=n)
+    size = rng.normal(1, 0.14, size=cells) ** 3
+    draws = 120
+    U = rng.random_sample((cells, n, draws))
+    base = e.counts(shift, size, uniforms=U[:, :, :48].copy())
+    off, lam = e.counts_ext(shift, size, 0.0, 0.0, uniforms=U[:, :, :48].copy(), want_lambda=True)
+    assert np.array_equal(base, off)
+    assert np.allclose(lam, fo.poisson_lambda(S, shift, 1.0, size).T, rtol=1e-14)
+    for phi, p in ((0.3, 0.0), (3.0, 0.0), (0.0, 0.4), (0.7, 0.2)):
+        got = e.counts_ext(shift, size, phi, p, uniforms=U)
+        want, used = poisson_ref.counts_ext_batch(lam, U, phi, p)
+        ok = want >= 0
+        assert ok.mean() > 0.999 and np.array_equal(got[ok], want[ok]), (phi, p)
+        assert not np.array_equal(got, base)
+    # free-running stream: switches off == the ordinary read-out
+    a = e.counts(shift, size, seed=9)
+    b = e.counts_ext(shift, size, 0.0, 0.0, seed=9)
+    assert np.array_equal(a, b)
+
+
+def test_extension_moments_free_running_and_module_flags(golden):
+    n, cells = 48, 30000
+    rng = np.random.RandomState(52)
+    e = engine(sparse_net(n, 6), cells, "f32")
+    S = np.repeat(np.tanh(rng.randn(n, 1)), cells, axis=1)              # identical cells: pure sampling noise
+    e.set_states(S)
+    shift = np.linspace(-1.0, 3.0, n)
+    lam = np.exp(S[:, 0].astype(np.float32).astype(np.float64) + shift)
+    phi, p = 0.5, 0.3
+    got = e.counts_ext(shift, np.ones(cells), phi, p, seed=77).astype(np.float64)
+    mean, var = got.mean(axis=0), got.var(axis=0)
+    want_mean = (1 - p) * lam
+    want_var = (1 - p) * (lam + phi * lam ** 2) + p * (1 - p) * lam ** 2     # zero-inflated negative binomial
+    assert np.all(np.abs(mean - want_mean) < 6 * np.sqrt(want_var / cells) + 1e-3)
+    assert np.all(np.abs(var / want_var - 1) < 0.12)
+    assert np.all(np.abs((got == 0).mean(axis=0) - (p + (1 - p) * (1 + phi * lam) ** (-1 / phi))) < 0.012)
+    # through the module: the reference's dropoutProportion stays unused unless applyDropout is set (MS:819)
+    import scrutiny_b200.MatriSeq as ms
+    Sg = golden("pipeline")["final_states"]
+    ng, cg = Sg.shape
+    outs = {}
+    for key, kw in (("plain", {}), ("ignored", dict(dropoutProportion=0.5)), ("drop", dict(dropoutProportion=0.5, applyDropout=True)),
+                    ("nb", dict(nbDispersion=1.0))):
+        ms.init(outputDir=None, seed=21, verbose=False)
+        outs[key] = ms.transformData(ng, cg, Sg.copy(), **kw)[0]
+    assert np.array_equal(outs["plain"], outs["ignored"])
+    assert abs((outs["drop"] == 0).mean() - (0.5 + 0.5 * (outs["plain"] == 0).mean())) < 0.02
+    assert outs["nb"].var() > 1.5 * outs["plain"].var() and abs(outs["nb"].mean() / outs["plain"].mean() - 1) < 0.15
