@@ -200,6 +200,8 @@ double scr_last_kernel_ms(const scr_ctx* ctx);
 /* accumulated device time (ms) and number of scr_run_phase stepping-kernel launches since the
  * last reset; bench.py derives roofline.achieved from these */
 int scr_step_kernel_stats(scr_ctx* ctx, double* total_ms, int64_t* launches, int reset);
+/* the same for the sparse convergence-probe kernel (scr_probe): small configurations spend a large share of a pass there */
+int scr_probe_kernel_stats(scr_ctx* ctx, double* total_ms, int64_t* launches, int reset);
 
 
 /* ---- RegNetInference front end ("RNI" = RNAscrutiny/RNAscrutiny/RegNetInference.py).

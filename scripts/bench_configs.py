@@ -57,24 +57,29 @@ def run(name):
         node.cellTypeMembers = np.asarray(node.cellTypeMembers, dtype=np.int64)
         node.childCellTypeMembers = np.asarray(node.childCellTypeMembers, dtype=np.int64)
     sim.prepare(tree)
-    out = np.empty((cells, n), dtype=np.int32)
+    out = np.empty((cells, n), dtype=np.uint8)                # compact read-out: bytes + overflow list (scr_counts_compact)
     best = None
-    for rep in range(3):
+    for rep in range(4):
         e.set_states_broadcast(x0)
         e.step_kernel_stats(reset=True)
+        e.probe_kernel_stats(reset=True)
         t0 = time.time()
-        res = sim.run_all(tree, counts_out=out, seed=100 + rep)
+        res = sim.run_all(tree, counts_out=out, seed=100 + rep, counts_dtype="uint8")
         wall = time.time() - t0
         kms, launches = e.step_kernel_stats()
-        if best is None or wall < best["wall_s"]:
-            best = dict(wall_s=wall, kernel_ms=kms, kernel_launches=launches, cell_steps=res["global_cell_steps"])
+        pms, plaunches = e.probe_kernel_stats()
+        if rep > 0 and (best is None or wall < best["wall_s"]):
+            best = dict(wall_s=wall, kernel_ms=kms, kernel_launches=launches, cell_steps=res["global_cell_steps"],
+                        probe_kernel_ms=pms, probe_launches=plaunches, overflow=len(res["overflow"]))
     cs = best["cell_steps"]
     line = {"config": name, "genes": n, "nnz": int(np.count_nonzero(gc)), "cells": cells, "alpha": alpha,
             "path": "dense tcgen05 3xTF32" if lay["dense_stepper"] else "sparse smem-resident",
             "node_iterations": sim.node_iterations, "cell_steps": cs,
             "cell_steps_per_s_whole_job": cs / best["wall_s"], "cell_steps_per_s_kernel": cs / (best["kernel_ms"] / 1e3),
             "wall_s": best["wall_s"], "kernel_ms": best["kernel_ms"], "kernel_launches": best["kernel_launches"],
-            "alpha_search_s": t_alpha, "setup_s": t_setup, "counts_sum": int(out.sum()), "zero_fraction": float((out == 0).mean())}
+            "probe_kernel_ms": best["probe_kernel_ms"], "probe_launches": best["probe_launches"],
+            "whole_job_over_kernel": (best["kernel_ms"] / 1e3) / best["wall_s"], "overflow_entries": best["overflow"],
+            "alpha_search_s": t_alpha, "setup_s": t_setup, "counts_sum_bytes": int(out.sum(dtype=np.int64)), "zero_fraction": float((out == 0).mean())}
     if lay["dense_stepper"]:
         line["tflops_3xtf32_issued"] = cs * 6.0 * n * n / (best["kernel_ms"] / 1e3) / 1e12
     else:

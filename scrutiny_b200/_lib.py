@@ -56,6 +56,7 @@ SIGNATURES = {
     "scr_debug_path_launches": (C.c_int64, [c_ctx, C.c_int]),
     "scr_last_kernel_ms": (C.c_double, [c_ctx]),
     "scr_step_kernel_stats": (C.c_int, [c_ctx, _f64p, _i64p, C.c_int]),
+    "scr_probe_kernel_stats": (C.c_int, [c_ctx, _f64p, _i64p, C.c_int]),
     "scr_rank_transform": (C.c_int, [c_ctx, C.c_int64, C.c_int64, _f64p, C.c_int64]),
     "scr_rank_transform_stats": (C.c_int, [c_ctx, _f64p, _i64p, _i64p]),
     "scr_cell_pairs": (C.c_int, [c_ctx, C.c_int64, C.c_int64, _f64p, C.c_int64, _f64p, _i64p, C.c_double,

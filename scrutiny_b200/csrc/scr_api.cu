@@ -88,7 +88,18 @@ struct scr_ctx {
   double rank_kernel_ms = 0.0;
   int64_t rank_counting = 0, rank_sorted = 0;
 
+  // probe scratch, kept between calls (a lineage run probes every node: cudaMalloc / cudaFree synchronise the device)
+  int* d_piters = nullptr;
+  double* d_pnd = nullptr;
+  size_t piters_cap = 0, pnd_cap = 0;
+  // stepper launch configuration per kernel variant [probe][supplied]: the dynamic shared-memory opt-in and the
+  // occupancy query are made once per size, not per launch
+  struct LaunchCfg { size_t smem = 0; int threads = 0, per_sm = 0; };
+  LaunchCfg launch_cfg[2][2];
+
   // stats
+  double total_probe_ms = 0.0;
+  int64_t total_probe_launches = 0;
   int64_t launches = 0;
   double last_ms = -1.0, total_step_ms = 0.0;
   int64_t total_step_launches = 0;
@@ -259,9 +270,14 @@ int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
   const size_t smem = ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * ctx->gbytes + p.w_prefix;
   const int threads = q * ctx->op.wq * 32;
   auto kern = ctx->w_smem ? scr::step_kernel<T, true, PROBE, SUPPLIED> : scr::step_kernel<T, false, PROBE, SUPPLIED>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  int per_sm = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  scr_ctx::LaunchCfg& cfg = ctx->launch_cfg[PROBE ? 1 : 0][SUPPLIED ? 1 : 0];
+  if (cfg.smem != smem || cfg.threads != threads) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    cfg.smem = smem; cfg.threads = threads; cfg.per_sm = occ;
+  }
+  const int per_sm = cfg.per_sm;
   if (per_sm < 1) return fail(ctx, SCR_E_RESOURCE, "stepper does not fit on an SM");
   const int grid = std::max(1, std::min((nitems + q - 1) / q, ctx->sm_count * per_sm));
   CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
@@ -275,6 +291,7 @@ int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_ms = ms;
   if (!PROBE) { ctx->total_step_ms += ms; ctx->total_step_launches++; ctx->sparse_launches++; }
+  else { ctx->total_probe_ms += ms; ctx->total_probe_launches++; }
   return SCR_OK;
 }
 
@@ -320,7 +337,18 @@ int upload_node(scr_ctx* ctx, const double* proj, const double* cnst, double mu,
     CK(cudaMemcpyAsync(ctx->d_bias, bias.data(), bias.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     p.bias = static_cast<const T*>(ctx->d_bias);
   }
-  CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+  // (copies from pageable host memory return once the source has been staged: the vectors may go out of scope)
+  return SCR_OK;
+}
+
+template <typename P>
+int ensure_buf(scr_ctx* ctx, P*& ptr, size_t& cap, size_t elems) {
+  if (elems <= cap) return SCR_OK;
+  cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+  CK(cudaMalloc(&ptr, elems * sizeof(P)));
+  cap = elems;
   return SCR_OK;
 }
 
@@ -755,41 +783,29 @@ int probe_t(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_
   p.thresh = thresh;
   p.max_iter = max_iter;
   p.avg_num = avg_num;
-  int* d_iters = nullptr;
-  double* d_nd = nullptr;
   T* d_noise = nullptr;
   const size_t nd_count = static_cast<size_t>(k) * max_iter;
-  CK(cudaMalloc(&d_iters, k * sizeof(int)));
-  CK(cudaMalloc(&d_nd, nd_count * sizeof(double)));
-  CK(cudaMemsetAsync(d_nd, 0, nd_count * sizeof(double), ctx->stream));
-  p.iters_out = d_iters;
-  p.nd = d_nd;
+  if ((rc = ensure_buf(ctx, ctx->d_piters, ctx->piters_cap, static_cast<size_t>(k)))) return rc;
+  if ((rc = ensure_buf(ctx, ctx->d_pnd, ctx->pnd_cap, nd_count))) return rc;
+  if (normdiff_out) CK(cudaMemsetAsync(ctx->d_pnd, 0, nd_count * sizeof(double), ctx->stream));   // entries past a cell's last iteration read 0
+  p.iters_out = ctx->d_piters;
+  p.nd = ctx->d_pnd;
   if (noise) {
     rc = upload_noise<T>(ctx, noise, nd_count * ctx->op.n, &d_noise);
-    if (rc) { cudaFree(d_iters); cudaFree(d_nd); return rc; }
+    if (rc) return rc;
     p.noise = d_noise;
     p.noise_steps = max_iter;
   }
   rc = launch_step<T>(ctx, p, nitems, true, noise != nullptr);
   if (rc == SCR_OK) {
-    cudaError_t e = cudaMemcpy(iters_out, d_iters, k * sizeof(int), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && normdiff_out) e = cudaMemcpy(normdiff_out, d_nd, nd_count * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(iters_out, ctx->d_piters, k * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && normdiff_out) e = cudaMemcpy(normdiff_out, ctx->d_pnd, nd_count * sizeof(double), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = fail_cuda(ctx, e, "probe result copy");
   }
-  cudaFree(d_iters); cudaFree(d_nd); cudaFree(d_noise);
+  cudaFree(d_noise);
   return rc;
 }
 
-template <typename P>
-int ensure_buf(scr_ctx* ctx, P*& ptr, size_t& cap, size_t elems) {
-  if (elems <= cap) return SCR_OK;
-  cudaFree(ptr);
-  ptr = nullptr;
-  cap = 0;
-  CK(cudaMalloc(&ptr, elems * sizeof(P)));
-  cap = elems;
-  return SCR_OK;
-}
 void free_counts_scratch(scr_ctx* ctx) {
   cudaFree(ctx->d_ctab); cudaFree(ctx->d_csize); cudaFree(ctx->d_lgam); cudaFree(ctx->d_cbuf[0]); cudaFree(ctx->d_cbuf[1]);
   cudaFree(ctx->d_covf); cudaFree(ctx->d_covf_count);
@@ -867,6 +883,7 @@ void scr_destroy(scr_ctx* ctx) {
     free_network(ctx);
     free_dense_work(ctx);
     cudaFree(ctx->d_state); cudaFree(ctx->d_items); cudaFreeHost(ctx->h_items); cudaFree(ctx->d_counter); cudaFree(ctx->d_err); cudaFree(ctx->d_stage);
+    cudaFree(ctx->d_piters); cudaFree(ctx->d_pnd);
     free_counts_scratch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1401,6 +1418,13 @@ int64_t scr_debug_path_launches(const scr_ctx* ctx, int which) {
   return which == 0 ? ctx->sparse_launches : ctx->dense_launches;
 }
 double scr_last_kernel_ms(const scr_ctx* ctx) { return ctx ? ctx->last_ms : -1.0; }
+int scr_probe_kernel_stats(scr_ctx* ctx, double* total_ms, int64_t* launches, int reset) {
+  if (!ctx) return SCR_E_ARG;
+  if (total_ms) *total_ms = ctx->total_probe_ms;
+  if (launches) *launches = ctx->total_probe_launches;
+  if (reset) { ctx->total_probe_ms = 0.0; ctx->total_probe_launches = 0; }
+  return SCR_OK;
+}
 int scr_step_kernel_stats(scr_ctx* ctx, double* total_ms, int64_t* launches, int reset) {
   if (!ctx) return SCR_E_ARG;
   if (total_ms) *total_ms = ctx->total_step_ms;

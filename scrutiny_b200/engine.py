@@ -347,3 +347,9 @@ class Engine:
         n = C.c_int64(0)
         self._check(self._lib.scr_step_kernel_stats(self._ctx, C.byref(ms), C.byref(n), int(reset)))
         return ms.value, n.value
+
+    def probe_kernel_stats(self, reset=False):
+        ms = C.c_double(0)
+        n = C.c_int64(0)
+        self._check(self._lib.scr_probe_kernel_stats(self._ctx, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value
