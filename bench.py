@@ -84,28 +84,13 @@ def build_network(n, kind="powerlaw"):
 
 
 def build_tree(n, cells, tf, parents=PARENTS, shares=SHARES, const_props=CONST_PROPS):
-    """Same structure formCellTypeTree builds (MatriSeq.py:175-297): every cell gets its final type
-    up front (a random permutation split by SHARES), proj/const inherited down the tree."""
-    from scrutiny_b200.MatriSeq import getNextProjConst
-    from scrutiny_b200.lineage import Tree
+    """formCellTypeTree (MatriSeq.py:175-297) through the module's scalable assignment (one permutation of the cells split
+    by SHARES instead of a Python set difference per type): every cell gets its final type up front, proj/const are
+    inherited down the tree."""
+    import scrutiny_b200.MatriSeq as ms
     counts = [int(round(s * cells)) for s in shares]
     counts[-1] = cells - sum(counts[:-1])
-    perm = np.random.permutation(cells)
-    bounds = np.cumsum([0] + counts)
-    members = [np.sort(perm[bounds[t]:bounds[t + 1]]) for t in range(len(parents))]
-    tree = Tree()
-    tree.add_head(-1, np.zeros(0, dtype=np.int64), np.zeros(n), np.ones(n), 0)
-
-    def attach(parent, proj_up, const_up):
-        below = []
-        for t in [i for i, p in enumerate(parents) if p == parent]:
-            proj, const = getNextProjConst(n, proj_up, const_up, const_props[t], tf)
-            tree.add_node(t, members[t], const, proj, 0, parent)
-            below += attach(t, proj, const) + [members[t]]
-        tree[parent].setChildCellTypeMembers(np.concatenate(below) if below else np.zeros(0, dtype=np.int64))
-        return below
-
-    attach(-1, np.ones(n), np.zeros(n))
+    tree, _, _ = ms.formCellTypeTree(n, cells, parents, counts, const_props, tf, [0] * len(parents), scalable=True)
     return tree
 
 

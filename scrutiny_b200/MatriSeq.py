@@ -83,17 +83,22 @@ def rangeTransformation(x):
 # input producers (host)
 # ------------------------------------------------------------------------------------------
 def generateGeneCorrelationMatrix(n, networkStructure='TRRUST', maxAlphaBeta=10, normalizeWRows=False,
-                                  powerLawExponent=2.05, networkSparsity=0.999, alpha=None):
-    """MS:34-172 -> (gc, tf).  ``alpha`` (extension): divide gc by it right away."""
-    gc, tf = _network.generate_gene_correlation_matrix(n, networkStructure, maxAlphaBeta, normalizeWRows,
-                                                       powerLawExponent, networkSparsity)
+                                  powerLawExponent=2.05, networkSparsity=0.999, alpha=None, sparse=False):
+    """MS:34-172 -> (gc, tf).  The network is generated as CSR (O(nnz + n) memory, same random stream as the reference);
+    ``gc`` is the reference's dense (n, n) float64 array unless ``sparse=True`` (extension), which returns a
+    ``scipy.sparse.csr_matrix`` every function of this module accepts in its place.  ``alpha`` (extension): divide gc by it
+    right away."""
+    n, rowptr, col, val, tf = _network.generate_csr(n, networkStructure, maxAlphaBeta, normalizeWRows, powerLawExponent,
+                                                    networkSparsity)
     if __verbose:
-        nnz = np.count_nonzero(gc)
-        print("Number of Connections: ", nnz)
-        print("Network Density: ", float(nnz) / gc.shape[0] ** 2)
+        print("Number of Connections: ", len(val))
+        print("Network Density: ", float(len(val)) / n ** 2)
     if alpha is not None:
-        gc /= alpha
-    return gc, tf
+        val = val / alpha
+    if sparse:
+        import scipy.sparse as sp
+        return sp.csr_matrix((val, col, rowptr), shape=(n, n)), tf
+    return _network.csr_to_dense(n, rowptr, col, val), tf
 
 
 def getNextProjConst(n, projInit, constInit, constProp, transcriptionFactors):
@@ -109,20 +114,31 @@ def getNextProjConst(n, projInit, constInit, constProp, transcriptionFactors):
 
 
 def formCellTypeTree(n, cells, cellTypeParents, cellTypeNumCells, cellTypeConstProps, transcriptionFactors,
-                     cellTypeMeans):
-    """MS:175-297 -> (tree, projMatrix, constMatrix).  Cells get their FINAL type up front."""
+                     cellTypeMeans, scalable=False):
+    """MS:175-297 -> (tree, projMatrix, constMatrix).  Cells get their FINAL type up front.
+    Default: the reference's own assignment, draw for draw (``random.sample`` from the shrinking pool, MS:223-228), which
+    costs a Python set difference over all cells per type.  ``scalable=True`` (extension, what bench.py and 10^6-cell runs
+    use): one ``numpy.random.permutation`` of the cells split by ``cellTypeNumCells`` -- the same distribution (a uniformly
+    random assignment with the given type sizes), members kept as sorted int64 arrays instead of Python lists."""
     kinds = len(cellTypeParents)
     tree = Tree()
-    root = tree.add_head(-1, [], np.zeros(n), np.ones(n), 0)
-    root.setChildCellTypeMembers(list(range(cells)))
     projMatrix = np.zeros((kinds, n))
     constMatrix = np.zeros((kinds, n))
-    pool = range(cells)
-    assigned = []
-    for kind in range(kinds):
-        chosen = random.sample(pool, cellTypeNumCells[kind])
-        assigned.append(chosen)
-        pool = list(set(pool) - set(chosen))
+    if scalable:
+        root = tree.add_head(-1, np.zeros(0, dtype=np.int64), np.zeros(n), np.ones(n), 0)
+        perm = np.random.permutation(cells)
+        bounds = np.cumsum([0] + [int(c) for c in cellTypeNumCells])
+        assigned = [np.sort(perm[bounds[k]:bounds[k + 1]]) for k in range(kinds)]
+        join = lambda parts: np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)   # noqa: E731
+    else:
+        root = tree.add_head(-1, [], np.zeros(n), np.ones(n), 0)
+        pool = range(cells)
+        assigned = []
+        for kind in range(kinds):
+            chosen = random.sample(pool, cellTypeNumCells[kind])
+            assigned.append(chosen)
+            pool = list(set(pool) - set(chosen))
+        join = lambda parts: [c for part in parts for c in part]                                # noqa: E731
     parents = np.array(cellTypeParents)
 
     def attach(parent, proj_up, const_up):
@@ -130,12 +146,14 @@ def formCellTypeTree(n, cells, cellTypeParents, cellTypeNumCells, cellTypeConstP
         for kind in np.where(parents == parent)[0]:
             proj, const = getNextProjConst(n, proj_up, const_up, cellTypeConstProps[kind], transcriptionFactors)
             projMatrix[kind], constMatrix[kind] = proj, const
-            tree.add_node(kind, assigned[kind], const, proj, cellTypeMeans[kind], parent)
-            gathered += attach(kind, proj, const) + assigned[kind]
-        tree[parent].setChildCellTypeMembers(gathered)
+            tree.add_node(int(kind), assigned[kind], const, proj, cellTypeMeans[kind], parent)
+            gathered += attach(int(kind), proj, const) + [assigned[kind]]
+        tree[parent].setChildCellTypeMembers(join(gathered))
         return gathered
 
     attach(-1, np.ones(n), np.zeros(n))
+    if not scalable:
+        root.setChildCellTypeMembers(list(tree[-1].childCellTypeMembers))
     return tree, projMatrix, constMatrix
 
 
@@ -160,6 +178,10 @@ def _fingerprint(gc):
     """Cheap identity of a dense network argument: buffer address and shape plus two content checks that any rescaling
     or edit of the matrix changes (full sum, bytes of a strided sample) -- a few ms at n = 3000 against the ~0.5 s of
     converting, packing and uploading the operator again."""
+    if hasattr(gc, "tocsr"):                                                     # scipy sparse: its three arrays
+        m = gc.tocsr()
+        return ("csr", m.shape, m.data.__array_interface__["data"][0], float(m.data.sum()), hash(m.indices.tobytes()),
+                hash(m.indptr.tobytes()))
     gc = np.asarray(gc)
     flat = gc.reshape(-1)
     return (gc.__array_interface__["data"][0], gc.shape, gc.dtype.str, float(flat.sum()),

@@ -65,7 +65,8 @@ class Engine:
         """``gc``: dense (n, n) float64 as the reference passes it (already divided by alpha),
         or ``csr=(rowptr, col, val)``."""
         if csr is None:
-            gc = np.asarray(gc)
+            if not hasattr(gc, "tocsr"):            # scipy sparse matrices go straight to CSR
+                gc = np.asarray(gc)
             n = gc.shape[0]
             csr = dense_to_csr(gc)
         rowptr, col, val = csr

@@ -87,3 +87,54 @@ def test_r_workspace_writer_reproduces_files_written_by_r():
         assert rdata.serialize(name, value) == gzip.open(path).read()
     _, proj = rdata.read_rdata(os.path.join(here, "r_projMatrix.gzip"))
     assert set(np.unique(proj)) <= {0.0, 1.0} and (proj == 0).sum(axis=1).tolist() == sorted((proj == 0).sum(axis=1).tolist())
+
+
+def test_network_as_csr_equals_the_dense_reference_matrix(golden):
+    """generate_csr draws exactly what the reference draws (MS:66-127) without forming the two dense (n, n) arrays; the
+    sparse=True result of the module is the same matrix as the dense one for every structure."""
+    import scipy.sparse as sp
+    import scrutiny_b200.MatriSeq as ms
+    from scrutiny_b200 import network
+    for kind, kw, n in (("SimulatedPowerLaw", dict(powerLawExponent=2.3), 40), ("Random", dict(networkSparsity=0.7), 60),
+                        ("TRRUST", {}, 0), ("SimulatedPowerLaw", dict(normalizeWRows=True), 80)):
+        ms.init(outputDir=None, seed=1337, verbose=False)
+        dense, tf = ms.generateGeneCorrelationMatrix(n, kind, **kw)
+        state = np.random.get_state()[1][:5].copy()
+        ms.init(outputDir=None, seed=1337, verbose=False)
+        sparse, tf2 = ms.generateGeneCorrelationMatrix(n, kind, sparse=True, **kw)
+        assert sp.issparse(sparse) and np.array_equal(sparse.toarray(), dense) and np.array_equal(tf, tf2)
+        assert np.array_equal(np.random.get_state()[1][:5], state)            # same stream position afterwards
+        rowptr, col, val = network.dense_to_csr(sparse)
+        r2, c2, v2 = network.dense_to_csr(dense)
+        assert np.array_equal(rowptr, r2) and np.array_equal(col, c2) and np.array_equal(val, v2)
+        assert np.array_equal(tf, np.nonzero((dense != 0).sum(axis=0))[0]) or kind == "TRRUST"
+    g = golden("pipeline")
+    ms.init(outputDir=None, seed=1337, verbose=False)
+    gc, tf = ms.generateGeneCorrelationMatrix(40, "SimulatedPowerLaw", powerLawExponent=2.3, alpha=0.5, sparse=True)
+    assert np.array_equal(gc.toarray(), g["gc_unscaled"] / 0.5)
+
+
+def test_scalable_tree_assignment():
+    """formCellTypeTree(scalable=True): same tree shape, node vectors and type sizes as the reference's assignment, members
+    a uniformly random partition held as sorted arrays."""
+    import scrutiny_b200.MatriSeq as ms
+    n, cells = 30, 5000
+    parents, sizes, props = [-1, 0, 0, 1, 1], [500, 1000, 1500, 1000, 1000], [0.1, 0.1, 0.2, 0.0, 0.3]
+    ms.init(outputDir=None, seed=4, verbose=False)
+    gc, tf = ms.generateGeneCorrelationMatrix(n, "SimulatedPowerLaw")
+    ref_tree, projR, constR = ms.formCellTypeTree(n, cells, parents, sizes, props, tf, [0] * 5)
+    ms.init(outputDir=None, seed=4, verbose=False)
+    gc, tf = ms.generateGeneCorrelationMatrix(n, "SimulatedPowerLaw")
+    state = __import__("random").getstate()
+    tree, projM, constM = ms.formCellTypeTree(n, cells, parents, sizes, props, tf, [0] * 5, scalable=True)
+    assert projM.shape == projR.shape and [nd.identifier for nd in tree.walk()] == [nd.identifier for nd in ref_tree.walk()]
+    allm = np.concatenate([tree[k].cellTypeMembers for k in range(5)])
+    assert np.array_equal(np.sort(allm), np.arange(cells))
+    for k in range(5):
+        m = tree[k].cellTypeMembers
+        assert m.dtype == np.int64 and len(m) == sizes[k] and np.all(np.diff(m) > 0)
+        assert abs(m.mean() - cells / 2) < 6 * cells / np.sqrt(12 * sizes[k])
+        assert len(tree[k].childCellTypeMembers) == len(ref_tree[k].childCellTypeMembers)
+    assert sorted(tree[0].childCellTypeMembers.tolist()) == sorted(np.concatenate([tree[k].cellTypeMembers for k in (1, 2, 3, 4)]).tolist())
+    assert np.array_equal((projM == 0).sum(axis=1) >= 0, np.ones(5, bool)) and np.all((projM == 0) | (projM == 1))
+    assert np.array_equal(constM[projM == 1], np.zeros((projM == 1).sum()))
