@@ -97,7 +97,8 @@ int scr_debug_gene_order(const scr_ctx* ctx, int32_t* perm_out, int32_t count);
  * [7]=cell groups per CTA, [8]=dynamic smem bytes, [9]=operator resident in smem (0/1),
  * [10]=cells per group, [11]=dense (tcgen05 GEMM) stepper selected (0/1), [12]=operator bytes staged in
  * smem when it is only partly resident, [13]=operator bytes in total, [14]=modelled shared-memory wavefronts of one
- * step's gathers (LDS.128 bank model, csrc/operator_pack.h), [15]=their conflict-free floor. */
+ * step's gathers (LDS.128 bank model, csrc/operator_pack.h), [15]=their conflict-free floor, [16]=cell groups held in
+ * global memory (0/1: the large-n fallback, n above ~7 000 genes in float32; any n up to 32 768 is accepted). */
 int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count);
 
 /* ---- cell states: `currentStates` of findAllNextStates (MS:540-554) --------------------------- */

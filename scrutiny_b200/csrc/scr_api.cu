@@ -45,6 +45,9 @@ struct scr_ctx {
   void *d_pc = nullptr, *d_bias = nullptr;
   int q = 1;
   bool w_smem = false;
+  bool gstate = false;                       // large n: cell groups in a global scratch area (step_kernel.cuh kModeGlobal)
+  unsigned char* d_gscratch = nullptr;
+  size_t gscratch_cap = 0;
   size_t gbytes = 0, fixed_bytes = 0;
 
   // dense (tcgen05 3xTF32) path
@@ -80,7 +83,7 @@ struct scr_ctx {
   int32_t* d_covf = nullptr;                 // compact read-out: overflow triplets {local cell, gene, count}
   unsigned long long* d_covf_count = nullptr;
   size_t covf_cap = 0;
-  bool counts_smem_optin = false;
+  bool counts_smem_optin = false, stream_smem_optin = false;
   std::vector<double> user_bias;            // scr_set_drive_bias: additive drive term per gene (original order), empty = none
   bool readout_only = false;                 // scr_set_genes: no network, only the state / read-out entry points work
 
@@ -94,7 +97,7 @@ struct scr_ctx {
   size_t piters_cap = 0, pnd_cap = 0;
   // stepper launch configuration per kernel variant [probe][supplied]: the dynamic shared-memory opt-in and the
   // occupancy query are made once per size, not per launch
-  struct LaunchCfg { size_t smem = 0; int threads = 0, per_sm = 0; };
+  struct LaunchCfg { size_t smem = 0; int threads = 0, per_sm = 0, mode = -1; };
   LaunchCfg launch_cfg[2][2];
 
   // stats
@@ -234,8 +237,18 @@ int choose_config(scr_ctx* ctx) {
   const long limit = ctx->smem_optin;
   const long q_glob = (limit - static_cast<long>(ctx->fixed_bytes)) / static_cast<long>(ctx->gbytes);
   const long q_smem = (limit - static_cast<long>(ctx->fixed_bytes) - ctx->w_bytes) / static_cast<long>(ctx->gbytes);
-  if (q_glob < 1)
-    return fail(ctx, SCR_E_RESOURCE, "n too large: one cell group does not fit in shared memory");
+  ctx->gstate = false;
+  if (q_glob < 1 || scr::env_int("SCR_GLOBAL_STATE", 0) == 1) {
+    // one cell group does not fit in shared memory: the groups' state buffers go to global memory, shared memory keeps
+    // the tables and the group headers only (slow path, any n up to kMaxBlocks * 128)
+    ctx->gstate = true;
+    ctx->w_smem = false;
+    ctx->fixed_bytes = ctx->tab_bytes + 16;
+    if (static_cast<long>(ctx->fixed_bytes) + 2 * scr::kGroupHdr > limit)
+      return fail(ctx, SCR_E_RESOURCE, "n too large: the operator tables do not fit in shared memory");
+    ctx->q = std::max(1, std::min(2, 16 / op.wq));
+    return SCR_OK;
+  }
   const int maxq = std::max(1, std::min(15, 16 / op.wq));
   bool w_smem = q_smem >= 1 && q_smem >= std::min<long>(std::min<long>(q_glob, maxq), 2);
   const int force = scr::env_int("SCR_W_SMEM", -1);
@@ -253,7 +266,7 @@ int choose_config(scr_ctx* ctx) {
 // SM's shared memory holds is staged there and the remainder is served by L1 (step_kernel.cuh "partial residency").
 // SCR_W_PREFIX_KB caps the staged part (0 disables it).
 int w_prefix_bytes(const scr_ctx* ctx, int q) {
-  if (ctx->w_smem) return 0;
+  if (ctx->w_smem || ctx->gstate) return 0;
   long room = static_cast<long>(ctx->smem_optin) - static_cast<long>(ctx->fixed_bytes) - static_cast<long>(q) * static_cast<long>(ctx->gbytes);
   const int cap_kb = scr::env_int("SCR_W_PREFIX_KB", -1);
   if (cap_kb >= 0) room = std::min<long>(room, static_cast<long>(cap_kb) * 1024);
@@ -267,19 +280,33 @@ int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
   int q = std::min(ctx->q, std::max(1, (nitems + ctx->sm_count - 1) / ctx->sm_count));
   p.q = q;
   p.w_prefix = w_prefix_bytes(ctx, q);
-  const size_t smem = ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * ctx->gbytes + p.w_prefix;
+  const size_t per_group = ctx->gstate ? static_cast<size_t>(scr::kGroupHdr) : ctx->gbytes;
+  const size_t smem = ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * per_group + p.w_prefix;
   const int threads = q * ctx->op.wq * 32;
-  auto kern = ctx->w_smem ? scr::step_kernel<T, true, PROBE, SUPPLIED> : scr::step_kernel<T, false, PROBE, SUPPLIED>;
+  auto kern = ctx->gstate ? scr::step_kernel<T, scr::kModeGlobal, PROBE, SUPPLIED>
+                          : (ctx->w_smem ? scr::step_kernel<T, scr::kModeSmem, PROBE, SUPPLIED> : scr::step_kernel<T, scr::kModeL1, PROBE, SUPPLIED>);
   scr_ctx::LaunchCfg& cfg = ctx->launch_cfg[PROBE ? 1 : 0][SUPPLIED ? 1 : 0];
-  if (cfg.smem != smem || cfg.threads != threads) {
+  const int mode = ctx->gstate ? scr::kModeGlobal : (ctx->w_smem ? scr::kModeSmem : scr::kModeL1);
+  if (cfg.smem != smem || cfg.threads != threads || cfg.mode != mode) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-    cfg.smem = smem; cfg.threads = threads; cfg.per_sm = occ;
+    cfg.smem = smem; cfg.threads = threads; cfg.per_sm = occ; cfg.mode = mode;
   }
   const int per_sm = cfg.per_sm;
   if (per_sm < 1) return fail(ctx, SCR_E_RESOURCE, "stepper does not fit on an SM");
   const int grid = std::max(1, std::min((nitems + q - 1) / q, ctx->sm_count * per_sm));
+  if (ctx->gstate) {
+    const size_t need = static_cast<size_t>(grid) * q * (ctx->gbytes - scr::kGroupHdr);
+    if (need > ctx->gscratch_cap) {
+      cudaFree(ctx->d_gscratch);
+      ctx->d_gscratch = nullptr;
+      ctx->gscratch_cap = 0;
+      CK(cudaMalloc(&ctx->d_gscratch, need));
+      ctx->gscratch_cap = need;
+    }
+    p.gscratch = ctx->d_gscratch;
+  }
   CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   kern<<<grid, threads, smem, ctx->stream>>>(p);
@@ -883,7 +910,7 @@ void scr_destroy(scr_ctx* ctx) {
     free_network(ctx);
     free_dense_work(ctx);
     cudaFree(ctx->d_state); cudaFree(ctx->d_items); cudaFreeHost(ctx->h_items); cudaFree(ctx->d_counter); cudaFree(ctx->d_err); cudaFree(ctx->d_stage);
-    cudaFree(ctx->d_piters); cudaFree(ctx->d_pnd);
+    cudaFree(ctx->d_piters); cudaFree(ctx->d_pnd); cudaFree(ctx->d_gscratch);
     free_counts_scratch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -917,7 +944,7 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
   // the gene order must not change under allocated cells (alpha rescaling keeps the pattern, hence the order)
   if (ctx->cells > 0 && ctx->has_net && op.perm != ctx->op.perm)
     return fail(ctx, SCR_E_STATE, "network pattern changed while cells are allocated");
-  if (op.nb > scr::kMaxBlocks) return fail(ctx, SCR_E_RESOURCE, "n too large: one cell group does not fit in shared memory");
+  if (op.nb > scr::kMaxBlocks) return fail(ctx, SCR_E_RESOURCE, "n too large: more than " + std::to_string(scr::kMaxBlocks * 128) + " genes");
   std::vector<unsigned char> tab, w;
   if (ctx->prec == SCR_F64) build_blobs<double>(op, tab, w, ctx->off_vrow);
   else build_blobs<float>(op, tab, w, ctx->off_vrow);
@@ -1050,12 +1077,13 @@ int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count) {
   if (!ctx || !out) return SCR_E_ARG;
   if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
   const PackedOperator& o = ctx->op;
-  const int64_t v[16] = {o.n_pad, o.npp, static_cast<int64_t>(o.tile_val.size()), o.nv, o.lv, o.cap, o.wq, ctx->q,
-                         static_cast<int64_t>(ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + ctx->q * ctx->gbytes +
+  const size_t per_group = ctx->gstate ? static_cast<size_t>(scr::kGroupHdr) : ctx->gbytes;
+  const int64_t v[17] = {o.n_pad, o.npp, static_cast<int64_t>(o.tile_val.size()), o.nv, o.lv, o.cap, o.wq, ctx->q,
+                         static_cast<int64_t>(ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + ctx->q * per_group +
                                               w_prefix_bytes(ctx, ctx->q)),
                          ctx->w_smem ? 1 : 0, ctx->cpg(), ctx->dense_mode ? 1 : 0, w_prefix_bytes(ctx, ctx->q), ctx->w_bytes,
-                         o.gather_wavefronts, o.gather_wavefronts_floor};
-  for (int i = 0; i < count && i < 16; ++i) out[i] = v[i];
+                         o.gather_wavefronts, o.gather_wavefronts_floor, ctx->gstate ? 1 : 0};
+  for (int i = 0; i < count && i < 17; ++i) out[i] = v[i];
   return SCR_OK;
 }
 
@@ -1264,7 +1292,33 @@ int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const doub
   // free-running stream without a lambda dump: float32 screening of the lambda < 10 sampler (identical integers,
   // aux_kernels.cuh); SCR_COUNTS_EXACT=1 forces the float64 sampler for every entry (A/B tests)
   const bool fast = !uniforms && !lambda_out && nb_phi == 0.0 && dropout_p == 0.0 && scr::env_int("SCR_COUNTS_EXACT", 0) == 0;
+  // free-running, no dumps: the persistent warp-decoupled kernel (SCR_COUNTS_STREAM=0: the one-CTA-per-cell kernel, A/B tests)
+  const bool stream_kernel = fast && scr::env_int("SCR_COUNTS_STREAM", 1) != 0;
+  const size_t stream_smem = 3 * ((static_cast<size_t>(n) * esz + 15) & ~static_cast<size_t>(15)) + 64;
+  if (stream_kernel && stream_smem > 48 * 1024 && !ctx->stream_smem_optin) {
+    if (stream_smem > static_cast<size_t>(ctx->smem_optin)) return fail(ctx, SCR_E_RESOURCE, "count read-out: n too large for the staging rows");
+#define SCR_OPTIN_S(T, OUT) CKC(cudaFuncSetAttribute(scr::counts_stream_kernel<T, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin))
+    SCR_OPTIN_S(float, int32_t); SCR_OPTIN_S(float, uint16_t); SCR_OPTIN_S(float, uint8_t);
+    SCR_OPTIN_S(double, int32_t); SCR_OPTIN_S(double, uint16_t); SCR_OPTIN_S(double, uint8_t);
+#undef SCR_OPTIN_S
+    ctx->stream_smem_optin = true;
+  }
   auto launch = [&](int64_t c0, int64_t cnt, void* out, double* lam) -> cudaError_t {
+    if (stream_kernel) {
+      const unsigned grid = static_cast<unsigned>(std::min<int64_t>(cnt, static_cast<int64_t>(ctx->sm_count) * SCR_COUNTS_CTAS_PER_SM));
+#define SCR_LAUNCH_STREAM(T, OUT) \
+      scr::counts_stream_kernel<T, OUT><<<grid, 256, stream_smem, ctx->stream>>>( \
+          static_cast<const T*>(ctx->d_state), ctx->op.n_pad, ctx->d_ctab, ctx->d_lgam, n, cell_begin + c0, cnt, exp_scale, \
+          size_by_slot, crk, ctx->cell_offset, static_cast<OUT*>(out), ctx->d_err, ctx->d_covf, dev_ovf_cap, ctx->d_covf_count)
+#define SCR_STREAM_PREC(OUT) if (ctx->prec == SCR_F64) SCR_LAUNCH_STREAM(double, OUT); else SCR_LAUNCH_STREAM(float, OUT);
+      if (out_dtype == SCR_COUNT_I32) { SCR_STREAM_PREC(int32_t) }
+      else if (out_dtype == SCR_COUNT_U16) { SCR_STREAM_PREC(uint16_t) }
+      else { SCR_STREAM_PREC(uint8_t) }
+#undef SCR_STREAM_PREC
+#undef SCR_LAUNCH_STREAM
+      ctx->launches++;
+      return cudaGetLastError();
+    }
     const double* uni_by_slot = d_uni ? d_uni - cell_begin * n * static_cast<int64_t>(draws_per_entry) : nullptr;
 #define SCR_LAUNCH_COUNTS(T, FAST, OUT) \
     scr::counts_kernel<T, FAST, OUT><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>( \

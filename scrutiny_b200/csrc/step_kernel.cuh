@@ -418,6 +418,7 @@ template <typename T> struct StepParams {
   const T* noise;
   int64_t noise_steps;
   const int* perm;            // internal -> original gene (or -1)
+  unsigned char* gscratch;    // kModeGlobal: per (CTA, group) state buffers, (n_pad + npp + nv_pad) * 16 bytes each
   // probe
   double thresh;
   int max_iter, avg_num;
@@ -473,7 +474,7 @@ __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&)[2][kWordsPe
 //   then ovfidx (long-row chunk ranges), the staged head of the operator, and the cell groups:
 //   group = [kGroupHdr: ctrl words, three mbarriers, CellRound0 words, probe partials][bufA][bufB][chunk partials]
 // The tables a 128-gene block needs sit at compile-time offsets so that their addresses cost no instructions.
-constexpr int kMaxBlocks = 128;                 // n_pad <= 16384 (a cell group of that size cannot fit an SM anyway)
+constexpr int kMaxBlocks = 256;                 // n_pad <= 32768 (beyond ~7 000 genes the groups live in global memory: kModeGlobal)
 constexpr int kRecBytes = kMaxBlocks * 16;
 constexpr int kFixedTab = kRecBytes + 128;
 // ctrl 16 | mbarriers 24 (+8 pad) | CellRound0 48 | steps 16 | cells 16 | step bases 16 | caller rows 16 | probe partials 16 x 16 |
@@ -492,22 +493,33 @@ __host__ __device__ inline size_t group_smem_bytes(int n_pad, int npp, int nv_pa
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <typename T, bool W_SMEM, bool PROBE, bool SUPPLIED>
+// MODE: where the operator and the cell groups live --
+//   kModeL1     groups in shared memory, operator read through L1 (its head staged in shared memory when room is left);
+//   kModeSmem   groups and the whole operator in shared memory;
+//   kModeGlobal LARGE n (one cell group does not fit in shared memory: n above ~7 000 genes in float32): the groups' state
+//               buffers live in a global scratch area (L1 / L2 resident) and proj/const are read from global memory; only
+//               the tables and the group headers stay on chip.  Same code, same results, far slower -- the fallback that
+//               lets the library take any n the reference takes (up to kMaxBlocks * 128 genes).
+constexpr int kModeL1 = 0, kModeSmem = 1, kModeGlobal = 2;
+
+template <typename T, int MODE, bool PROBE, bool SUPPLIED>
 __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   using TR = Traits<T>;
   using WEnt = typename TR::WEnt;
   using PC = typename TR::PC;
   using RowT = Row<T>;
   constexpr int CPG = TR::CPG;
+  constexpr bool W_SMEM = MODE == kModeSmem, GSTATE = MODE == kModeGlobal;
 
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* s_pc = smem + kFixedTab;
-  unsigned char* s_var = s_pc + static_cast<size_t>(p.n_pad) * sizeof(PC);   // ovfidx
+  unsigned char* s_pc = GSTATE ? const_cast<unsigned char*>(p.pc) : smem + kFixedTab;
+  unsigned char* s_var = GSTATE ? smem + kFixedTab : s_pc + static_cast<size_t>(p.n_pad) * sizeof(PC);   // ovfidx
   const int var_bytes = p.tab_bytes - kFixedTab;
   unsigned char* s_w = s_var + var_bytes;
-  const int wpre = W_SMEM ? p.w_bytes : p.w_prefix;   // bytes of the operator held in shared memory
+  const int wpre = W_SMEM ? p.w_bytes : (GSTATE ? 0 : p.w_prefix);   // bytes of the operator held in shared memory
   unsigned char* s_groups = s_w + wpre;
-  const size_t gbytes = group_smem_bytes(p.n_pad, p.npp, p.nv_pad);
+  const size_t gstate_bytes = group_smem_bytes(p.n_pad, p.npp, p.nv_pad) - kGroupHdr;   // bufA | bufB | chunk partials
+  const size_t gbytes = GSTATE ? static_cast<size_t>(kGroupHdr) : gstate_bytes + kGroupHdr;   // per group in shared memory
   uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_groups + static_cast<size_t>(p.q) * gbytes);
 
   const int warp = threadIdx.x >> 5, lane_id = threadIdx.x & 31;
@@ -531,9 +543,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t pc_bytes = static_cast<uint32_t>(p.n_pad * sizeof(PC));
-    mbar_expect_tx(s_mbar, p.tab_bytes + pc_bytes + wpre);
+    mbar_expect_tx(s_mbar, p.tab_bytes + (GSTATE ? 0u : pc_bytes) + wpre);
     bulk_g2s(smem, p.tab, kFixedTab, s_mbar);
-    bulk_g2s(s_pc, p.pc, pc_bytes, s_mbar);
+    if (!GSTATE) bulk_g2s(s_pc, p.pc, pc_bytes, s_mbar);
     if (var_bytes > 0) bulk_g2s(s_var, p.tab + kFixedTab, var_bytes, s_mbar);
     if (wpre > 0) bulk_g2s(s_w, p.wblob, wpre, s_mbar);
   }
@@ -607,7 +619,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   int* hrows = reinterpret_cast<int*>(ghdr + kHdrRows);             // position of each cell in the caller's list
   RowT* red = reinterpret_cast<RowT*>(ghdr + kHdrRed);              // PROBE: per-warp partial sums of |dx|
   double* ring = reinterpret_cast<double*>(ghdr + kHdrRing);        // PROBE: [cell][kProbeRing] window of the convergence trace
-  unsigned char* bufA = ghdr + kGroupHdr;
+  unsigned char* bufA = GSTATE ? p.gscratch + (static_cast<size_t>(blockIdx.x) * p.q + grp) * gstate_bytes : ghdr + kGroupHdr;
   unsigned char* bufB = bufA + static_cast<size_t>(p.n_pad) * 16;
   RowT* ovf = reinterpret_cast<RowT*>(bufB + static_cast<size_t>(p.npp) * 16);
 

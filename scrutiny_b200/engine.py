@@ -114,9 +114,9 @@ class Engine:
 
     def block_records(self):
         """(records (blocks, 4) int32 = first gene / first slot / end slot / flags, list bounds per warp of a group)."""
-        rec = np.zeros((128, 4), dtype=np.int32)
+        rec = np.zeros((256, 4), dtype=np.int32)
         bounds = np.zeros(17, dtype=np.int32)
-        nb = self._lib.scr_debug_block_records(self._ctx, _ptr(rec, C.c_int32), 128, _ptr(bounds, C.c_int32), 17)
+        nb = self._lib.scr_debug_block_records(self._ctx, _ptr(rec, C.c_int32), 256, _ptr(bounds, C.c_int32), 17)
         if nb < 0:
             self._check(nb)
         wq = self.layout()["warps_per_group"]
@@ -132,12 +132,12 @@ class Engine:
         return int(self._lib.scr_noise_stream_version())
 
     def layout(self):
-        out = np.zeros(16, dtype=np.int64)
-        self._check(self._lib.scr_get_layout(self._ctx, _ptr(out, C.c_int64), 16))
+        out = np.zeros(17, dtype=np.int64)
+        self._check(self._lib.scr_get_layout(self._ctx, _ptr(out, C.c_int64), 17))
         keys = ("n_pad", "pingpong_genes", "tile_slots", "chunks", "chunk_len", "row_cap",
                 "warps_per_group", "groups_per_cta", "smem_bytes", "operator_in_smem",
                 "cells_per_group", "dense_stepper", "operator_prefix_bytes", "operator_bytes",
-                "gather_wavefronts_model", "gather_wavefronts_floor")
+                "gather_wavefronts_model", "gather_wavefronts_floor", "state_in_global")
         return dict(zip(keys, (int(v) for v in out)))
 
     # -- states -----------------------------------------------------------------------------

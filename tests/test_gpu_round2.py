@@ -47,6 +47,15 @@ def test_compact_counts_are_the_int32_counts(prec):
     size = rng.normal(1, 0.14, size=cells) ** 3
     want = e.counts(shift, size, seed=77)
     assert (want >= 255).sum() > 500 and (want >= 65535).sum() == 0 and want.max() > 1000
+    # the persistent warp-decoupled kernel (default) against the one-CTA-per-cell kernel and the float64 sampler
+    import os
+    for env in ("SCR_COUNTS_STREAM", "SCR_COUNTS_EXACT"):
+        os.environ[env] = "0" if env == "SCR_COUNTS_STREAM" else "1"
+        try:
+            assert np.array_equal(e.counts(shift, size, seed=77), want), env
+            assert np.array_equal(e.counts_compact(shift, size, seed=77, dtype="uint8")[0], np.minimum(want, 255)), env
+        finally:
+            del os.environ[env]
     for dtype, esc in (("uint8", 255), ("uint16", 65535)):
         got, ovf = e.counts_compact(shift, size, seed=77, dtype=dtype)
         assert got.dtype == np.dtype(dtype) and ovf.shape[1] == 3
@@ -280,3 +289,66 @@ def test_extension_moments_free_running_and_module_flags(golden):
     assert np.array_equal(outs["plain"], outs["ignored"])
     assert abs((outs["drop"] == 0).mean() - (0.5 + 0.5 * (outs["plain"] == 0).mean())) < 0.02
     assert outs["nb"].var() > 1.5 * outs["plain"].var() and abs(outs["nb"].mean() / outs["plain"].mean() - 1) < 0.15
+
+
+# ---------------------------------------------------------------------------------------------
+# large n: cell groups in global memory (step_kernel.cuh kModeGlobal)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec,tol", [("f32", 1e-4), ("f64", 1e-10)])
+def test_large_gene_count_falls_back_to_global_state(prec, tol):
+    """n = 9000 (a float32 cell group of that size needs 290 KB: more than an SM has): the stepper keeps the groups in
+    global memory instead of refusing the network.  Ragged supplied-noise phase against the oracle, free-running noise
+    against its own dump, the probe against the oracle; SCR_GLOBAL_STATE=1 forces the same path on a small network, where
+    it must reproduce the shared-memory path bit for bit."""
+    import os
+    import scipy.sparse as sp
+    n, cells, smax = 9000, 21, 12
+    rng = np.random.RandomState(61)
+    deg = np.minimum((0.5 * (1 - rng.rand(n)) ** (-1 / 1.3) + 0.5).astype(int), 400)
+    regs = rng.choice(n, size=3000, replace=False)
+    rows = np.repeat(np.arange(n), deg)
+    cols = np.concatenate([rng.choice(regs, size=k, replace=False) for k in deg])
+    W = sp.csr_matrix((rng.beta(2, 3, size=len(rows)) * rng.choice([-1.0, 1.0], size=len(rows)) * 2.0, (rows, cols)), shape=(n, n))
+    from scrutiny_b200 import engine as em
+    e = em.Engine(0, prec)
+    e.set_network(W)
+    e.alloc_cells(cells, 7)
+    lay = e.layout()
+    assert lay["state_in_global"] == 1 and lay["chunks"] > 0
+    X0 = rng.uniform(-1, 1, size=(cells, n))
+    proj = (rng.rand(n) > 0.05).astype(float)
+    const = np.where(proj == 0, -1.0, 0.0)
+    steps = rng.randint(0, smax + 1, size=cells)
+    steps[:3] = [smax, 0, smax]
+    noise = (0.05 * rng.randn(cells, smax, n)).astype(np.float32).astype(np.float64)
+    e.set_states(np.ascontiguousarray(X0.T))
+    e.run_phase(np.arange(cells), steps, proj, const, noise=noise)
+    want = X0.astype(np.float32).astype(np.float64) if prec == "f32" else X0.copy()
+    fo.run_phase(W, want, steps, proj, const, 0.01, noise)
+    assert np.max(np.abs(e.get_states().T - want)) <= tol
+    # free-running == supplied(dump of the free-running noise)
+    e.set_states(np.ascontiguousarray(X0.T))
+    e.run_phase(np.arange(cells), np.full(cells, 3), proj, const, seed=5, step_base=np.full(cells, 40))
+    free = e.get_states()
+    dump = np.stack([[e.debug_noise(7 + c, 40 + s, 0.05, 5) for s in range(3)] for c in range(cells)])
+    e.set_states(np.ascontiguousarray(X0.T))
+    e.run_phase(np.arange(cells), np.full(cells, 3), proj, const, noise=dump)
+    assert np.max(np.abs(free - e.get_states())) <= (1e-12 if prec == "f64" else 1e-6)
+    it = e.probe(np.arange(6), proj, const, max_iter=30, avg_num=5, thresh=0.3, noise=np.zeros((6, 30, n)))
+    want_it, _, _ = fo.probe(W, e.get_states()[:, :6].T.copy(), proj, const, 0.01, np.zeros((6, 30, n)), 0.3, 30, 5)
+    assert np.max(np.abs(it - want_it)) <= (0 if prec == "f64" else 1)
+    # forced on a small network: identical to the shared-memory path
+    Ws = sparse_net(300, 17, gain=3.0)
+    st = rng.randint(0, 30, size=50)
+    outs = []
+    for force in ("1", "0"):
+        os.environ["SCR_GLOBAL_STATE"] = force
+        try:
+            s = engine(Ws, 50, prec, offset=3)
+        finally:
+            del os.environ["SCR_GLOBAL_STATE"]
+        assert s.layout()["state_in_global"] == int(force)
+        s.set_states_broadcast(np.linspace(-1, 1, 300))
+        s.run_phase(np.arange(50), st, np.ones(300), np.zeros(300), seed=8)
+        outs.append(s.get_states())
+    assert np.array_equal(outs[0], outs[1])
