@@ -343,110 +343,6 @@ counts_kernel(const T* __restrict__ state, int64_t ld, const CountGene* __restri
   }
 }
 
-// The free-running read-out as a PERSISTENT kernel (what scr_counts / scr_counts_compact launch when no uniforms are
-// supplied and no lambda dump is asked for).  In counts_kernel a CTA's warps meet at a barrier per cell and then leave
-// together: 30 % of the warp time was barrier / exit wait (profiles/r2_counts_kernel_ncu_summary.txt) because a warp that
-// draws a lambda >= 10 gene takes several times longer than its neighbours.  Here a CTA walks over many cells and its
-// warps are decoupled: three staging rows (OUT-typed, in the caller's gene order) rotate; a warp that has finished its
-// entries of cell i arrives on full[i % 3] and moves on to cell i + 1; the coalesced write-out of row i is shared by the
-// warps, each doing its slice AFTER it has finished cell i + 1 (by then full[i % 3] has normally completed), followed by
-// an arrival on empty[i % 3], which the warps wait for before they store entries of cell i + 3.  Same per-entry code,
-// same integers as counts_kernel<T, true, OUT> (tests compare them entry for entry).
-template <typename T, typename OUT>
-__global__ void __launch_bounds__(256, SCR_COUNTS_CTAS_PER_SM)
-counts_stream_kernel(const T* __restrict__ state, int64_t ld, const CountGene* __restrict__ genes, const float* __restrict__ lgam,
-                     int n, int64_t cell0, int64_t ncells, double exp_scale, const double* __restrict__ sizef, const RoundKeys rk,
-                     int64_t cell_offset, OUT* __restrict__ out, int* err, int32_t* __restrict__ ovf, unsigned long long ovf_cap,
-                     unsigned long long* __restrict__ ovf_count) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  const int row_bytes = (n * static_cast<int>(sizeof(OUT)) + 15) & ~15;
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + 3 * row_bytes);
-  uint64_t* empty = full + 3;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  if (threadIdx.x == 0) {
-    for (int b = 0; b < 3; ++b) { mbar_init(&full[b], nwarps); mbar_init(&empty[b], nwarps); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  constexpr int kEscape = CountLimit<OUT>::kEscape;
-  const double esl = exp_scale * 1.4426950408889634;
-
-  // this warp's slice of staging row (j % 3) -> row j of the output, then the slot is released
-  auto write_out = [&](int64_t j, int64_t cell) {
-    const int b = static_cast<int>(j % 3);
-    mbar_wait(&full[b], static_cast<uint32_t>((j / 3) & 1));
-    const unsigned char* src = s_raw + b * row_bytes;
-    unsigned char* dst = reinterpret_cast<unsigned char*>(out + (cell - cell0) * n);
-    const int total = n * static_cast<int>(sizeof(OUT));
-    if (((reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(total)) & 3) == 0) {
-      const int words = total >> 2, per = (words + nwarps - 1) / nwarps;
-      const int w0 = warp * per, w1 = min(words, w0 + per);
-      for (int w = w0 + lane; w < w1; w += 32) reinterpret_cast<uint32_t*>(dst)[w] = reinterpret_cast<const uint32_t*>(src)[w];
-    } else {
-      const int per = (total + nwarps - 1) / nwarps;
-      const int b0 = warp * per, b1 = min(total, b0 + per);
-      for (int q = b0 + lane; q < b1; q += 32) dst[q] = src[q];
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[b]);
-  };
-
-  int64_t i = 0, prev_cell = -1;
-  for (int64_t c = cell0 + blockIdx.x; c < cell0 + ncells; c += gridDim.x, ++i) {
-    const int b = static_cast<int>(i % 3);
-    if (i >= 3) mbar_wait(&empty[b], static_cast<uint32_t>((i / 3 - 1) & 1));
-    OUT* buf = reinterpret_cast<OUT*>(s_raw + b * row_bytes);
-    const uint64_t gid = static_cast<uint64_t>(cell_offset + c);
-    const double sf = sizef[c];
-    const T* row = state + c * ld;
-    const bool sf_ok = sf >= 0.05 && sf <= 8.0;
-    const float sf_f = static_cast<float>(sf);
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-      const CountGene cg = genes[t];
-      const int o = cg.gene;
-      const double x = static_cast<double>(row[cg.state_idx]);
-      int cnt = -1;
-      if (sf_ok) {
-        const float t2 = static_cast<float>((x + cg.shift) * esl);
-        if (t2 > -64.0f && t2 < 12.0f) {
-          const float lam_f = ptx_ex2(t2) * sf_f;
-          if (lam_f < 9.999f) cnt = poisson_small_f32(lam_f, static_cast<uint32_t>(o), gid, rk);
-#if SCR_COUNTS_PTRS_F32
-          else if (lam_f > 10.001f && lam_f < kPtrsLamMax) cnt = poisson_ptrs_f32(lam_f, static_cast<uint32_t>(o), gid, rk, lgam);
-#endif
-        }
-      }
-      if (cnt < 0) {
-        double lam = exp(exp_scale * (x + cg.shift)) * sf;
-        if (lam < 0.0) lam = 0.0;
-        UniformSource u;
-        u.supplied = nullptr; u.sup_base = 0; u.sup_count = 0; u.used = 0;
-        u.c0 = static_cast<uint32_t>(o);
-        u.c2 = static_cast<uint32_t>(gid);
-        u.c3 = static_cast<uint32_t>(gid >> 32);
-        u.rk = &rk; u.call = 0; u.have = 0; u.err = err;
-        u.w0 = u.w1 = u.w2 = u.w3 = 0;
-        cnt = poisson_draw(lam, u);
-      }
-      if (sizeof(OUT) < 4 && cnt >= kEscape) {
-        const unsigned long long k = atomicAdd(ovf_count, 1ULL);
-        if (k < ovf_cap) {
-          ovf[3 * k] = static_cast<int32_t>(c);
-          ovf[3 * k + 1] = o;
-          ovf[3 * k + 2] = cnt;
-        }
-        cnt = kEscape;
-      }
-      buf[o] = static_cast<OUT>(cnt);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&full[b]);
-    if (i >= 1) write_out(i - 1, prev_cell);
-    prev_cell = c;
-  }
-  if (i >= 1) write_out(i - 1, prev_cell);
-}
-
 // ------------------------------------------------------------------------------------------
 // debug / parity aids
 // ------------------------------------------------------------------------------------------

@@ -2,6 +2,7 @@
 #include "../../include/scrutiny_b200.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
 
 #include <algorithm>
 #include <cmath>
@@ -22,6 +23,17 @@ using scr::Item;
 using scr::PackedOperator;
 
 namespace {
+// NVTX range over one ABI call; the label carries what a lineage node's phase looks like (cells, longest cell)
+struct NvtxRange {
+  explicit NvtxRange(const char* name, long long a = -1, long long b = -1) {
+    char buf[96];
+    if (a >= 0 && b >= 0) std::snprintf(buf, sizeof(buf), "%s m=%lld max=%lld", name, a, b);
+    else if (a >= 0) std::snprintf(buf, sizeof(buf), "%s m=%lld", name, a);
+    else std::snprintf(buf, sizeof(buf), "%s", name);
+    nvtxRangePushA(buf);
+  }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 std::string g_create_error;
 constexpr int kSmemDefault = 232448;   // 227 KB opt-in limit of sm_100
 }
@@ -46,6 +58,7 @@ struct scr_ctx {
   int q = 1;
   bool w_smem = false;
   bool gstate = false;                       // large n: cell groups in a global scratch area (step_kernel.cuh kModeGlobal)
+  size_t gbytes_probe = 0;                   // shared memory of one cell group in a PROBE launch (header with the convergence window)
   unsigned char* d_gscratch = nullptr;
   size_t gscratch_cap = 0;
   size_t gbytes = 0, fixed_bytes = 0;
@@ -83,7 +96,7 @@ struct scr_ctx {
   int32_t* d_covf = nullptr;                 // compact read-out: overflow triplets {local cell, gene, count}
   unsigned long long* d_covf_count = nullptr;
   size_t covf_cap = 0;
-  bool counts_smem_optin = false, stream_smem_optin = false;
+  bool counts_smem_optin = false;
   std::vector<double> user_bias;            // scr_set_drive_bias: additive drive term per gene (original order), empty = none
   bool readout_only = false;                 // scr_set_genes: no network, only the state / read-out entry points work
 
@@ -136,11 +149,11 @@ int align16(int x) { return (x + 15) & ~15; }
 
 template <typename T>
 void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std::vector<unsigned char>& w,
-                 int& off_vrow) {
+                 int& off_vrow, bool large) {
   using WEnt = typename scr::Traits<T>::WEnt;
   // fixed part (step_kernel.cuh "Shared-memory layout"): block records in the order of the warps' lists, list bounds;
   // variable part: chunk ranges of the long rows
-  const int off_wblk_ptr = scr::kRecBytes, off_ovfidx = scr::kFixedTab;
+  const int off_wblk_ptr = scr::rec_bytes(large), off_ovfidx = scr::fixed_tab(large);
   const int total = align16(off_ovfidx + static_cast<int>(op.ovf_start.size()) * 8);
   tab.assign(total, 0);
   for (int w = 0; w < op.wq; ++w) {
@@ -232,23 +245,24 @@ int make_tmap(scr_ctx* ctx, CUtensorMap* tm, const float* ptr, int64_t rows, int
 int choose_config(scr_ctx* ctx) {
   const PackedOperator& op = ctx->op;
   const size_t pc_bytes = static_cast<size_t>(op.n_pad) * 2 * ctx->esize();
-  ctx->gbytes = scr::group_smem_bytes(op.n_pad, op.npp, op.nv_pad);
+  ctx->gbytes = scr::group_smem_bytes(op.n_pad, op.npp, op.nv_pad, false);
+  ctx->gbytes_probe = scr::group_smem_bytes(op.n_pad, op.npp, op.nv_pad, true);
   ctx->fixed_bytes = ctx->tab_bytes + pc_bytes + 16;
   const long limit = ctx->smem_optin;
   const long q_glob = (limit - static_cast<long>(ctx->fixed_bytes)) / static_cast<long>(ctx->gbytes);
-  const long q_smem = (limit - static_cast<long>(ctx->fixed_bytes) - ctx->w_bytes) / static_cast<long>(ctx->gbytes);
-  ctx->gstate = false;
-  if (q_glob < 1 || scr::env_int("SCR_GLOBAL_STATE", 0) == 1) {
-    // one cell group does not fit in shared memory: the groups' state buffers go to global memory, shared memory keeps
-    // the tables and the group headers only (slow path, any n up to kMaxBlocks * 128)
-    ctx->gstate = true;
+  const long q_smem = (limit - static_cast<long>(ctx->fixed_bytes) - ctx->w_bytes) / static_cast<long>(ctx->gbytes_probe);
+  if (ctx->gstate) {
+    // one cell group does not fit in shared memory (decided in scr_set_network_csr, wants_global_state): the groups' state
+    // buffers go to global memory, shared memory keeps the tables and the group headers only (slow path, any n up to
+    // kMaxBlocks * 128)
     ctx->w_smem = false;
     ctx->fixed_bytes = ctx->tab_bytes + 16;
-    if (static_cast<long>(ctx->fixed_bytes) + 2 * scr::kGroupHdr > limit)
+    if (static_cast<long>(ctx->fixed_bytes) + 2 * scr::group_hdr(true) > limit)
       return fail(ctx, SCR_E_RESOURCE, "n too large: the operator tables do not fit in shared memory");
     ctx->q = std::max(1, std::min(2, 16 / op.wq));
     return SCR_OK;
   }
+  if (q_glob < 1) return fail(ctx, SCR_E_RESOURCE, "internal: cell group does not fit in shared memory");
   const int maxq = std::max(1, std::min(15, 16 / op.wq));
   bool w_smem = q_smem >= 1 && q_smem >= std::min<long>(std::min<long>(q_glob, maxq), 2);
   const int force = scr::env_int("SCR_W_SMEM", -1);
@@ -265,9 +279,10 @@ int choose_config(scr_ctx* ctx) {
 // When the operator does not fit in shared memory next to q cell groups, the leading part of it that the rest of the
 // SM's shared memory holds is staged there and the remainder is served by L1 (step_kernel.cuh "partial residency").
 // SCR_W_PREFIX_KB caps the staged part (0 disables it).
-int w_prefix_bytes(const scr_ctx* ctx, int q) {
+int w_prefix_bytes(const scr_ctx* ctx, int q, bool probe = false) {
   if (ctx->w_smem || ctx->gstate) return 0;
-  long room = static_cast<long>(ctx->smem_optin) - static_cast<long>(ctx->fixed_bytes) - static_cast<long>(q) * static_cast<long>(ctx->gbytes);
+  long room = static_cast<long>(ctx->smem_optin) - static_cast<long>(ctx->fixed_bytes) -
+              static_cast<long>(q) * static_cast<long>(probe ? ctx->gbytes_probe : ctx->gbytes);
   const int cap_kb = scr::env_int("SCR_W_PREFIX_KB", -1);
   if (cap_kb >= 0) room = std::min<long>(room, static_cast<long>(cap_kb) * 1024);
   room = std::min<long>(room, ctx->w_bytes);
@@ -278,9 +293,11 @@ template <typename T, bool PROBE, bool SUPPLIED>
 int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
   // few groups: spread them over SMs instead of stacking them in one CTA
   int q = std::min(ctx->q, std::max(1, (nitems + ctx->sm_count - 1) / ctx->sm_count));
+  const size_t per_group = ctx->gstate ? static_cast<size_t>(scr::group_hdr(PROBE)) : (PROBE ? ctx->gbytes_probe : ctx->gbytes);
+  if (!ctx->gstate)   // a probe group carries a larger header: fewer of them may fit
+    while (q > 1 && ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * per_group > static_cast<size_t>(ctx->smem_optin)) --q;
   p.q = q;
-  p.w_prefix = w_prefix_bytes(ctx, q);
-  const size_t per_group = ctx->gstate ? static_cast<size_t>(scr::kGroupHdr) : ctx->gbytes;
+  p.w_prefix = w_prefix_bytes(ctx, q, PROBE);
   const size_t smem = ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * per_group + p.w_prefix;
   const int threads = q * ctx->op.wq * 32;
   auto kern = ctx->gstate ? scr::step_kernel<T, scr::kModeGlobal, PROBE, SUPPLIED>
@@ -297,7 +314,7 @@ int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
   if (per_sm < 1) return fail(ctx, SCR_E_RESOURCE, "stepper does not fit on an SM");
   const int grid = std::max(1, std::min((nitems + q - 1) / q, ctx->sm_count * per_sm));
   if (ctx->gstate) {
-    const size_t need = static_cast<size_t>(grid) * q * (ctx->gbytes - scr::kGroupHdr);
+    const size_t need = static_cast<size_t>(grid) * q * scr::group_state_bytes(ctx->op.n_pad, ctx->op.npp, ctx->op.nv_pad);
     if (need > ctx->gscratch_cap) {
       cudaFree(ctx->d_gscratch);
       ctx->d_gscratch = nullptr;
@@ -945,9 +962,17 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
   if (ctx->cells > 0 && ctx->has_net && op.perm != ctx->op.perm)
     return fail(ctx, SCR_E_STATE, "network pattern changed while cells are allocated");
   if (op.nb > scr::kMaxBlocks) return fail(ctx, SCR_E_RESOURCE, "n too large: more than " + std::to_string(scr::kMaxBlocks * 128) + " genes");
+  // Does one cell group (with the probe's header) fit in shared memory next to the tables and the node's proj/const?  If
+  // not, the groups live in global memory (step_kernel.cuh kModeGlobal) and the tables take the large record layout.
+  {
+    const size_t tab_small = static_cast<size_t>(align16(scr::fixed_tab(false) + static_cast<int>(op.ovf_start.size()) * 8));
+    const size_t need = tab_small + static_cast<size_t>(op.n_pad) * 2 * ctx->esize() + 16 +
+                        scr::group_smem_bytes(op.n_pad, op.npp, op.nv_pad, true);
+    ctx->gstate = op.nb > scr::kMaxBlocksOnChip || need > static_cast<size_t>(ctx->smem_optin) || scr::env_int("SCR_GLOBAL_STATE", 0) == 1;
+  }
   std::vector<unsigned char> tab, w;
-  if (ctx->prec == SCR_F64) build_blobs<double>(op, tab, w, ctx->off_vrow);
-  else build_blobs<float>(op, tab, w, ctx->off_vrow);
+  if (ctx->prec == SCR_F64) build_blobs<double>(op, tab, w, ctx->off_vrow, ctx->gstate);
+  else build_blobs<float>(op, tab, w, ctx->off_vrow, ctx->gstate);
   ctx->tab_bytes = static_cast<int>(tab.size());
   ctx->w_bytes = static_cast<int>(w.size());
   ctx->h_tab = tab;
@@ -1053,7 +1078,7 @@ int scr_debug_block_records(const scr_ctx* ctx, int32_t* records, int32_t max_re
   const PackedOperator& o = ctx->op;
   if (max_records < o.nb || max_bounds < o.wq + 1) return fail(ctx, SCR_E_ARG, "output buffers too small");
   std::memcpy(records, ctx->h_tab.data(), static_cast<size_t>(o.nb) * 16);
-  std::memcpy(list_bounds, ctx->h_tab.data() + scr::kRecBytes, static_cast<size_t>(o.wq + 1) * 4);
+  std::memcpy(list_bounds, ctx->h_tab.data() + scr::rec_bytes(ctx->gstate), static_cast<size_t>(o.wq + 1) * 4);
   return o.nb;
 }
 
@@ -1077,7 +1102,7 @@ int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count) {
   if (!ctx || !out) return SCR_E_ARG;
   if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
   const PackedOperator& o = ctx->op;
-  const size_t per_group = ctx->gstate ? static_cast<size_t>(scr::kGroupHdr) : ctx->gbytes;
+  const size_t per_group = ctx->gstate ? static_cast<size_t>(scr::group_hdr(false)) : ctx->gbytes;
   const int64_t v[17] = {o.n_pad, o.npp, static_cast<int64_t>(o.tile_val.size()), o.nv, o.lv, o.cap, o.wq, ctx->q,
                          static_cast<int64_t>(ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + ctx->q * per_group +
                                               w_prefix_bytes(ctx, ctx->q)),
@@ -1174,6 +1199,7 @@ int scr_run_phase(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_
                   const double* proj, const double* cnst, double dt, double sigma, double mu, uint64_t seed,
                   const double* noise, int64_t noise_steps) {
   NEED_GPU();
+  NvtxRange nvtx("scr_run_phase (lineage node: members + descendants)", m);
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (m < 0 || (m > 0 && (!cell_ids || !steps)) || !proj || !cnst) return fail(ctx, SCR_E_ARG, "bad arguments");
   if (ctx->readout_only) return fail(ctx, SCR_E_STATE, "read-out context (scr_set_genes): no network to step with");
@@ -1189,6 +1215,7 @@ int scr_probe(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* 
               const double* cnst, double dt, double sigma, double mu, double thresh, int32_t max_iter, int32_t avg_num,
               uint64_t seed, uint32_t stream, const double* noise, int32_t* iters_out, double* normdiff_out) {
   NEED_GPU();
+  NvtxRange nvtx("scr_probe (lineage node: convergence probe)", k, max_iter);
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (k <= 0 || !sample_ids || !proj || !cnst || !iters_out || max_iter <= 0 || avg_num <= 0)
     return fail(ctx, SCR_E_ARG, "bad arguments");
@@ -1202,6 +1229,7 @@ int scr_probe(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* 
 
 int scr_gene_sums(scr_ctx* ctx, double* sums_out) {
   NEED_GPU();
+  NvtxRange nvtx("scr_gene_sums");
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (!sums_out) return fail(ctx, SCR_E_ARG, "null output");
   const int n = ctx->op.n, n_pad = ctx->op.n_pad;
@@ -1232,6 +1260,7 @@ int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const doub
                 void* counts_out, int out_on_device, double* lambda_out, int out_dtype, int64_t* ovf_out,
                 int64_t ovf_cap, int64_t* ovf_count_out, double nb_phi = 0.0, double dropout_p = 0.0) {
   NEED_GPU();
+  NvtxRange nvtx("scr_counts (read-out)", cell_count);
   if (!(nb_phi >= 0.0) || !(dropout_p >= 0.0) || dropout_p > 1.0) return fail(ctx, SCR_E_ARG, "bad extension parameters");
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (!shift || !size_factors || !counts_out) return fail(ctx, SCR_E_ARG, "bad arguments");
@@ -1292,33 +1321,7 @@ int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const doub
   // free-running stream without a lambda dump: float32 screening of the lambda < 10 sampler (identical integers,
   // aux_kernels.cuh); SCR_COUNTS_EXACT=1 forces the float64 sampler for every entry (A/B tests)
   const bool fast = !uniforms && !lambda_out && nb_phi == 0.0 && dropout_p == 0.0 && scr::env_int("SCR_COUNTS_EXACT", 0) == 0;
-  // free-running, no dumps: the persistent warp-decoupled kernel (SCR_COUNTS_STREAM=0: the one-CTA-per-cell kernel, A/B tests)
-  const bool stream_kernel = fast && scr::env_int("SCR_COUNTS_STREAM", 1) != 0;
-  const size_t stream_smem = 3 * ((static_cast<size_t>(n) * esz + 15) & ~static_cast<size_t>(15)) + 64;
-  if (stream_kernel && stream_smem > 48 * 1024 && !ctx->stream_smem_optin) {
-    if (stream_smem > static_cast<size_t>(ctx->smem_optin)) return fail(ctx, SCR_E_RESOURCE, "count read-out: n too large for the staging rows");
-#define SCR_OPTIN_S(T, OUT) CKC(cudaFuncSetAttribute(scr::counts_stream_kernel<T, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin))
-    SCR_OPTIN_S(float, int32_t); SCR_OPTIN_S(float, uint16_t); SCR_OPTIN_S(float, uint8_t);
-    SCR_OPTIN_S(double, int32_t); SCR_OPTIN_S(double, uint16_t); SCR_OPTIN_S(double, uint8_t);
-#undef SCR_OPTIN_S
-    ctx->stream_smem_optin = true;
-  }
   auto launch = [&](int64_t c0, int64_t cnt, void* out, double* lam) -> cudaError_t {
-    if (stream_kernel) {
-      const unsigned grid = static_cast<unsigned>(std::min<int64_t>(cnt, static_cast<int64_t>(ctx->sm_count) * SCR_COUNTS_CTAS_PER_SM));
-#define SCR_LAUNCH_STREAM(T, OUT) \
-      scr::counts_stream_kernel<T, OUT><<<grid, 256, stream_smem, ctx->stream>>>( \
-          static_cast<const T*>(ctx->d_state), ctx->op.n_pad, ctx->d_ctab, ctx->d_lgam, n, cell_begin + c0, cnt, exp_scale, \
-          size_by_slot, crk, ctx->cell_offset, static_cast<OUT*>(out), ctx->d_err, ctx->d_covf, dev_ovf_cap, ctx->d_covf_count)
-#define SCR_STREAM_PREC(OUT) if (ctx->prec == SCR_F64) SCR_LAUNCH_STREAM(double, OUT); else SCR_LAUNCH_STREAM(float, OUT);
-      if (out_dtype == SCR_COUNT_I32) { SCR_STREAM_PREC(int32_t) }
-      else if (out_dtype == SCR_COUNT_U16) { SCR_STREAM_PREC(uint16_t) }
-      else { SCR_STREAM_PREC(uint8_t) }
-#undef SCR_STREAM_PREC
-#undef SCR_LAUNCH_STREAM
-      ctx->launches++;
-      return cudaGetLastError();
-    }
     const double* uni_by_slot = d_uni ? d_uni - cell_begin * n * static_cast<int64_t>(draws_per_entry) : nullptr;
 #define SCR_LAUNCH_COUNTS(T, FAST, OUT) \
     scr::counts_kernel<T, FAST, OUT><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>( \

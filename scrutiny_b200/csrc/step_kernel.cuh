@@ -382,6 +382,31 @@ template <> struct Traits<double> {
 // 16-byte row of one gene across the group's cells
 template <typename T> struct __align__(16) Row { T v[16 / sizeof(T)]; };
 
+// The state matrix is touched once per cell and phase (load at the start, store at the end): with SCR_STREAM_STATE these
+// 16-byte accesses use the streaming cache hint (evict-first), so they do not push the operator's L1-resident part out.
+#ifndef SCR_STREAM_STATE
+#define SCR_STREAM_STATE 0
+#endif
+template <typename RowT, typename T>
+__device__ __forceinline__ RowT load_state_row(const T* ptr) {
+#if SCR_STREAM_STATE
+  const float4 v = __ldcs(reinterpret_cast<const float4*>(ptr));
+  RowT r;
+  *reinterpret_cast<float4*>(&r) = v;
+  return r;
+#else
+  return *reinterpret_cast<const RowT*>(ptr);
+#endif
+}
+template <typename RowT, typename T>
+__device__ __forceinline__ void store_state_row(T* ptr, const RowT& r) {
+#if SCR_STREAM_STATE
+  __stcs(reinterpret_cast<float4*>(ptr), *reinterpret_cast<const float4*>(&r));
+#else
+  *reinterpret_cast<RowT*>(ptr) = r;
+#endif
+}
+
 struct __align__(16) Item {   // one cell group
   int cell[4];                // local slots, -1 = empty lane of the group
   int steps[4];               // iterations to run (0 for empty)
@@ -474,20 +499,27 @@ __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&)[2][kWordsPe
 //   then ovfidx (long-row chunk ranges), the staged head of the operator, and the cell groups:
 //   group = [kGroupHdr: ctrl words, three mbarriers, CellRound0 words, probe partials][bufA][bufB][chunk partials]
 // The tables a 128-gene block needs sit at compile-time offsets so that their addresses cost no instructions.
-constexpr int kMaxBlocks = 256;                 // n_pad <= 32768 (beyond ~7 000 genes the groups live in global memory: kModeGlobal)
-constexpr int kRecBytes = kMaxBlocks * 16;
-constexpr int kFixedTab = kRecBytes + 128;
+// Shared memory is the stepper's scarce resource: every byte the tables and headers take is a byte less of the operator's
+// staged head, and on the bench network 2 KB less of it cost 20 % (profiles/r2_stepper_ab.txt) -- so the on-chip modes keep
+// the 128-record table and the probe's window only exists in PROBE kernels.
+constexpr int kMaxBlocksOnChip = 128;           // n_pad <= 16384 with the groups in shared memory (they stop fitting near n = 7 000)
+constexpr int kMaxBlocks = 256;                 // n_pad <= 32768 with the groups in global memory (kModeGlobal)
+__host__ __device__ constexpr int rec_bytes(bool large) { return (large ? kMaxBlocks : kMaxBlocksOnChip) * 16; }
+__host__ __device__ constexpr int fixed_tab(bool large) { return rec_bytes(large) + 128; }
 // ctrl 16 | mbarriers 24 (+8 pad) | CellRound0 48 | steps 16 | cells 16 | step bases 16 | caller rows 16 | probe partials 16 x 16 |
 // probe window: the last kProbeRing values of mean|dx|/dt per cell (float64)
 constexpr int kProbeRing = 32;
 constexpr int kHdrBar = 16, kHdrR0 = 48, kHdrSteps = 96, kHdrCells = 112, kHdrBase = 128, kHdrRows = 144, kHdrRed = 160,
               kHdrRing = kHdrRed + 256;
-constexpr int kGroupHdr = kHdrRing + 4 * kProbeRing * 8;
+__host__ __device__ constexpr int group_hdr(bool probe) { return probe ? kHdrRing + 4 * kProbeRing * 8 : kHdrRing; }
 // block record flags
 constexpr int kBlkPP = 1, kBlkLong = 2, kBlkLastReg = 4, kBlkFirstPP = 8, kBlkBias = 16, kBlkFlagMask = 127;
 
-__host__ __device__ inline size_t group_smem_bytes(int n_pad, int npp, int nv_pad) {
-  return static_cast<size_t>(n_pad + npp + nv_pad) * 16 + kGroupHdr;
+__host__ __device__ inline size_t group_state_bytes(int n_pad, int npp, int nv_pad) {   // bufA | bufB | chunk partials
+  return static_cast<size_t>(n_pad + npp + nv_pad) * 16;
+}
+__host__ __device__ inline size_t group_smem_bytes(int n_pad, int npp, int nv_pad, bool probe) {
+  return group_state_bytes(n_pad, npp, nv_pad) + group_hdr(probe);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -510,6 +542,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   using RowT = Row<T>;
   constexpr int CPG = TR::CPG;
   constexpr bool W_SMEM = MODE == kModeSmem, GSTATE = MODE == kModeGlobal;
+  constexpr int kRecBytes = rec_bytes(GSTATE), kFixedTab = fixed_tab(GSTATE), kGroupHdr = group_hdr(PROBE);
 
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* s_pc = GSTATE ? const_cast<unsigned char*>(p.pc) : smem + kFixedTab;
@@ -518,7 +551,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
   unsigned char* s_w = s_var + var_bytes;
   const int wpre = W_SMEM ? p.w_bytes : (GSTATE ? 0 : p.w_prefix);   // bytes of the operator held in shared memory
   unsigned char* s_groups = s_w + wpre;
-  const size_t gstate_bytes = group_smem_bytes(p.n_pad, p.npp, p.nv_pad) - kGroupHdr;   // bufA | bufB | chunk partials
+  const size_t gstate_bytes = group_state_bytes(p.n_pad, p.npp, p.nv_pad);
   const size_t gbytes = GSTATE ? static_cast<size_t>(kGroupHdr) : gstate_bytes + kGroupHdr;   // per group in shared memory
   uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_groups + static_cast<size_t>(p.q) * gbytes);
 
@@ -660,7 +693,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
 #pragma unroll
       for (int c = 0; c < CPG; ++c) {
         if (it.cell[c] >= 0) {
-          r[c] = *reinterpret_cast<const RowT*>(p.state + static_cast<int64_t>(it.cell[c]) * p.ld + g0);
+          r[c] = load_state_row<RowT>(p.state + static_cast<int64_t>(it.cell[c]) * p.ld + g0);
         } else {
 #pragma unroll
           for (int jj = 0; jj < CPG; ++jj) r[c].v[jj] = T(0);
@@ -1055,7 +1088,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
 #pragma unroll
         for (int c = 0; c < CPG; ++c) {
           const int cell = hcells[c];
-          if (cell >= 0) *reinterpret_cast<RowT*>(p.state + static_cast<int64_t>(cell) * p.ld + g0) = r[c];
+          if (cell >= 0) store_state_row<RowT>(p.state + static_cast<int64_t>(cell) * p.ld + g0, r[c]);
         }
       }
     }

@@ -47,15 +47,14 @@ def test_compact_counts_are_the_int32_counts(prec):
     size = rng.normal(1, 0.14, size=cells) ** 3
     want = e.counts(shift, size, seed=77)
     assert (want >= 255).sum() > 500 and (want >= 65535).sum() == 0 and want.max() > 1000
-    # the persistent warp-decoupled kernel (default) against the one-CTA-per-cell kernel and the float64 sampler
+    # the float32-screened sampler (small-lambda and PTRS screens, default) against the float64 sampler alone
     import os
-    for env in ("SCR_COUNTS_STREAM", "SCR_COUNTS_EXACT"):
-        os.environ[env] = "0" if env == "SCR_COUNTS_STREAM" else "1"
-        try:
-            assert np.array_equal(e.counts(shift, size, seed=77), want), env
-            assert np.array_equal(e.counts_compact(shift, size, seed=77, dtype="uint8")[0], np.minimum(want, 255)), env
-        finally:
-            del os.environ[env]
+    os.environ["SCR_COUNTS_EXACT"] = "1"
+    try:
+        assert np.array_equal(e.counts(shift, size, seed=77), want)
+        assert np.array_equal(e.counts_compact(shift, size, seed=77, dtype="uint8")[0], np.minimum(want, 255))
+    finally:
+        del os.environ["SCR_COUNTS_EXACT"]
     for dtype, esc in (("uint8", 255), ("uint16", 65535)):
         got, ovf = e.counts_compact(shift, size, seed=77, dtype=dtype)
         assert got.dtype == np.dtype(dtype) and ovf.shape[1] == 3
