@@ -114,7 +114,7 @@ struct BankModel {
   }
 };
 
-// SCR_BANK_OPT (default 6 passes, 0 = off; +5.8 % on the bench network, profiles/r2_stepper_ab.txt): genes are exchanged inside aligned groups of 8 positions
+// SCR_BANK_OPT (default 6 passes, 0 = off; +5.8 % on the bench network, profiles/r2_experiments.txt): genes are exchanged inside aligned groups of 8 positions
 // -- which keeps every block's row set, the class prefixes and the rows of each quarter warp, and only changes the bank
 // group a gene's state row falls into -- whenever that lowers the modelled wavefront count.  Long rows stay where they
 // are (their order numbers the chunks, i.e. decides which chunks share a quarter warp), so every read set keeps its

@@ -286,7 +286,14 @@ int w_prefix_bytes(const scr_ctx* ctx, int q, bool probe = false) {
   const int cap_kb = scr::env_int("SCR_W_PREFIX_KB", -1);
   if (cap_kb >= 0) room = std::min<long>(room, static_cast<long>(cap_kb) * 1024);
   room = std::min<long>(room, ctx->w_bytes);
-  return room >= 128 ? static_cast<int>(room / 128 * 128) : 0;
+  int prefix = room >= 128 ? static_cast<int>(room / 128 * 128) : 0;
+  // Any prefix beyond ~1.5 KB moves the SM to its largest shared-memory carve-out and leaves 28 KB of L1, where the part
+  // of the operator that is NOT staged has to stay resident next to the state traffic: measured on the bench network
+  // (profiles/r2_experiments.txt), a rest of <= 20 KB runs at full speed, 24 KB at -20 %, while no prefix at all (60 KB of
+  // L1 for a 54 KB operator) is as fast as the full one.  So: stage the head only if the rest then fits L1; an operator that
+  // fits the larger L1 whole is left there; one that fits neither keeps the prefix (fewer trips to L2).
+  if (cap_kb < 0 && prefix > 0 && ctx->w_bytes - prefix > 20 * 1024 && ctx->w_bytes <= 56 * 1024) prefix = 0;
+  return prefix;
 }
 
 template <typename T, bool PROBE, bool SUPPLIED>

@@ -382,30 +382,6 @@ template <> struct Traits<double> {
 // 16-byte row of one gene across the group's cells
 template <typename T> struct __align__(16) Row { T v[16 / sizeof(T)]; };
 
-// The state matrix is touched once per cell and phase (load at the start, store at the end): with SCR_STREAM_STATE these
-// 16-byte accesses use the streaming cache hint (evict-first), so they do not push the operator's L1-resident part out.
-#ifndef SCR_STREAM_STATE
-#define SCR_STREAM_STATE 0
-#endif
-template <typename RowT, typename T>
-__device__ __forceinline__ RowT load_state_row(const T* ptr) {
-#if SCR_STREAM_STATE
-  const float4 v = __ldcs(reinterpret_cast<const float4*>(ptr));
-  RowT r;
-  *reinterpret_cast<float4*>(&r) = v;
-  return r;
-#else
-  return *reinterpret_cast<const RowT*>(ptr);
-#endif
-}
-template <typename RowT, typename T>
-__device__ __forceinline__ void store_state_row(T* ptr, const RowT& r) {
-#if SCR_STREAM_STATE
-  __stcs(reinterpret_cast<float4*>(ptr), *reinterpret_cast<const float4*>(&r));
-#else
-  *reinterpret_cast<RowT*>(ptr) = r;
-#endif
-}
 
 struct __align__(16) Item {   // one cell group
   int cell[4];                // local slots, -1 = empty lane of the group
@@ -500,7 +476,7 @@ __device__ __forceinline__ void fast_update_f32x2(const uint32_t (&)[2][kWordsPe
 //   group = [kGroupHdr: ctrl words, three mbarriers, CellRound0 words, probe partials][bufA][bufB][chunk partials]
 // The tables a 128-gene block needs sit at compile-time offsets so that their addresses cost no instructions.
 // Shared memory is the stepper's scarce resource: every byte the tables and headers take is a byte less of the operator's
-// staged head, and on the bench network 2 KB less of it cost 20 % (profiles/r2_stepper_ab.txt) -- so the on-chip modes keep
+// staged head, and on the bench network 2 KB less of it cost 20 % (profiles/r2_experiments.txt) -- so the on-chip modes keep
 // the 128-record table and the probe's window only exists in PROBE kernels.
 constexpr int kMaxBlocksOnChip = 128;           // n_pad <= 16384 with the groups in shared memory (they stop fitting near n = 7 000)
 constexpr int kMaxBlocks = 256;                 // n_pad <= 32768 with the groups in global memory (kModeGlobal)
@@ -693,7 +669,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
 #pragma unroll
       for (int c = 0; c < CPG; ++c) {
         if (it.cell[c] >= 0) {
-          r[c] = load_state_row<RowT>(p.state + static_cast<int64_t>(it.cell[c]) * p.ld + g0);
+          r[c] = *reinterpret_cast<const RowT*>(p.state + static_cast<int64_t>(it.cell[c]) * p.ld + g0);
         } else {
 #pragma unroll
           for (int jj = 0; jj < CPG; ++jj) r[c].v[jj] = T(0);
@@ -1088,7 +1064,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
 #pragma unroll
         for (int c = 0; c < CPG; ++c) {
           const int cell = hcells[c];
-          if (cell >= 0) store_state_row<RowT>(p.state + static_cast<int64_t>(cell) * p.ld + g0, r[c]);
+          if (cell >= 0) *reinterpret_cast<RowT*>(p.state + static_cast<int64_t>(cell) * p.ld + g0) = r[c];
         }
       }
     }

@@ -97,8 +97,8 @@ def test_transform_data_compact_equals_dense(golden):
 # read-out context without a network: any n
 # ---------------------------------------------------------------------------------------------
 def test_readout_context_takes_a_gene_count_beyond_the_steppers_budget():
-    """n = 20 000 (the reference's driver mentions n = 19 027): one cell group of that size cannot live in shared memory,
-    so the stepper refuses such a network -- but transformData needs none."""
+    """n = 20 000 (the reference's driver mentions n = 19 027): transformData needs no network at all, so the read-out
+    context takes any n; the stepper takes it too, through its global-memory fallback."""
     from scrutiny_b200 import engine as em
     n, cells = 20000, 24
     rng = np.random.RandomState(8)
@@ -118,9 +118,12 @@ def test_readout_context_takes_a_gene_count_beyond_the_steppers_budget():
     with pytest.raises(em.ScrutinyError) as err:
         e.run_phase([0], [1], np.ones(n), np.zeros(n))
     assert err.value.code == -3
-    big = em.Engine(0, "f32")
-    with pytest.raises(em.ScrutinyError) as err:                          # the stepper's own limit is a clear error
-        big.set_network(csr=(np.arange(n + 1, dtype=np.int32), np.arange(n, dtype=np.int32), np.ones(n)), n=n)
+    big = em.Engine(0, "f32")                                             # the stepper takes this n with its groups in global memory
+    big.set_network(csr=(np.arange(n + 1, dtype=np.int32), np.arange(n, dtype=np.int32), np.ones(n)), n=n)
+    assert big.layout()["state_in_global"] == 1
+    huge = 40000                                                          # beyond 32 768 genes: a clear error
+    with pytest.raises(em.ScrutinyError) as err:
+        big.set_network(csr=(np.arange(huge + 1, dtype=np.int32), np.arange(huge, dtype=np.int32), np.ones(huge)), n=huge)
     assert err.value.code == -4 and "n too large" in str(err.value)
 
 
