@@ -481,7 +481,7 @@ def test_counts_uniform_exhaustion_is_an_error(eng_mod):
 def test_partly_resident_operator_is_bit_identical(eng_mod, prec):
     """When the operator does not fit in shared memory next to the cell groups, its head is staged there and the
     rest read through L1 (StepParams::w_prefix).  Where an entry is read from must not change a single bit: compare
-    SCR_W_PREFIX_KB=0 (all global), 4 (a few blocks staged) and the default (all that fits) on a network big enough
+    SCR_W_PREFIX_KB=0 (all global), 4 / 24 (some blocks staged) and the default policy on a network big enough
     that the default is partial, with long rows (chunk table beyond the prefix) and ragged steps."""
     import os
     n, cells, seed = 3000, 1300, 99   # > 2 x 148 groups: two groups per CTA, so the default prefix is partial
@@ -496,7 +496,7 @@ def test_partly_resident_operator_is_bit_identical(eng_mod, prec):
     proj = (rng.rand(n) > 0.05).astype(np.float64)
     const = 0.1 * rng.randn(n) * (1 - proj)
     outs, iters = [], []
-    for kb in ("0", "4", None):
+    for kb in ("0", "4", "24", None):
         if kb is not None:
             os.environ["SCR_W_PREFIX_KB"] = kb
         try:
@@ -511,8 +511,10 @@ def test_partly_resident_operator_is_bit_identical(eng_mod, prec):
             assert lay["operator_prefix_bytes"] == 0
         elif kb == "4":
             assert lay["operator_prefix_bytes"] == 4096
-        elif not lay["operator_in_smem"]:
-            assert 0 < lay["operator_prefix_bytes"] < lay["operator_bytes"]
+        elif kb == "24":
+            assert lay["operator_prefix_bytes"] == min(24576, lay["operator_bytes"] // 128 * 128) and not lay["operator_in_smem"]
+        elif not lay["operator_in_smem"]:   # the default policy: all that fits, or nothing when the rest would overflow L1
+            assert 0 <= lay["operator_prefix_bytes"] < lay["operator_bytes"]
         outs.append(e.get_states())
         iters.append(it)
     for o, it in zip(outs[1:], iters[1:]):
