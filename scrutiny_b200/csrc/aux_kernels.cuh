@@ -257,8 +257,11 @@ struct __align__(16) CountGene { int gene; int state_idx; double shift; };
 #ifndef SCR_COUNTS_PTRS_F32
 #define SCR_COUNTS_PTRS_F32 1   // 0: lambda >= 10 always through the float64 sampler (A/B builds)
 #endif
+#ifndef SCR_COUNTS_THREADS
+#define SCR_COUNTS_THREADS 256     // threads of a CTA = of one cell's read-out
+#endif
 #ifndef SCR_COUNTS_CTAS_PER_SM
-#define SCR_COUNTS_CTAS_PER_SM 4   // 64 registers: the sampler is latency-bound (dependent FP64 chains), more warps pay (2 / 3 / 4 CTAs: 28.8 / 22.5 / 21.5 ms at 400k cells)
+#define SCR_COUNTS_CTAS_PER_SM (1024 / SCR_COUNTS_THREADS)   // 64 registers: the sampler is latency-bound, more warps pay (2 / 3 / 4 CTAs of 256: 28.8 / 22.5 / 21.5 ms at 400k cells)
 #endif
 // OUT = int32_t, or a compact type (uint16_t / uint8_t): a count that does not fit below the type's largest value is
 // stored as that value (the escape code) and appended as {local cell, gene, count} to the overflow list (capacity
@@ -269,7 +272,7 @@ template <> struct CountLimit<uint16_t> { static constexpr int kEscape = 0xffff;
 template <> struct CountLimit<uint8_t> { static constexpr int kEscape = 0xff; };
 
 template <typename T, bool FAST, typename OUT>
-__global__ void __launch_bounds__(256, SCR_COUNTS_CTAS_PER_SM)
+__global__ void __launch_bounds__(SCR_COUNTS_THREADS, SCR_COUNTS_CTAS_PER_SM)
 counts_kernel(const T* __restrict__ state, int64_t ld, const CountGene* __restrict__ genes, const float* __restrict__ lgam,
                               int n, int64_t cell0,
                               double exp_scale, const double* __restrict__ sizef, const RoundKeys rk,

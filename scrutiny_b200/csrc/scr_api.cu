@@ -618,6 +618,7 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
     if ((rc = make_tmap(ctx, &tm_alo[i], ctx->d_xlo[i], m_pad, ld, ld, D::BM))) return rc;
   }
   float* d_noise = nullptr;
+  struct FreeOnExit { float*& ptr; ~FreeOnExit() { cudaFree(ptr); } } free_noise{d_noise};   // every return below frees it
   if (noise) {
     rc = upload_noise<float>(ctx, noise, static_cast<size_t>(m) * noise_steps * n, &d_noise);
     if (rc) return rc;
@@ -657,7 +658,6 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
   ctx->launches++;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_noise);
   if (e != cudaSuccess) return fail_cuda(ctx, e, "dense stepper");
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -1331,7 +1331,7 @@ int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const doub
   auto launch = [&](int64_t c0, int64_t cnt, void* out, double* lam) -> cudaError_t {
     const double* uni_by_slot = d_uni ? d_uni - cell_begin * n * static_cast<int64_t>(draws_per_entry) : nullptr;
 #define SCR_LAUNCH_COUNTS(T, FAST, OUT) \
-    scr::counts_kernel<T, FAST, OUT><<<static_cast<unsigned>(cnt), 256, n * sizeof(int32_t), ctx->stream>>>( \
+    scr::counts_kernel<T, FAST, OUT><<<static_cast<unsigned>(cnt), SCR_COUNTS_THREADS, n * sizeof(int32_t), ctx->stream>>>( \
         static_cast<const T*>(ctx->d_state), ctx->op.n_pad, ctx->d_ctab, ctx->d_lgam, n, cell_begin + c0, exp_scale, \
         size_by_slot, crk, ctx->cell_offset, uni_by_slot, draws_per_entry, static_cast<OUT*>(out), lam, ctx->d_err, \
         ctx->d_covf, dev_ovf_cap, ctx->d_covf_count, nb_phi, dropout_p)
@@ -1523,7 +1523,11 @@ int scr_rank_transform(scr_ctx* ctx, int64_t n, int64_t cells, double* S, int64_
   double* d_slab[2] = {nullptr, nullptr};
   int* d_paths = nullptr;
   int* d_fb[2] = {nullptr, nullptr};
-  auto cleanup = [&]() { cudaFree(d_keys); cudaFree(d_slab[0]); cudaFree(d_slab[1]); cudaFree(d_paths); cudaFree(d_fb[0]); cudaFree(d_fb[1]); };
+  cudaEvent_t k0[2] = {nullptr, nullptr}, k1[2] = {nullptr, nullptr};
+  auto cleanup = [&]() {
+    cudaFree(d_keys); cudaFree(d_slab[0]); cudaFree(d_slab[1]); cudaFree(d_paths); cudaFree(d_fb[0]); cudaFree(d_fb[1]);
+    for (int b = 0; b < 2; ++b) { if (k0[b]) cudaEventDestroy(k0[b]); if (k1[b]) cudaEventDestroy(k1[b]); }
+  };
 #define CKR(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
   CKR(cudaMalloc(&d_keys, static_cast<size_t>(n) * cells * sizeof(uint16_t)));
   CKR(cudaMalloc(&d_slab[0], static_cast<size_t>(slab_elems) * 8));
@@ -1533,7 +1537,6 @@ int scr_rank_transform(scr_ctx* ctx, int64_t n, int64_t cells, double* S, int64_
   CKR(cudaMalloc(&d_fb[1], static_cast<size_t>(cw) * sizeof(int)));
   CKR(cudaMemsetAsync(d_paths, 0, 2 * sizeof(int), ctx->stream));
   CKR(cudaStreamSynchronize(ctx->stream));
-  cudaEvent_t k0[2], k1[2];
   for (int b = 0; b < 2; ++b) { CKR(cudaEventCreate(&k0[b])); CKR(cudaEventCreate(&k1[b])); }
   double kernel_ms = 0.0;
   auto reap = [&](int b) {   // the kernel that last used slab b has been waited for: add its time
@@ -1592,7 +1595,6 @@ int scr_rank_transform(scr_ctx* ctx, int64_t n, int64_t cells, double* S, int64_
   int paths[2] = {0, 0};
   CKR(cudaMemcpy(paths, d_paths, sizeof(paths), cudaMemcpyDeviceToHost));
 #undef CKR
-  for (int b = 0; b < 2; ++b) { cudaEventDestroy(k0[b]); cudaEventDestroy(k1[b]); }
   cleanup();
   ctx->rank_kernel_ms = kernel_ms;
   ctx->rank_counting = paths[0];
