@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--extra", default="trrust,powerlaw205,f64,dense_c4,counts,alpha_search,strong",
+    ap.add_argument("--extra", default="trrust,powerlaw205,f64,dense_c4,counts,alpha_search,module_api,strong",
                     help="comma-separated extra blocks to measure after the headline")
     ap.add_argument("--gather", action="store_true", help="also gather the count shards on rank 0 with NCCL (N > 1)")
     ap.add_argument("--counts-dtype", default="uint8", choices=["uint8", "uint16", "int32"])
@@ -565,6 +565,39 @@ def run_extras(args, env, rig, counts_dev, want, peak, peak_source, dev):
             res["scaling"] = "strong"
             return res
         block("strong", strong)
+
+    # -- the drop-in MODULE surface end to end: the reference's own call sequence with its float64
+    #    (genes, cells) host matrices -- upload, lineage run with probes, download, read-out -- on one GPU
+    def module_block():
+        if rank != 0:
+            return None
+        import scrutiny_b200.MatriSeq as ms
+        cells = min(100000, args.cells)
+        ms.init(outputDir=None, seed=1337, verbose=False, device=env["local"])
+        import scipy.sparse as sp
+        gc = sp.csr_matrix((rig.csr[2], rig.csr[1], rig.csr[0]), shape=(n, n))
+        tree = build_tree(n, cells, rig.tf)
+        sampler = ClockSampler(env["local"]).start()
+        best = None
+        for rep in range(3):
+            states = np.repeat(rig.x0[:, None], cells, axis=1)
+            types = np.zeros(cells, dtype="int64")
+            iters = np.zeros(cells, dtype="int64")
+            t0 = time.perf_counter()
+            ms.findAllNextStates(gc, tree.head(), tree, states, types, iters)
+            t1 = time.perf_counter()
+            counts, size = ms.transformData(n, cells, states, compact=True)
+            t2 = time.perf_counter()
+            if rep and (best is None or t2 - t0 < best[0]):
+                best = (t2 - t0, t1 - t0, t2 - t1, float(iters.sum()), counts.nbytes_compact())
+        ms.init(outputDir=None, seed=1337, verbose=False, device=env["local"])     # drops the cached context
+        return {"metric": "cell_steps_per_sec", "workload": "scrutiny_b200.MatriSeq.findAllNextStates + transformData(compact=True) on "
+                "%d cells, contract network: float64 (genes, cells) host matrix in, the same matrix and the counts out" % cells,
+                "value": best[3] / best[0], "seconds": best[0], "findAllNextStates_s": best[1], "transformData_s": best[2],
+                "cell_steps": best[3], "h2d_bytes": int(2 * 8 * n * cells), "d2h_bytes": int(8 * n * cells + best[4]),
+                "clocks": sampler.stop()}
+    block("module_api", module_block)
+    env["barrier"]()
 
     # -- config c4 on the tcgen05 3xTF32 stepper -------------------------------------------------------------------
     def dense_block():

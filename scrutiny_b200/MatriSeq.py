@@ -41,7 +41,7 @@ from . import artefacts as _artefacts
 from . import network as _network
 from .engine import STREAM_ALPHA, Engine
 from .lineage import Tree
-from .simulate import LineageSimulation
+from .simulate import Comm, LineageSimulation
 
 __outputDir = None
 __verbose = None
@@ -315,7 +315,7 @@ def findAllNextStates(gc, cellTypeNode, cellTypeTree, currentStates, cellTypesRe
     ``currentStates`` (n, cells), ``cellTypesRecord`` and ``totalCellIterations`` in place; returns None."""
     cells = currentStates.shape[1]
     eng = _engine_for(gc, cells, currentStates, precision)
-    sim = LineageSimulation(eng, cells, seed=_next_seed(), verbose=bool(__verbose))
+    sim = LineageSimulation(eng, cells, comm=Comm(single=True), seed=_next_seed(), verbose=bool(__verbose))
     user = dict(timeStep=timeStep, noiseDisp=noiseDisp, convergenceThreshold=convergenceThreshold,
                 maxNumIterations=maxNumIterations, convDistAvgNum=convDistAvgNum, cellsToSample=cellsToSample,
                 cellDevelopmentMode=cellDevelopmentMode, geneMeanLevels=geneMeanLevels)
@@ -348,7 +348,7 @@ def transformData(n, cells, finalCellStates, dropoutProportion=0.0, cellRadiusDi
         eng.set_genes(n)                                                         # the read-out needs no network
         eng.alloc_cells(cells)
         eng.set_states(finalCellStates)
-        sim = LineageSimulation(eng, cells, seed=_next_seed())
+        sim = LineageSimulation(eng, cells, comm=Comm(single=True), seed=_next_seed())
         ext = dict(nb_dispersion=float(nbDispersion), dropout=float(dropoutProportion) if applyDropout else 0.0)
         dense = (compact is False or (compact is None and 8 * n * cells <= _artefacts.DENSE_LIMIT) or capture is not None
                  or ext["nb_dispersion"] > 0 or ext["dropout"] > 0)

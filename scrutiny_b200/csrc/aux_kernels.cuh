@@ -258,7 +258,7 @@ struct __align__(16) CountGene { int gene; int state_idx; double shift; };
 #define SCR_COUNTS_PTRS_F32 1   // 0: lambda >= 10 always through the float64 sampler (A/B builds)
 #endif
 #ifndef SCR_COUNTS_THREADS
-#define SCR_COUNTS_THREADS 256     // threads of a CTA = of one cell's read-out
+#define SCR_COUNTS_THREADS 128     // threads of a CTA = of one cell's read-out (64 / 128 / 256: 76.4 / 86.4 / 83.2 G entries/s: fewer warps wait at a cell's barrier)
 #endif
 #ifndef SCR_COUNTS_CTAS_PER_SM
 #define SCR_COUNTS_CTAS_PER_SM (1024 / SCR_COUNTS_THREADS)   // 64 registers: the sampler is latency-bound, more warps pay (2 / 3 / 4 CTAs of 256: 28.8 / 22.5 / 21.5 ms at 400k cells)

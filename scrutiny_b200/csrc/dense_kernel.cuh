@@ -26,11 +26,19 @@
 namespace scr {
 namespace dense {
 
-constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2;
-constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;          // 96 KB
+constexpr int BM = 128, BN = 256, BK = 32;   // BN: the wide output tile, also the padding unit of n
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + BN * 8 /*pc tile*/ + 256 /*barriers*/;
+// Tile shapes.  Wide (128 x 256 outputs, 2-stage 96 KB ring): large cell batches, the tensor pipe is the bound (config c4).
+// Narrow (128 x 64 outputs, 4-stage 48 KB ring): small batches -- with 1 000 cells and n = 500 (config c1) the wide shape makes
+// only 16 tiles for 148 SMs; the narrow one makes 64, each a quarter of the work, so a timestep's launch is ~3x shorter.
+template <int BN_> struct Tile {
+  static constexpr int BN = BN_, STAGES = BN_ >= 256 ? 2 : 4;
+  static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN_ * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN_;                      // two accumulators (power of two >= 32)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + BN_ * 8 /*pc tile*/ + 256 /*barriers*/;
+};
+constexpr int BN_NARROW = 64;
 
 struct Params {
   const float* x_cur;        // [m_pad][ld]
@@ -100,9 +108,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <int BN_>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const Params p) {
+  using TL = Tile<BN_>;
+  constexpr int BN = TL::BN, STAGES = TL::STAGES, A_BYTES = TL::A_BYTES, B_BYTES = TL::B_BYTES, STAGE_BYTES = TL::STAGE_BYTES;
   extern __shared__ unsigned char dsmem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   unsigned char* stage_mem = base;
@@ -122,8 +133,8 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_const
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: all 512 columns (two 256-column accumulators)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+  if (warp == 1) {   // TMEM: two accumulators of BN columns (all 512 columns for the wide tile)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TL::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -275,7 +286,7 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_const
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TL::TMEM_COLS) : "memory");
   }
 }
 

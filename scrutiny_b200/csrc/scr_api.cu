@@ -66,7 +66,9 @@ struct scr_ctx {
   // dense (tcgen05 3xTF32) path
   bool dense_mode = false;
   float *d_whi = nullptr, *d_wlo = nullptr;      // [n_pad][n_pad] hi / lo splits of W
-  CUtensorMap tm_bhi, tm_blo;
+  CUtensorMap tm_bhi, tm_blo;                  // B operands, boxes of the wide tile (256 genes x 32)
+  CUtensorMap tm_bhi_n, tm_blo_n;              // ... of the narrow tile (64 genes x 32)
+  bool dense_attr_set = false;
   float *d_x[2] = {nullptr, nullptr}, *d_xlo[2] = {nullptr, nullptr};   // working set [rows_cap][n_pad]
   int64_t rows_cap = 0;
   int *d_row_cell = nullptr, *d_row_steps = nullptr, *d_row_src = nullptr, *d_tile_steps = nullptr;
@@ -108,6 +110,8 @@ struct scr_ctx {
   int* d_piters = nullptr;
   double* d_pnd = nullptr;
   size_t piters_cap = 0, pnd_cap = 0;
+  unsigned char* d_parena = nullptr;         // dense probe: one arena for its private working set
+  size_t parena_cap = 0;
   // stepper launch configuration per kernel variant [probe][supplied]: the dynamic shared-memory opt-in and the
   // occupancy query are made once per size, not per launch
   struct LaunchCfg { size_t smem = 0; int threads = 0, per_sm = 0, mode = -1; };
@@ -553,6 +557,34 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
 
 
 // ---- dense path: one tcgen05 GEMM launch per timestep over the phase's working set ----
+// Tile shape per launch: the narrow tile (128 x 64) when the wide one (128 x 256) would leave more than half of the SMs
+// without a tile (small cell batches: config c1, every probe), the wide one otherwise.
+bool dense_use_narrow(const scr_ctx* ctx, int m_tiles, int ld) {
+  const int force = scr::env_int("SCR_DENSE_NARROW", -1);
+  if (force >= 0) return force != 0;
+  return m_tiles * (ld / scr::dense::BN) * 2 <= ctx->sm_count;
+}
+int dense_set_attrs(scr_ctx* ctx) {
+  namespace D = scr::dense;
+  if (ctx->dense_attr_set) return SCR_OK;
+  CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN_NARROW>::SMEM_BYTES));
+  ctx->dense_attr_set = true;
+  return SCR_OK;
+}
+void dense_launch(scr_ctx* ctx, bool narrow, int m_tiles, const CUtensorMap& tm_a, const CUtensorMap& tm_alo, scr::dense::Params& p) {
+  namespace D = scr::dense;
+  if (narrow) {
+    p.n_tiles = p.ld / D::BN_NARROW;
+    const int grid = std::min(m_tiles * p.n_tiles, ctx->sm_count);
+    D::dense_step_kernel<D::BN_NARROW><<<grid, D::NUM_THREADS, D::Tile<D::BN_NARROW>::SMEM_BYTES, ctx->stream>>>(tm_a, tm_alo, ctx->tm_bhi_n, ctx->tm_blo_n, p);
+  } else {
+    p.n_tiles = p.ld / D::BN;
+    const int grid = std::min(m_tiles * p.n_tiles, ctx->sm_count);
+    D::dense_step_kernel<D::BN><<<grid, D::NUM_THREADS, D::Tile<D::BN>::SMEM_BYTES, ctx->stream>>>(tm_a, tm_alo, ctx->tm_bhi, ctx->tm_blo, p);
+  }
+  ctx->launches++;
+}
 int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t* steps, const int64_t* step_base,
                     const double* proj, const double* cnst, double dt, double sigma, double mu, uint64_t seed,
                     const double* noise, int64_t noise_steps) {
@@ -634,7 +666,7 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
   scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_STEP), p.rk);
   p.noise = d_noise; p.noise_steps = noise_steps;
 
-  CK(cudaFuncSetAttribute(D::dense_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM_BYTES));
+  if ((rc = dense_set_attrs(ctx))) return rc;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   D::gather_rows_kernel<<<static_cast<unsigned>(m_pad), 256, 0, ctx->stream>>>(
       static_cast<const float*>(ctx->d_state), ld, ctx->d_row_cell, static_cast<int>(live), ctx->d_x[0], ctx->d_xlo[0], ld);
@@ -646,9 +678,7 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
     const int cur = s & 1;
     p.x_cur = ctx->d_x[cur]; p.x_next = ctx->d_x[cur ^ 1]; p.xlo_next = ctx->d_xlo[cur ^ 1];
     p.m_tiles = active_tiles; p.s = s;
-    const int grid = std::min(active_tiles * p.n_tiles, ctx->sm_count);
-    D::dense_step_kernel<<<grid, D::NUM_THREADS, D::SMEM_BYTES, ctx->stream>>>(tm_a[cur], tm_alo[cur], ctx->tm_bhi, ctx->tm_blo, p);
-    ctx->launches++;
+    dense_launch(ctx, dense_use_narrow(ctx, active_tiles, ld), active_tiles, tm_a[cur], tm_alo[cur], p);
     ctx->dense_launches++;
   }
   CK(cudaGetLastError());
@@ -681,7 +711,9 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   const PackedOperator& op = ctx->op;
   const int n = op.n, ld = op.n_pad;
   const int64_t m_pad = (static_cast<int64_t>(k) + D::BM - 1) / D::BM * D::BM;
-  const int m_tiles = static_cast<int>(m_pad / D::BM), n_tiles = ld / D::BN;
+  const int m_tiles = static_cast<int>(m_pad / D::BM);
+  const bool narrow = dense_use_narrow(ctx, m_tiles, ld);
+  const int n_tiles = ld / (narrow ? D::BN_NARROW : D::BN);
   std::vector<int> h_cell(m_pad, -1), h_steps(m_pad, 0), h_src(m_pad, 0);
   std::vector<uint32_t> h_base(m_pad, 0);
   std::vector<int64_t> h_gid(m_pad, 0);
@@ -701,17 +733,27 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   int64_t* d_gid = nullptr;
   const int chunk = 64;
   const size_t diff_per_step = static_cast<size_t>(n_tiles) * m_pad;
-  auto cleanup = [&]() {
-    for (int i = 0; i < 2; ++i) { cudaFree(x[i]); cudaFree(xlo[i]); }
-    cudaFree(d_scale); cudaFree(d_diff); cudaFree(d_noise); cudaFree(d_cell); cudaFree(d_steps); cudaFree(d_src);
-    cudaFree(d_base); cudaFree(d_gid);
-  };
+  auto cleanup = [&]() { cudaFree(d_noise); };   // (supplied noise only; everything else lives in the context's probe arena)
 #define CKP(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
+  // the working set is carved out of one arena the context keeps between calls (an alpha search probes dozens of times:
+  // eleven cudaMalloc / cudaFree pairs per call cost more than a probe's kernels)
   const size_t bytes = static_cast<size_t>(m_pad) * ld * 4;
-  for (int i = 0; i < 2; ++i) { CKP(cudaMalloc(&x[i], bytes)); CKP(cudaMalloc(&xlo[i], bytes)); }
-  CKP(cudaMalloc(&d_scale, m_pad * 4)); CKP(cudaMalloc(&d_diff, diff_per_step * chunk * 4));
-  CKP(cudaMalloc(&d_cell, m_pad * 4)); CKP(cudaMalloc(&d_steps, m_pad * 4)); CKP(cudaMalloc(&d_src, m_pad * 4));
-  CKP(cudaMalloc(&d_base, m_pad * 4)); CKP(cudaMalloc(&d_gid, m_pad * 8));
+  {
+    auto al = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+    const size_t need = 4 * al(bytes) + al(m_pad * 4) * 5 + al(diff_per_step * chunk * 4) + al(m_pad * 8);
+    int rcb = ensure_buf(ctx, ctx->d_parena, ctx->parena_cap, need);
+    if (rcb) return rcb;
+    unsigned char* at = ctx->d_parena;
+    auto take = [&](size_t v) { unsigned char* r = at; at += al(v); return r; };
+    for (int i = 0; i < 2; ++i) { x[i] = reinterpret_cast<float*>(take(bytes)); xlo[i] = reinterpret_cast<float*>(take(bytes)); }
+    d_scale = reinterpret_cast<float*>(take(m_pad * 4));
+    d_diff = reinterpret_cast<float*>(take(diff_per_step * chunk * 4));
+    d_cell = reinterpret_cast<int*>(take(m_pad * 4));
+    d_steps = reinterpret_cast<int*>(take(m_pad * 4));
+    d_src = reinterpret_cast<int*>(take(m_pad * 4));
+    d_base = reinterpret_cast<uint32_t*>(take(m_pad * 4));
+    d_gid = reinterpret_cast<int64_t*>(take(m_pad * 8));
+  }
   CKP(cudaMemcpyAsync(d_scale, h_scale.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
   CKP(cudaMemcpyAsync(d_cell, h_cell.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
   CKP(cudaMemcpyAsync(d_steps, h_steps.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -743,7 +785,7 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma);
   scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ stream, p.rk);
   p.noise = d_noise; p.noise_steps = max_iter;
-  CKP(cudaFuncSetAttribute(D::dense_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM_BYTES));
+  if ((rc = dense_set_attrs(ctx))) { cleanup(); return rc; }
   D::gather_rows_kernel<<<static_cast<unsigned>(m_pad), 256, 0, ctx->stream>>>(
       static_cast<const float*>(ctx->d_state), ld, d_cell, k, x[0], xlo[0], ld);
   CKP(cudaGetLastError());
@@ -752,7 +794,6 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   std::vector<int> iters(k, 0);
   std::vector<char> done(k, 0);
   std::vector<float> h_diff(diff_per_step * chunk);
-  const int grid = std::min(m_tiles * n_tiles, ctx->sm_count);
   int ndone = 0;
   for (int s0 = 0; s0 < max_iter && ndone < k; s0 += chunk) {
     const int cnt = std::min(chunk, max_iter - s0);
@@ -760,8 +801,7 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
       const int s = s0 + j, cur = s & 1;
       p.x_cur = x[cur]; p.x_next = x[cur ^ 1]; p.xlo_next = xlo[cur ^ 1]; p.s = s;
       p.rowdiff = d_diff + diff_per_step * j;
-      D::dense_step_kernel<<<grid, D::NUM_THREADS, D::SMEM_BYTES, ctx->stream>>>(tm_a[cur], tm_alo[cur], ctx->tm_bhi, ctx->tm_blo, p);
-      ctx->launches++;
+      dense_launch(ctx, narrow, m_tiles, tm_a[cur], tm_alo[cur], p);
     }
     CKP(cudaGetLastError());
     CKP(cudaMemcpyAsync(h_diff.data(), d_diff, diff_per_step * cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -934,7 +974,7 @@ void scr_destroy(scr_ctx* ctx) {
     free_network(ctx);
     free_dense_work(ctx);
     cudaFree(ctx->d_state); cudaFree(ctx->d_items); cudaFreeHost(ctx->h_items); cudaFree(ctx->d_counter); cudaFree(ctx->d_err); cudaFree(ctx->d_stage);
-    cudaFree(ctx->d_piters); cudaFree(ctx->d_pnd); cudaFree(ctx->d_gscratch);
+    cudaFree(ctx->d_piters); cudaFree(ctx->d_pnd); cudaFree(ctx->d_gscratch); cudaFree(ctx->d_parena);
     free_counts_scratch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1023,6 +1063,8 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
       CK(cudaMemcpy(ctx->d_wlo, wlo.data(), cnt * 4, cudaMemcpyHostToDevice));
       int rc2 = make_tmap(ctx, &ctx->tm_bhi, ctx->d_whi, ld, ld, ld, scr::dense::BN);
       if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo, ctx->d_wlo, ld, ld, ld, scr::dense::BN);
+      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_bhi_n, ctx->d_whi, ld, ld, ld, scr::dense::BN_NARROW);
+      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo_n, ctx->d_wlo, ld, ld, ld, scr::dense::BN_NARROW);
       if (rc2) return rc2;
     }
   }

@@ -26,10 +26,12 @@ class Comm:
     """Sum all-reduce over ranks.  Single process: identity.  With torch.distributed initialised
     (NCCL on GPU boxes, gloo in CPU tests) it reduces through a tensor on ``device``."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, single=False):
         self.rank, self.world = 0, 1
         self._dist = None
         self._device = device
+        if single:          # a one-process run inside a multi-rank job (the MatriSeq module's functions): no collectives
+            return
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():

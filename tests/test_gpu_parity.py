@@ -512,7 +512,7 @@ def test_partly_resident_operator_is_bit_identical(eng_mod, prec):
         elif kb == "4":
             assert lay["operator_prefix_bytes"] == 4096
         elif kb == "24":
-            assert lay["operator_prefix_bytes"] == min(24576, lay["operator_bytes"] // 128 * 128) and not lay["operator_in_smem"]
+            assert 4096 < lay["operator_prefix_bytes"] <= 24576 and not lay["operator_in_smem"]   # capped by the cap or by the room left
         elif not lay["operator_in_smem"]:   # the default policy: all that fits, or nothing when the rest would overflow L1
             assert 0 <= lay["operator_prefix_bytes"] < lay["operator_bytes"]
         outs.append(e.get_states())
