@@ -833,7 +833,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         unsigned char* dst = (pp ? oth : bufA) + static_cast<size_t>(gbase) * 16;
         RowT xo[4];
         PC pcv[4];
+#if SCR_PC_ASM
         const uint32_t pc_addr = s_rec + kFixedTab + static_cast<uint32_t>(gbase) * static_cast<uint32_t>(sizeof(PC));
+#endif
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           xo[j] = *reinterpret_cast<const RowT*>(src + j * 512);
