@@ -44,7 +44,9 @@ def readout(e):
     n = e.n
     sums = e.gene_sums()
     out = e.counts(np.zeros(n) - sums / e.cells, np.ones(e.cells), seed=5)
-    print("readout ok", int(np.asarray(out).sum()), flush=True)
+    packed, ovf = e.counts_compact(np.zeros(n) - sums / e.cells + 3.0, np.ones(e.cells), seed=5, dtype="uint8")   # some entries overflow a byte
+    ext = e.counts_ext(np.zeros(n) - sums / e.cells, np.ones(e.cells), nb_dispersion=0.5, dropout=0.2, seed=5)
+    print("readout ok", int(np.asarray(out).sum()), int(packed.sum()), len(ovf), int(ext.sum()), flush=True)
 
 
 def dense():
