@@ -291,6 +291,7 @@ counts_kernel(const T* __restrict__ state, int64_t ld, const CountGene* __restri
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     const CountGene cg = genes[t];
     const int o = cg.gene;
+    SCR_CHECK(err, o >= 0 && o < n && cg.state_idx >= 0 && cg.state_idx < ld, 108);
     const double x = static_cast<double>(row[cg.state_idx]);
     int cnt = -1;
     if (FAST && sf_ok) {

@@ -26,13 +26,19 @@
 namespace scr {
 namespace dense {
 
-constexpr int BM = 128, BN = 256, BK = 32;   // BN: the wide output tile, also the padding unit of n
+// K extent of one pipeline stage in floats: 32 (one 128-byte swizzle atom per row) or 16 (64-byte atoms: the same bytes in
+// flight cut into twice as many stages, so the TMA producer runs further ahead of the MMA issuer)
+#ifndef SCR_DENSE_BK
+#define SCR_DENSE_BK 32
+#endif
+constexpr int BM = 128, BN = 256, BK = SCR_DENSE_BK;   // BN: the wide output tile, also the padding unit of n
+static_assert(BK == 32 || BK == 16, "BK must be one 128-byte or one 64-byte swizzle atom");
 constexpr int NUM_THREADS = 192;
 // Tile shapes.  Wide (128 x 256 outputs, 2-stage 96 KB ring): large cell batches, the tensor pipe is the bound (config c4).
 // Narrow (128 x 64 outputs, 4-stage 48 KB ring): small batches -- with 1 000 cells and n = 500 (config c1) the wide shape makes
 // only 16 tiles for 148 SMs; the narrow one makes 64, each a quarter of the work, so a timestep's launch is ~3x shorter.
 template <int BN_> struct Tile {
-  static constexpr int BN = BN_, STAGES = BN_ >= 256 ? 2 : 4;
+  static constexpr int BN = BN_, STAGES = (BN_ >= 256 ? 2 : 4) * (32 / BK);
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN_ * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN_;                      // two accumulators (power of two >= 32)
@@ -79,14 +85,15 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity)
       "bra LAB_WAIT;\n\t"
       "LAB_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
-// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart
+// K-major operand tile, rows of BK floats = one swizzle atom (128 B or 64 B), 8-row groups 8 * row bytes apart
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  constexpr uint64_t kRowBytes = BK * 4, kLayout = BK == 32 ? 2 : 4;   // SWIZZLE_128B = 2, SWIZZLE_64B = 4
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);   // start address
   d |= static_cast<uint64_t>(1) << 16;                       // leading byte offset (unused for swizzled K-major)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // stride byte offset between 8-row groups
+  d |= static_cast<uint64_t>((8 * kRowBytes) >> 4) << 32;    // stride byte offset between 8-row groups
   d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
+  d |= kLayout << 61;
   return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {

@@ -240,7 +240,8 @@ int make_tmap(scr_ctx* ctx, CUtensorMap* tm, const float* ptr, int64_t rows, int
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(scr::dense::BK), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, scr::dense::BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ctx, SCR_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ")");
   return SCR_OK;
@@ -336,12 +337,25 @@ int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
     p.gscratch = ctx->d_gscratch;
   }
   CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+#if SCR_DEBUG_CHECKS
+  CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+  p.dbg = ctx->d_err;
+  p.ncells = ctx->cells;
+  if (p.nrows == 0) p.nrows = 0x7fffffffffffLL;
+#endif
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   kern<<<grid, threads, smem, ctx->stream>>>(p);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->launches++;
   CK(cudaStreamSynchronize(ctx->stream));
+#if SCR_DEBUG_CHECKS
+  {
+    int code = 0;
+    CK(cudaMemcpy(&code, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (code) return fail(ctx, SCR_E_CUDA, "stepper bounds check " + std::to_string(code) + " failed (SCR_DEBUG_CHECKS build)");
+  }
+#endif
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_ms = ms;
@@ -540,6 +554,7 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
   if (rc) return rc;
   p.items = ctx->d_items;
   p.nitems = static_cast<int>(nitems);
+  p.nrows = m;
   p.dt = static_cast<T>(dt);
   p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma * scr::Traits<T>::kDriveScale * scr::Traits<T>::kDriveScale);   // radius of K sigma xi
   scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(SCR_STREAM_STEP), p.rk);
@@ -868,6 +883,7 @@ int probe_t(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_
   if (rc) return rc;
   p.items = ctx->d_items;
   p.nitems = nitems;
+  p.nrows = k;
   p.dt = static_cast<T>(dt);
   p.rscale = static_cast<float>(-2.0 * 0.6931471805599453 * sigma * sigma * scr::Traits<T>::kDriveScale * scr::Traits<T>::kDriveScale);   // radius of K sigma xi
   scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ stream, p.rk);
@@ -1440,6 +1456,7 @@ int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const doub
   }
 #undef CKC
   cleanup();
+  if (herr >= 100) return fail(ctx, SCR_E_CUDA, "count kernel bounds check " + std::to_string(herr) + " failed (SCR_DEBUG_CHECKS build)");
   if (herr) return fail(ctx, SCR_E_DRAWS, "supplied uniforms exhausted (raise draws_per_entry)");
   if (novf > dev_ovf_cap) return fail(ctx, SCR_E_RESOURCE, "overflow list too small: " + std::to_string(novf) + " counts reach the escape code (call again with that capacity)");
   return rc;

@@ -31,6 +31,18 @@
 
 namespace scr {
 
+// Bounds-checked builds (-DSCR_DEBUG_CHECKS=1; compute-sanitizer is closed on the GPU pool, profiles/r2_sanitizer.txt): every
+// index the kernels form from tables or items is range-checked on the device; a violation records its code in the context's
+// debug word and the ABI call returns SCR_E_CUDA.  Off by default: the checks cost instructions in the block loop.
+#ifndef SCR_DEBUG_CHECKS
+#define SCR_DEBUG_CHECKS 0
+#endif
+#if SCR_DEBUG_CHECKS
+#define SCR_CHECK(word, cond, code) do { if (!(cond)) atomicMax((word), (code)); } while (0)
+#else
+#define SCR_CHECK(word, cond, code) ((void)0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // small PTX wrappers
 // ------------------------------------------------------------------------------------------
@@ -420,6 +432,8 @@ template <typename T> struct StepParams {
   int64_t noise_steps;
   const int* perm;            // internal -> original gene (or -1)
   unsigned char* gscratch;    // kModeGlobal: per (CTA, group) state buffers, (n_pad + npp + nv_pad) * 16 bytes each
+  int* dbg;                   // SCR_DEBUG_CHECKS builds: code of the first failed bounds check (0 = none)
+  int64_t ncells, nrows;      // ... what the indices are checked against: cells of the context, rows of the caller's list
   // probe
   double thresh;
   int max_iter, avg_num;
@@ -646,6 +660,11 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
     const int item_idx = ctrl[0];
     if (item_idx >= p.nitems) break;
     const Item it = p.items[item_idx];
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) {
+      SCR_CHECK(p.dbg, it.cell[c] >= -1 && it.cell[c] < p.ncells, 1);
+      SCR_CHECK(p.dbg, it.cell[c] < 0 || (it.row[c] >= 0 && it.row[c] < p.nrows), 2);
+    }
 
     // per-cell Philox round-0 invariants (published by the barrier that ends the state load below)
 #pragma unroll
@@ -736,6 +755,8 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) e[k] = wchunk[k * p.nv_pad + v];
 #pragma unroll
+            for (int k = 0; k < 8; ++k) SCR_CHECK(p.dbg, e[k].off >= 0 && e[k].off < p.npp * 16 && (e[k].off & 15) == 0, 3);
+#pragma unroll
             for (int k = 0; k < 8; ++k) xv[k] = *reinterpret_cast<const RowT*>(cur + e[k].off);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -745,6 +766,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
           } else {
             for (int k = 0; k < p.lv; ++k) {
               const WEnt e = wchunk[k * p.nv_pad + v];
+              SCR_CHECK(p.dbg, e.off >= 0 && e.off < p.npp * 16 && (e.off & 15) == 0, 3);
               const RowT xv = *reinterpret_cast<const RowT*>(cur + e.off);
 #pragma unroll
               for (int c = 0; c < CPG; ++c) acc[c] = fma(e.v, xv.v[c], acc[c]);
@@ -782,6 +804,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
         const int4 rec = lds_i4(s_rec + bi * 16);   // {first gene | flags, slots, pointer to the first entry}
         const int bflags = rec.x & kBlkFlagMask;
         const int gbase = (rec.x & ~kBlkFlagMask) | lane;   // first gene is a multiple of 128: one LOP3
+        SCR_CHECK(p.dbg, gbase >= 0 && gbase + 96 < p.n_pad && rec.y >= 0 && rec.y <= 128 * 4096, 4);
         T acc[4][CPG];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -795,6 +818,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const WEnt e = wt[j * 32];
+              SCR_CHECK(p.dbg, e.off >= 0 && e.off < p.npp * 16 && (e.off & 15) == 0, 5);
               const RowT xv = *reinterpret_cast<const RowT*>(cur + e.off);
 #pragma unroll
               for (int c = 0; c < CPG; ++c) acc[j][c] = fma(e.v, xv.v[c], acc[j][c]);
@@ -817,6 +841,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int2 oi = ovfidx[gbase + j * 32];
+            SCR_CHECK(p.dbg, oi.x >= 0 && oi.y >= 0 && oi.x + oi.y <= p.nv_pad, 6);
             for (int e = oi.x; e < oi.x + oi.y; ++e) {
               const RowT pv = ovf[e];
 #pragma unroll
@@ -936,6 +961,8 @@ __global__ void __launch_bounds__(512, 1) step_kernel(const StepParams<T> p) {
               float rr[4] = {0.f, 0.f, 0.f, 0.f}, uu[4] = {0.f, 0.f, 0.f, 0.f};
               if (SUPPLIED) {
                 const int64_t nbase = (static_cast<int64_t>(it.row[c]) * p.noise_steps + s) * p.n;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) SCR_CHECK(p.dbg, og[j] < p.n && s < p.noise_steps, 7);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) nz[j] = og[j] >= 0 ? p.noise[nbase + og[j]] : T(0);
               } else {
