@@ -288,17 +288,9 @@ counts_kernel(const T* __restrict__ state, int64_t ld, const CountGene* __restri
   const bool sf_ok = FAST && sf >= 0.05 && sf <= 8.0;
   const float sf_f = static_cast<float>(sf);
   const double esl = exp_scale * 1.4426950408889634;
-  // the entry's two dependent loads (table entry -> state value) are issued one iteration ahead, so their latency hides
-  // behind the sampling of the current entry (they were 15 % of the stall samples: profiles/r2_counts_kernel_ncu_summary.txt)
-  CountGene cg_next = genes[min(static_cast<int>(threadIdx.x), n - 1)];
-  T x_next = row[cg_next.state_idx];
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    const CountGene cg = cg_next;
-    const T x_raw = x_next;
-    if (t + static_cast<int>(blockDim.x) < n) {
-      cg_next = genes[t + blockDim.x];
-      x_next = row[cg_next.state_idx];
-    }
+    const CountGene cg = genes[t];
+    const T x_raw = row[cg.state_idx];
     const int o = cg.gene;
     SCR_CHECK(err, o >= 0 && o < n && cg.state_idx >= 0 && cg.state_idx < ld, 108);
     const double x = static_cast<double>(x_raw);
