@@ -14,6 +14,7 @@
 //   wblk          128-gene blocks assigned to the wq warps of a cell group (LPT on a cost model)
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <numeric>
@@ -148,6 +149,164 @@ inline void bank_optimize(BankModel& bm, std::vector<int>& order, const std::vec
   }
 }
 
+// Annealed version of the same move set (exchanges inside aligned groups of 8 positions): the pairwise descent above stops
+// in a local minimum; random exchanges accepted with probability exp(-delta / T) under a falling temperature get lower.
+// Deterministic (fixed-seed LCG): the gene order is a pure function of the network's pattern.
+inline void bank_anneal(BankModel& bm, std::vector<int>& order, const std::vector<int>& klass, int64_t proposals) {
+  const int n = bm.n;
+  if (n < 16) return;
+  uint64_t rng = 0x9E3779B97F4A7C15ull;
+  auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return static_cast<uint32_t>(rng >> 33); };
+  std::vector<int> touched;
+  std::vector<int> best_order = order;
+  int64_t cur = bm.total(), best = cur;
+  const double t0 = 0.6, t1 = 0.02;
+  for (int64_t it = 0; it < proposals; ++it) {
+    const double T = t0 * std::pow(t1 / t0, static_cast<double>(it) / static_cast<double>(proposals));
+    const int g0 = static_cast<int>(next() % static_cast<uint32_t>((n + 7) / 8)) * 8;
+    const int a = g0 + static_cast<int>(next() & 7), b = g0 + static_cast<int>(next() & 7);
+    if (a == b || a >= n || b >= n) continue;
+    const int ga = order[a], gb = order[b];
+    if (klass[ga] != klass[gb] || klass[ga] == 0) continue;
+    if (bm.readers[ga].empty() && bm.readers[gb].empty()) continue;
+    touched.assign(bm.readers[ga].begin(), bm.readers[ga].end());
+    touched.insert(touched.end(), bm.readers[gb].begin(), bm.readers[gb].end());
+    std::sort(touched.begin(), touched.end());
+    touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+    int before = 0, after = 0;
+    for (int s : touched) before += bm.cost(s);
+    std::swap(bm.pos[ga], bm.pos[gb]);
+    for (int s : touched) after += bm.cost(s);
+    const int delta = after - before;
+    bool accept = delta <= 0;
+    if (!accept) accept = (next() & 0xffffff) * (1.0 / 16777216.0) < std::exp(-delta / T);
+    if (accept) {
+      std::swap(order[a], order[b]);
+      cur += delta;
+      if (cur < best) { best = cur; best_order = order; }
+    } else {
+      std::swap(bm.pos[ga], bm.pos[gb]);
+    }
+  }
+  order = best_order;
+}
+
+// Second stage (round 2, SCR_BANK_OPT2 passes, default 3): exchanges of two same-class genes anywhere inside one 128-gene block.
+// That keeps every block's row set (slot counts, class prefixes) but, unlike the exchanges inside an aligned group of 8,
+// also changes WHICH rows share a quarter warp, and lets a gene take any of the 8 bank groups.  Incremental evaluation: a
+// trial touches the two quarter warps the genes sit in, the quarter warps of the rows that read either gene, and the
+// long-row chunk sets that read them.  Long rows keep their places (their order numbers the chunks).
+struct BankSearch {
+  int n = 0, cap = 0, lv = 0, nlong = 0;
+  const int32_t* rowptr = nullptr;
+  const int32_t* col = nullptr;
+  const std::vector<int>* indeg = nullptr;
+  std::vector<int> order, pos;
+  std::vector<std::vector<int>> readers;                    // gene -> rows whose first `cap` entries read it
+  std::vector<std::pair<int, int>> chunks;                  // (row gene, first entry) in chunk order
+  std::vector<std::vector<std::pair<int, int>>> chunk_reads;   // gene -> (chunk set, k) it is read in
+
+  static int max_mult(const int* p, int cnt) {               // most distinct positions sharing a bank group
+    int best = cnt > 0 ? 1 : 0;
+    for (int i = 0; i < cnt; ++i) {
+      int m = 1;
+      for (int j = 0; j < i; ++j) if (p[j] == p[i]) { m = 0; break; }        // duplicate address: counted once
+      if (!m) continue;
+      for (int j = i + 1; j < cnt; ++j) if ((p[j] & 7) == (p[i] & 7) && p[j] != p[i]) {
+        bool dup = false;
+        for (int q = i + 1; q < j; ++q) dup |= p[q] == p[j];
+        if (!dup) ++m;
+      }
+      best = std::max(best, m);
+    }
+    return best;
+  }
+  int quarter_cost(int q) const {
+    int len = 0;
+    const int p0 = q * 8, p1 = std::min(n, p0 + 8);
+    for (int i = p0; i < p1; ++i) len = std::max(len, std::min((*indeg)[order[i]], cap));
+    int total = 0;
+    for (int k = 0; k < len; ++k) {
+      int pp[8], cnt = 0;
+      for (int i = p0; i < p1; ++i) {
+        const int r = order[i];
+        if (k < std::min((*indeg)[r], cap)) pp[cnt++] = pos[col[rowptr[r] + k]];
+      }
+      total += std::max(1, max_mult(pp, cnt));
+    }
+    return total;
+  }
+  int chunk_set_cost(int s, int k) const {
+    int pp[8], cnt = 0;
+    for (size_t v = static_cast<size_t>(s) * 8; v < static_cast<size_t>(s) * 8 + 8 && v < chunks.size(); ++v)
+      if (chunks[v].second + k < (*indeg)[chunks[v].first]) pp[cnt++] = pos[col[rowptr[chunks[v].first] + chunks[v].second + k]];
+    return std::max(1, max_mult(pp, cnt));
+  }
+  void init(const std::vector<int>& ord, int nl) {
+    order = ord;
+    nlong = nl;
+    pos.assign(n, 0);
+    for (int i = 0; i < n; ++i) pos[order[i]] = i;
+    readers.assign(n, {});
+    for (int r = 0; r < n; ++r)
+      for (int k = 0; k < std::min((*indeg)[r], cap); ++k) readers[col[rowptr[r] + k]].push_back(r);
+    for (auto& v : readers) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    chunks.clear();
+    for (int i = 0; i < nlong; ++i)
+      for (int e = cap; e < (*indeg)[order[i]]; e += lv) chunks.emplace_back(order[i], e);
+    chunk_reads.assign(n, {});
+    for (size_t v = 0; v < chunks.size(); ++v)
+      for (int k = 0; k < lv && chunks[v].second + k < (*indeg)[chunks[v].first]; ++k)
+        chunk_reads[col[rowptr[chunks[v].first] + chunks[v].second + k]].emplace_back(static_cast<int>(v / 8), k);
+    for (auto& v : chunk_reads) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+  }
+  int64_t run(const std::vector<int>& klass, int passes) {
+    int64_t gained = 0;
+    std::vector<int> qs;
+    std::vector<std::pair<int, int>> cs;
+    for (int ps = 0; ps < passes; ++ps) {
+      int64_t gain = 0;
+      for (int b0 = 0; b0 < n; b0 += 128) {
+        const int b1 = std::min(n, b0 + 128);
+        for (int pa = b0; pa < b1; ++pa)
+          for (int pb = pa + 1; pb < b1; ++pb) {
+            const int ga = order[pa], gb = order[pb];
+            if (klass[ga] != klass[gb] || klass[ga] == 0) continue;
+            if ((pa >> 3) == (pb >> 3) && readers[ga].empty() && readers[gb].empty() && chunk_reads[ga].empty() && chunk_reads[gb].empty()) continue;
+            if (readers[ga].size() + readers[gb].size() > 600) continue;      // hubs: a trial would touch most of the operator
+            qs.clear(); cs.clear();
+            qs.push_back(pa >> 3); qs.push_back(pb >> 3);
+            for (int r : readers[ga]) qs.push_back(pos[r] >> 3);
+            for (int r : readers[gb]) qs.push_back(pos[r] >> 3);
+            std::sort(qs.begin(), qs.end());
+            qs.erase(std::unique(qs.begin(), qs.end()), qs.end());
+            cs.insert(cs.end(), chunk_reads[ga].begin(), chunk_reads[ga].end());
+            cs.insert(cs.end(), chunk_reads[gb].begin(), chunk_reads[gb].end());
+            std::sort(cs.begin(), cs.end());
+            cs.erase(std::unique(cs.begin(), cs.end()), cs.end());
+            int before = 0, after = 0;
+            for (int q : qs) before += quarter_cost(q);
+            for (auto& c : cs) before += chunk_set_cost(c.first, c.second);
+            std::swap(order[pa], order[pb]);
+            pos[ga] = pb; pos[gb] = pa;
+            // the rows' own quarters may have changed: a reader that IS ga or gb now sits elsewhere, both quarters are in qs
+            for (int q : qs) after += quarter_cost(q);
+            for (auto& c : cs) after += chunk_set_cost(c.first, c.second);
+            if (after < before) {
+              gain += before - after;
+            } else {
+              std::swap(order[pa], order[pb]);
+              pos[ga] = pa; pos[gb] = pb;
+            }
+          }
+      }
+      gained += gain;
+      if (gain == 0) break;
+    }
+    return gained;
+  }
+};
+
 // identity_order: keep the caller's gene order and no row cap (dense networks: every row is long and
 // every gene is read, so sorting buys nothing and the GEMM path needs the natural order);
 // pad_to: n_pad is rounded up to a multiple of this (128 for the sparse path, 256 for the GEMM tiles)
@@ -203,6 +362,20 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
       // row's k-th entry shares with its neighbours' k-th entries is fixed: rebuild the read sets after the exchange
       bm.build(order, indeg, nlong);
       bank_optimize(bm, order, klass, bank_passes == 1 ? 6 : bank_passes);
+      const int anneal = env_int("SCR_BANK_ANNEAL", 0);
+      if (anneal > 0) {
+        bank_anneal(bm, order, klass, static_cast<int64_t>(anneal) * 1000);
+        bm.build(order, indeg, nlong);
+        bank_optimize(bm, order, klass, 6);
+      }
+      const int passes2 = env_int("SCR_BANK_OPT2", 0);
+      if (passes2 > 0) {
+        BankSearch bs;
+        bs.n = n; bs.cap = cap; bs.lv = op.lv; bs.rowptr = rowptr; bs.col = col; bs.indeg = &indeg;
+        bs.init(order, nlong);
+        bs.run(klass, passes2);
+        order = bs.order;
+      }
     }
     bm.build(order, indeg, nlong);
     op.gather_wavefronts = bm.total();
