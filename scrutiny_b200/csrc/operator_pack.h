@@ -386,13 +386,19 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
       auto it = OrderCache::get().orders.find(okey);
       if (it != OrderCache::get().orders.end() && static_cast<int>(it->second.size()) == n) { order = it->second; cached = true; }
     }
-    if (bank_passes > 0 && !cached) {
+    // the search is for the sparse biological networks (mean in-degree 1.5 - 3); denser operators (mean in-degree > 8) are
+    // left in plain order: an exchange would touch hundreds of read sets (seconds of packing), and their gather is bound by
+    // operator traffic rather than by bank conflicts
+    const bool searchable = nnz <= static_cast<int64_t>(n) * 8;
+    if (bank_passes > 0 && !cached && searchable) {
       // the rows of a quarter warp are the members of its 8-group whatever their order inside it, but WHICH slot a
       // row's k-th entry shares with its neighbours' k-th entries is fixed: rebuild the read sets after the exchange
       bm.build(order, indeg, nlong);
       bank_optimize(bm, order, klass, bank_passes == 1 ? 6 : bank_passes);
       if (anneal > 0) {
-        bank_anneal(bm, order, klass, static_cast<int64_t>(anneal) * std::max<int64_t>(nnz, 1));
+        // work per proposal ~ the read sets of two genes ~ 2 nnz / n: keep the whole search near 5 M set evaluations
+        const int64_t budget = 5000000 / std::max<int64_t>(1, 2 * nnz / std::max(n, 1));
+        bank_anneal(bm, order, klass, std::min<int64_t>(static_cast<int64_t>(anneal) * std::max<int64_t>(nnz, 1), budget));
         bm.build(order, indeg, nlong);
         bank_optimize(bm, order, klass, 6);
       }
