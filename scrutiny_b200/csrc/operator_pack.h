@@ -38,6 +38,10 @@ struct PackedOperator {
   std::vector<int> ovf_start, ovf_cnt;
   std::vector<double> rowsum;   // internal order, length n_pad
   std::vector<int> wblk_ptr, wblk;
+  // the same assignment for a group run by 16 warps (convergence probes: few groups, the SM is theirs, and a step's
+  // latency is the number of blocks a warp walks); empty when the operator has fewer than 16 blocks
+  int wq_wide = 0;
+  std::vector<int> wblk_ptr_wide, wblk_wide;
   // shared-memory wavefront model of one step's gathers (LDS.128: a quarter warp per wavefront, 8 x 16-byte bank groups;
   // rows in the same bank group at different addresses serialise), over the quarter-warp reads that have at least one
   // real entry: modelled count and its conflict-free floor
@@ -529,30 +533,36 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
   std::vector<int> by_cost(op.nb);
   std::iota(by_cost.begin(), by_cost.end(), 0);
   std::stable_sort(by_cost.begin(), by_cost.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-  std::vector<double> load(wq, 0.0);
-  // warps 0 .. nv_pad/32-1 evaluate the long-row chunks at the start of every step (step_kernel.cuh phase A):
-  // charge them for it so that LPT hands them lighter blocks
-  {
+  // LPT of the blocks onto `warps` warps -> (list bounds, blocks in list order)
+  auto assign = [&](int warps, std::vector<int>& ptr, std::vector<int>& blk) {
+    std::vector<double> load(warps, 0.0);
+    // warps 0 .. nv_pad/32-1 evaluate the long-row chunks at the start of every step (step_kernel.cuh phase A):
+    // charge them for it so that LPT hands them lighter blocks
     const double chunk_cost = env_int("SCR_CHUNK_COST", 60);
-    for (int v0 = 0; v0 < op.nv_pad; v0 += 32) load[(v0 / 32) % wq] += chunk_cost;
-  }
-  std::vector<std::vector<int>> lists(wq);
-  for (int b : by_cost) {
-    int w = 0;
-    for (int k = 1; k < wq; ++k)
-      if (load[k] < load[w] - 1e-9 || (std::abs(load[k] - load[w]) <= 1e-9 && lists[k].size() < lists[w].size())) w = k;
-    lists[w].push_back(b);
-    load[w] += cost[b];
-  }
-  op.wblk_ptr.assign(wq + 1, 0);
-  op.wblk.clear();
-  for (int w = 0; w < wq; ++w) {
-    // order the stepper's split barriers rely on: regulator blocks without long rows, blocks with long
-    // rows (their chunk partials arrive late), then blocks nobody reads (step_kernel.cuh)
-    auto kls = [&](int b) { return b < op.nlong_blocks ? 1 : (b < op.npp_blocks ? 0 : 2); };
-    std::sort(lists[w].begin(), lists[w].end(), [&](int a, int b) { return kls(a) != kls(b) ? kls(a) < kls(b) : a < b; });
-    for (int b : lists[w]) op.wblk.push_back(b);
-    op.wblk_ptr[w + 1] = static_cast<int>(op.wblk.size());
+    for (int v0 = 0; v0 < op.nv_pad; v0 += 32) load[(v0 / 32) % warps] += chunk_cost;
+    std::vector<std::vector<int>> lists(warps);
+    for (int b : by_cost) {
+      int w = 0;
+      for (int k = 1; k < warps; ++k)
+        if (load[k] < load[w] - 1e-9 || (std::abs(load[k] - load[w]) <= 1e-9 && lists[k].size() < lists[w].size())) w = k;
+      lists[w].push_back(b);
+      load[w] += cost[b];
+    }
+    ptr.assign(warps + 1, 0);
+    blk.clear();
+    for (int w = 0; w < warps; ++w) {
+      // order the stepper's split barriers rely on: regulator blocks without long rows, blocks with long
+      // rows (their chunk partials arrive late), then blocks nobody reads (step_kernel.cuh)
+      auto kls = [&](int b) { return b < op.nlong_blocks ? 1 : (b < op.npp_blocks ? 0 : 2); };
+      std::sort(lists[w].begin(), lists[w].end(), [&](int a, int b) { return kls(a) != kls(b) ? kls(a) < kls(b) : a < b; });
+      for (int b : lists[w]) blk.push_back(b);
+      ptr[w + 1] = static_cast<int>(blk.size());
+    }
+  };
+  assign(wq, op.wblk_ptr, op.wblk);
+  if (wq == 8 && op.nb >= 16 && env_int("SCR_PROBE_WIDE", 1)) {
+    op.wq_wide = 16;
+    assign(16, op.wblk_ptr_wide, op.wblk_wide);
   }
   return true;
 }

@@ -51,6 +51,7 @@ struct scr_ctx {
   bool has_net = false;
   PackedOperator op;
   unsigned char *d_tab = nullptr, *d_w = nullptr;
+  unsigned char* d_tab_wide = nullptr;   // the 16-warp block assignment (probe launches), same size as d_tab
   std::vector<unsigned char> h_tab;   // host copy of the table blob (scr_debug_block_records)
   int tab_bytes = 0, w_bytes = 0, off_vrow = 0;
   int *d_perm = nullptr, *d_inv = nullptr;
@@ -151,26 +152,25 @@ int fail_cuda(const scr_ctx* ctx, cudaError_t e, const char* what) {
 
 int align16(int x) { return (x + 15) & ~15; }
 
-template <typename T>
-void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std::vector<unsigned char>& w,
-                 int& off_vrow, bool large) {
-  using WEnt = typename scr::Traits<T>::WEnt;
+// table blob for one block-to-warp assignment (wq warps, list bounds wblk_ptr, blocks wblk)
+void build_tab(const PackedOperator& op, int wq, const std::vector<int>& wblk_ptr, const std::vector<int>& wblk,
+               std::vector<unsigned char>& tab, bool large) {
   // fixed part (step_kernel.cuh "Shared-memory layout"): block records in the order of the warps' lists, list bounds;
   // variable part: chunk ranges of the long rows
   const int off_wblk_ptr = scr::rec_bytes(large), off_ovfidx = scr::fixed_tab(large);
   const int total = align16(off_ovfidx + static_cast<int>(op.ovf_start.size()) * 8);
   tab.assign(total, 0);
-  for (int w = 0; w < op.wq; ++w) {
-    int reg_end = op.wblk_ptr[w];
-    while (reg_end < op.wblk_ptr[w + 1] && op.wblk[reg_end] < op.npp_blocks) ++reg_end;
-    for (int bi = op.wblk_ptr[w]; bi < op.wblk_ptr[w + 1]; ++bi) {
-      const int b = op.wblk[bi];
+  for (int w = 0; w < wq; ++w) {
+    int reg_end = wblk_ptr[w];
+    while (reg_end < wblk_ptr[w + 1] && wblk[reg_end] < op.npp_blocks) ++reg_end;
+    for (int bi = wblk_ptr[w]; bi < wblk_ptr[w + 1]; ++bi) {
+      const int b = wblk[bi];
       const bool pp = b < op.npp_blocks;
       int flags = 0;
       if (pp) flags |= scr::kBlkPP;
       if (b < op.nlong_blocks) flags |= scr::kBlkLong;
       if (bi == reg_end - 1) flags |= scr::kBlkLastReg;
-      if (bi == op.wblk_ptr[w] && pp) flags |= scr::kBlkFirstPP;
+      if (bi == wblk_ptr[w] && pp) flags |= scr::kBlkFirstPP;
       const int4 rec = make_int4(b * 128, op.slice_off[b], op.slice_off[b + 1], flags);
       std::memcpy(tab.data() + static_cast<size_t>(bi) * 16, &rec, 16);
     }
@@ -179,8 +179,14 @@ void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std:
     int2 v = make_int2(op.ovf_start[i], op.ovf_cnt[i]);
     std::memcpy(tab.data() + off_ovfidx + i * 8, &v, 8);
   }
-  std::memcpy(tab.data() + off_wblk_ptr, op.wblk_ptr.data(), (op.wq + 1) * 4);
+  std::memcpy(tab.data() + off_wblk_ptr, wblk_ptr.data(), (wq + 1) * 4);
+}
 
+template <typename T>
+void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std::vector<unsigned char>& w,
+                 int& off_vrow, bool large) {
+  using WEnt = typename scr::Traits<T>::WEnt;
+  build_tab(op, op.wq, op.wblk_ptr, op.wblk, tab, large);
   const size_t nslots = op.tile_val.size(), nch = op.chunk_val.size();
   off_vrow = align16(static_cast<int>(nslots * sizeof(WEnt)));
   const int wtotal = align16(off_vrow + static_cast<int>(nch * sizeof(WEnt)));
@@ -201,7 +207,8 @@ void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std:
 
 void free_network(scr_ctx* ctx) {
   if (ctx->host_only) return;
-  cudaFree(ctx->d_tab); cudaFree(ctx->d_w); cudaFree(ctx->d_perm); cudaFree(ctx->d_inv);
+  cudaFree(ctx->d_tab); cudaFree(ctx->d_tab_wide); cudaFree(ctx->d_w); cudaFree(ctx->d_perm); cudaFree(ctx->d_inv);
+  ctx->d_tab_wide = nullptr;
   cudaFree(ctx->d_pc); cudaFree(ctx->d_bias); cudaFree(ctx->d_whi); cudaFree(ctx->d_wlo);
   ctx->d_tab = ctx->d_w = nullptr; ctx->d_perm = ctx->d_inv = nullptr; ctx->d_pc = ctx->d_bias = nullptr;
   ctx->d_whi = ctx->d_wlo = nullptr;
@@ -305,13 +312,18 @@ template <typename T, bool PROBE, bool SUPPLIED>
 int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
   // few groups: spread them over SMs instead of stacking them in one CTA
   int q = std::min(ctx->q, std::max(1, (nitems + ctx->sm_count - 1) / ctx->sm_count));
+  if (PROBE && q == 1 && ctx->d_tab_wide) {   // few probe groups: 16 warps per group, half the blocks per warp and step
+    p.tab = ctx->d_tab_wide;
+    p.wq = 16;
+    p.wq_log2 = 4;
+  }
   const size_t per_group = ctx->gstate ? static_cast<size_t>(scr::group_hdr(PROBE)) : (PROBE ? ctx->gbytes_probe : ctx->gbytes);
   if (!ctx->gstate)   // a probe group carries a larger header: fewer of them may fit
     while (q > 1 && ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * per_group > static_cast<size_t>(ctx->smem_optin)) --q;
   p.q = q;
   p.w_prefix = w_prefix_bytes(ctx, q, PROBE);
   const size_t smem = ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + static_cast<size_t>(q) * per_group + p.w_prefix;
-  const int threads = q * ctx->op.wq * 32;
+  const int threads = q * p.wq * 32;
   auto kern = ctx->gstate ? scr::step_kernel<T, scr::kModeGlobal, PROBE, SUPPLIED>
                           : (ctx->w_smem ? scr::step_kernel<T, scr::kModeSmem, PROBE, SUPPLIED> : scr::step_kernel<T, scr::kModeL1, PROBE, SUPPLIED>);
   scr_ctx::LaunchCfg& cfg = ctx->launch_cfg[PROBE ? 1 : 0][SUPPLIED ? 1 : 0];
@@ -1055,6 +1067,12 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
     CK(cudaMalloc(&ctx->d_pc, static_cast<size_t>(o.n_pad) * 2 * ctx->esize()));
     CK(cudaMalloc(&ctx->d_bias, static_cast<size_t>(o.n_pad) * ctx->esize()));
     CK(cudaMemcpy(ctx->d_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+    if (o.wq_wide == 16) {
+      std::vector<unsigned char> tab_wide;
+      build_tab(o, 16, o.wblk_ptr_wide, o.wblk_wide, tab_wide, ctx->gstate);
+      CK(cudaMalloc(&ctx->d_tab_wide, tab_wide.size()));
+      CK(cudaMemcpy(ctx->d_tab_wide, tab_wide.data(), tab_wide.size(), cudaMemcpyHostToDevice));
+    }
     CK(cudaMemcpy(ctx->d_w, w.data(), w.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_perm, o.perm.data(), o.n_pad * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_inv, o.inv.data(), o.n * sizeof(int), cudaMemcpyHostToDevice));
