@@ -863,14 +863,21 @@ int probe_t(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_
             int32_t avg_num, uint64_t seed, uint32_t stream, const double* noise, int32_t* iters_out,
             double* normdiff_out) {
   constexpr int CPG = scr::Traits<T>::CPG;
-  const int nitems = (k + CPG - 1) / CPG;
+  // Cells per group: a probe step of a group costs what its ACTIVE cells cost, and a group has an SM to itself as long as
+  // there are no more groups than SMs -- so few samples (a node's 50) are spread one cell per group (50 SMs, a quarter of
+  // the per-step work each: 8.0 -> ms per 7 probes, profiles/r2_experiments.txt); the alpha ladder's ~1250 samples keep 4.
+  // (the divisor check below keeps the documented contract: constant within each run of CPG consecutive samples)
+  int per = CPG;
+  if (scr::env_int("SCR_PROBE_SPREAD", 1))
+    while (per > 1 && (k + per / 2 - 1) / (per / 2) <= ctx->sm_count) per /= 2;
+  const int nitems = (k + per - 1) / per;
   std::vector<Item> items(nitems);
   for (int g = 0; g < nitems; ++g) {
     Item& it = items[g];
     std::memset(&it, 0, sizeof(it));
     for (int c = 0; c < 4; ++c) {
-      const int i = g * CPG + c;
-      if (c < CPG && i < k) {
+      const int i = g * per + c;
+      if (c < per && i < k) {
         if (sample_ids[i] < 0 || sample_ids[i] >= ctx->cells) return fail(ctx, SCR_E_ARG, "sample id out of range");
         it.cell[c] = static_cast<int>(sample_ids[i]);
         it.row[c] = i;
@@ -879,12 +886,15 @@ int probe_t(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_
       }
     }
     // one divisor per group: the ladder is laid out so that a group never mixes alphas
-    const int i0 = g * CPG;
+    const int i0 = g * per;
     it.scale = w_div ? 1.0 / w_div[i0] : 1.0;
     if (w_div)
-      for (int c = 1; c < CPG && i0 + c < k; ++c)
+      for (int c = 1; c < per && i0 + c < k; ++c)
         if (w_div[i0 + c] != w_div[i0]) return fail(ctx, SCR_E_ARG, "w_div must be constant within a cell group");
   }
+  if (w_div)
+    for (int i = 0; i < k; ++i)
+      if (w_div[i] != w_div[i / CPG * CPG]) return fail(ctx, SCR_E_ARG, "w_div must be constant within a cell group");
   int rc = ensure_items(ctx, items.size());
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->d_items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, ctx->stream));
