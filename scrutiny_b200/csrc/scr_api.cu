@@ -1367,10 +1367,13 @@ int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const doub
   double *d_uni = nullptr, *d_lam = nullptr;   // parity / debug inputs only: allocated per call
   int rc = SCR_OK;
   auto cleanup = [&]() { cudaFree(d_uni); cudaFree(d_lam); };
-  // genes sorted by shift: neighbouring lanes get similar lambda (see counts_kernel)
+  // genes sorted by shift, LARGEST first: neighbouring lanes get similar lambda (see counts_kernel), and the partial last
+  // trip of a cell's thread loop (n is not a multiple of the CTA size) handles the cheapest genes instead of the rejection
+  // sampler's, so the warps of a CTA reach the barrier closer together
   std::vector<int> order(n);
   for (int i = 0; i < n; ++i) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return shift[a] < shift[b]; });
+  const bool descending = scr::env_int("SCR_COUNTS_DESCENDING", 1) != 0;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return descending ? shift[a] > shift[b] : shift[a] < shift[b]; });
   std::vector<scr::CountGene> tab(n);
   for (int t = 0; t < n; ++t) tab[t] = scr::CountGene{order[t], ctx->op.inv[order[t]], shift[order[t]]};
   if ((rc = ensure_buf(ctx, ctx->d_ctab, ctx->ctab_cap, static_cast<size_t>(n)))) return rc;
