@@ -86,6 +86,18 @@ def test_bank_aware_gene_order_is_a_valid_packing(n, seed, heavy):
     for key in ("n_pad", "pingpong_genes", "tile_slots", "chunks", "smem_bytes", "gather_wavefronts_floor"):
         assert a[key] == b[key], key
     assert b["gather_wavefronts_floor"] <= b["gather_wavefronts_model"] <= a["gather_wavefronts_model"]
+    # the annealed refinement (default) is at least as good as the pairwise descent alone, and the order is a pure
+    # function of the pattern: a second context (order cache hit) and a rescaled network (same pattern) get the same one
+    os.environ["SCR_BANK_ANNEAL"] = "0"
+    try:
+        pairwise = engine.Engine(device=-1)
+        pairwise.set_network(W)
+    finally:
+        del os.environ["SCR_BANK_ANNEAL"]
+    assert b["gather_wavefronts_model"] <= pairwise.layout()["gather_wavefronts_model"]
+    again = engine.Engine(device=-1)
+    again.set_network(W / 3.0)
+    assert np.array_equal(again.gene_order(), eng.gene_order()) and sorted(eng.gene_order()[:n]) == list(range(n))
     if n >= 1000:
         assert b["gather_wavefronts_model"] < 0.9 * a["gather_wavefronts_model"]
 
