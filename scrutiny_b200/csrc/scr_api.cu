@@ -89,6 +89,11 @@ struct scr_ctx {
   int* d_err = nullptr;
   double* d_stage = nullptr;
   size_t stage_elems = 0;
+  // transfer of (genes, cells) float64 host matrices (scr_set_states / scr_get_states): two pinned host slabs and two
+  // device slabs, so that the host-side strided copy of one chunk runs under the DMA + (un)pack kernel of the other
+  double *h_xfer[2] = {nullptr, nullptr}, *d_xfer[2] = {nullptr, nullptr};
+  size_t xfer_elems = 0;
+  cudaEvent_t ev_x[2] = {nullptr, nullptr};
   // read-out scratch, kept between scr_counts calls (cudaMalloc / cudaFree of the 256 MB staging buffers
   // synchronise the device and cost more than the kernel itself)
   double* d_csize = nullptr;
@@ -1013,6 +1018,7 @@ void scr_destroy(scr_ctx* ctx) {
     free_dense_work(ctx);
     cudaFree(ctx->d_state); cudaFree(ctx->d_items); cudaFreeHost(ctx->h_items); cudaFree(ctx->d_counter); cudaFree(ctx->d_err); cudaFree(ctx->d_stage);
     cudaFree(ctx->d_piters); cudaFree(ctx->d_pnd); cudaFree(ctx->d_gscratch); cudaFree(ctx->d_parena);
+    for (int b = 0; b < 2; ++b) { cudaFreeHost(ctx->h_xfer[b]); cudaFree(ctx->d_xfer[b]); if (ctx->ev_x[b]) cudaEventDestroy(ctx->ev_x[b]); }
     free_counts_scratch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1221,27 +1227,69 @@ int scr_alloc_cells(scr_ctx* ctx, int64_t cells, int64_t global_cell_offset) {
   return SCR_OK;
 }
 
+namespace {
+int ensure_xfer(scr_ctx* ctx, size_t elems) {
+  if (elems <= ctx->xfer_elems) return SCR_OK;
+  for (int b = 0; b < 2; ++b) {
+    cudaFreeHost(ctx->h_xfer[b]); cudaFree(ctx->d_xfer[b]);
+    ctx->h_xfer[b] = ctx->d_xfer[b] = nullptr;
+  }
+  ctx->xfer_elems = 0;
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaHostAlloc(&ctx->h_xfer[b], elems * sizeof(double), cudaHostAllocDefault));
+    CK(cudaMalloc(&ctx->d_xfer[b], elems * sizeof(double)));
+    if (!ctx->ev_x[b]) CK(cudaEventCreateWithFlags(&ctx->ev_x[b], cudaEventDisableTiming));
+  }
+  ctx->xfer_elems = elems;
+  return SCR_OK;
+}
+// rows [g0, g1) of a chunk: user matrix (row stride ld) <-> contiguous slab [n][cnt]
+void copy_rows(bool to_slab, double* slab, double* user, int64_t ld, int64_t cnt, int n) {
+  const int nthr = (static_cast<int64_t>(n) * cnt >= (1 << 20)) ? std::max(1, std::min(scr::env_int("SCR_HOST_THREADS", 4), 16)) : 1;
+  auto work = [&](int t) {
+    const int g0 = static_cast<int>(static_cast<int64_t>(n) * t / nthr), g1 = static_cast<int>(static_cast<int64_t>(n) * (t + 1) / nthr);
+    for (int g = g0; g < g1; ++g) {
+      if (to_slab) std::memcpy(slab + static_cast<int64_t>(g) * cnt, user + static_cast<int64_t>(g) * ld, cnt * sizeof(double));
+      else std::memcpy(user + static_cast<int64_t>(g) * ld, slab + static_cast<int64_t>(g) * cnt, cnt * sizeof(double));
+    }
+  };
+  std::vector<std::thread> th;
+  int started = 1;
+  try {
+    for (int t = 1; t < nthr; ++t) { th.emplace_back(work, t); ++started; }
+  } catch (...) {}
+  work(0);
+  for (int t = started; t < nthr; ++t) work(t);
+  for (auto& x : th) x.join();
+}
+}  // namespace
+
 int scr_set_states(scr_ctx* ctx, int64_t cell0, int64_t count, const double* S, int64_t ld) {
   NEED_GPU();
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (cell0 < 0 || count < 0 || cell0 + count > ctx->cells || !S || ld < count) return fail(ctx, SCR_E_ARG, "bad range");
+  if (count == 0) return SCR_OK;
   const int n = ctx->op.n, n_pad = ctx->op.n_pad;
-  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(count, (64LL << 20) / n));
-  int rc = ensure_stage(ctx, static_cast<size_t>(chunk) * n);
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(count, (16LL << 20) / n));   // 128 MB slabs
+  int rc = ensure_xfer(ctx, static_cast<size_t>(chunk) * n);
   if (rc) return rc;
-  for (int64_t c0 = 0; c0 < count; c0 += chunk) {
+  int64_t ci = 0;
+  for (int64_t c0 = 0; c0 < count; c0 += chunk, ++ci) {
+    const int b = static_cast<int>(ci & 1);
     const int64_t cnt = std::min(chunk, count - c0);
-    CK(cudaMemcpy2DAsync(ctx->d_stage, cnt * sizeof(double), S + c0, ld * sizeof(double), cnt * sizeof(double), n,
-                         cudaMemcpyHostToDevice, ctx->stream));
+    if (ci >= 2) CK(cudaEventSynchronize(ctx->ev_x[b]));      // the slab's previous chunk has been packed
+    copy_rows(true, ctx->h_xfer[b], const_cast<double*>(S) + c0, ld, cnt, n);
+    CK(cudaMemcpyAsync(ctx->d_xfer[b], ctx->h_xfer[b], static_cast<size_t>(cnt) * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid((n_pad + 127) / 128, static_cast<unsigned>(std::min<int64_t>(cnt, 4096)));
     if (ctx->prec == SCR_F64)
-      scr::pack_states_kernel<double><<<grid, 128, 0, ctx->stream>>>(ctx->d_stage, cnt, static_cast<double*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
+      scr::pack_states_kernel<double><<<grid, 128, 0, ctx->stream>>>(ctx->d_xfer[b], cnt, static_cast<double*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
     else
-      scr::pack_states_kernel<float><<<grid, 128, 0, ctx->stream>>>(ctx->d_stage, cnt, static_cast<float*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
+      scr::pack_states_kernel<float><<<grid, 128, 0, ctx->stream>>>(ctx->d_xfer[b], cnt, static_cast<float*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
     CK(cudaGetLastError());
     ctx->launches++;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev_x[b], ctx->stream));
   }
+  CK(cudaStreamSynchronize(ctx->stream));
   return SCR_OK;
 }
 
@@ -1268,23 +1316,33 @@ int scr_get_states(scr_ctx* ctx, int64_t cell0, int64_t count, double* S, int64_
   NEED_GPU();
   if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
   if (cell0 < 0 || count < 0 || cell0 + count > ctx->cells || !S || ld < count) return fail(ctx, SCR_E_ARG, "bad range");
+  if (count == 0) return SCR_OK;
   const int n = ctx->op.n, n_pad = ctx->op.n_pad;
-  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(count, (64LL << 20) / n));
-  int rc = ensure_stage(ctx, static_cast<size_t>(chunk) * n);
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(count, (16LL << 20) / n));
+  int rc = ensure_xfer(ctx, static_cast<size_t>(chunk) * n);
   if (rc) return rc;
-  for (int64_t c0 = 0; c0 < count; c0 += chunk) {
+  int64_t ci = 0, prev_c0 = 0, prev_cnt = 0;
+  for (int64_t c0 = 0; c0 < count; c0 += chunk, ++ci) {
+    const int b = static_cast<int>(ci & 1);
     const int64_t cnt = std::min(chunk, count - c0);
     dim3 grid((n_pad + 127) / 128, static_cast<unsigned>(std::min<int64_t>(cnt, 4096)));
     if (ctx->prec == SCR_F64)
-      scr::unpack_states_kernel<double><<<grid, 128, 0, ctx->stream>>>(ctx->d_stage, cnt, static_cast<const double*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
+      scr::unpack_states_kernel<double><<<grid, 128, 0, ctx->stream>>>(ctx->d_xfer[b], cnt, static_cast<const double*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
     else
-      scr::unpack_states_kernel<float><<<grid, 128, 0, ctx->stream>>>(ctx->d_stage, cnt, static_cast<const float*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
+      scr::unpack_states_kernel<float><<<grid, 128, 0, ctx->stream>>>(ctx->d_xfer[b], cnt, static_cast<const float*>(ctx->d_state), n_pad, cell0 + c0, ctx->d_perm, n_pad);
     CK(cudaGetLastError());
     ctx->launches++;
-    CK(cudaMemcpy2DAsync(S + c0, ld * sizeof(double), ctx->d_stage, cnt * sizeof(double), cnt * sizeof(double), n,
-                         cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_xfer[b], ctx->d_xfer[b], static_cast<size_t>(cnt) * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_x[b], ctx->stream));
+    if (ci >= 1) {   // the previous chunk has arrived in the other slab: scatter it while this one is in flight
+      CK(cudaEventSynchronize(ctx->ev_x[b ^ 1]));
+      copy_rows(false, ctx->h_xfer[b ^ 1], S + prev_c0, ld, prev_cnt, n);
+    }
+    prev_c0 = c0;
+    prev_cnt = cnt;
   }
+  CK(cudaStreamSynchronize(ctx->stream));
+  copy_rows(false, ctx->h_xfer[(ci - 1) & 1], S + prev_c0, ld, prev_cnt, n);
   return SCR_OK;
 }
 
