@@ -343,10 +343,18 @@ def transformData(n, cells, finalCellStates, dropoutProportion=0.0, cellRadiusDi
     array); None (default) -> dense up to ``artefacts.DENSE_LIMIT`` bytes (2 GiB), compact above.
     ``capture`` (extension, parity aid): a dict that receives the Poisson rate matrix ``lambda`` (n, cells) and the
     per-gene ``shift`` the read-out used."""
-    eng = Engine(__device, precision or __precision)
+    key = ("readout", __device, precision or __precision)
+    slot = _engine_cache.get(key)
+    if slot is None or slot[0] != n:                                             # the read-out needs no network: a context
+        if slot is not None:                                                     # of its own, kept like the stepping one
+            slot[1].close()
+        eng = Engine(__device, key[2])
+        eng.set_genes(n)
+        _engine_cache[key] = slot = [n, eng]
+    eng = slot[1]
     try:
-        eng.set_genes(n)                                                         # the read-out needs no network
-        eng.alloc_cells(cells)
+        if eng.cells != cells:
+            eng.alloc_cells(cells)
         eng.set_states(finalCellStates)
         sim = LineageSimulation(eng, cells, comm=Comm(single=True), seed=_next_seed())
         ext = dict(nb_dispersion=float(nbDispersion), dropout=float(dropoutProportion) if applyDropout else 0.0)
@@ -355,8 +363,10 @@ def transformData(n, cells, finalCellStates, dropoutProportion=0.0, cellRadiusDi
         counts, size = sim.counts(cellRadiusDisp=cellRadiusDisp, expScale=expScale, shape=shape, rate=rate,
                                   geneScale=geneScale, expLambda=expLambda, gammaDistMean=gammaDistMean, capture=capture,
                                   dtype="int32" if dense else "uint8", **ext)
-    finally:
+    except Exception:
+        _engine_cache.pop(key, None)
         eng.close()
+        raise
     if dense:
         return np.ascontiguousarray(counts.T, dtype=np.float64), size
     return _artefacts.CountMatrix([counts[0]], [counts[1]], n), size
