@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -64,17 +65,23 @@ struct scr_ctx {
   size_t gscratch_cap = 0;
   size_t gbytes = 0, fixed_bytes = 0;
 
-  // dense (tcgen05 3xTF32) path
+  // dense (tcgen05 split-precision GEMM) path
   bool dense_mode = false;
-  float *d_whi = nullptr, *d_wlo = nullptr;      // [n_pad][n_pad] hi / lo splits of W
-  CUtensorMap tm_bhi, tm_blo;                  // B operands, boxes of the wide tile (256 genes x 32)
-  CUtensorMap tm_bhi_n, tm_blo_n;              // ... of the narrow tile (64 genes x 32)
+  int dense_kind = scr::dense::kF16;           // operand encoding (dense_kernel.cuh): fp16 split (default) or 3xTF32
+  float dense_acc_scale = 1.f;                 // 1 / (sx sw) of the fp16 encoding
+  void *d_whi = nullptr, *d_wlo = nullptr;     // [n_pad][n_pad] hi / lo splits of W (fp16 or fp32)
+  CUtensorMap tm_bhi, tm_blo;                  // B operands, boxes of the wide tile (256 genes x 128 bytes)
+  CUtensorMap tm_bhi_n, tm_blo_n;              // ... of the narrow tile (64 genes x 128 bytes)
   bool dense_attr_set = false;
-  float *d_x[2] = {nullptr, nullptr}, *d_xlo[2] = {nullptr, nullptr};   // working set [rows_cap][n_pad]
+  // working set [rows_cap][n_pad], ping-pong: state (fp32) and its operand split (hi only in the fp16 encoding)
+  float* d_x[2] = {nullptr, nullptr};
+  void *d_xhi[2] = {nullptr, nullptr}, *d_xlo[2] = {nullptr, nullptr};
   int64_t rows_cap = 0;
   int *d_row_cell = nullptr, *d_row_steps = nullptr, *d_row_src = nullptr, *d_tile_steps = nullptr;
   uint32_t* d_row_base = nullptr;
   int64_t* d_row_gid = nullptr;
+  unsigned* d_mt_count = nullptr;              // steps-inside schedule: arrival counters per cell tile
+  size_t mt_count_cap = 0;
   int64_t dense_launches = 0, sparse_launches = 0;
 
   // cells
@@ -220,7 +227,10 @@ void free_network(scr_ctx* ctx) {
 }
 
 void free_dense_work(scr_ctx* ctx) {
-  for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_x[i]); cudaFree(ctx->d_xlo[i]); ctx->d_x[i] = ctx->d_xlo[i] = nullptr; }
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(ctx->d_x[i]); cudaFree(ctx->d_xhi[i]); cudaFree(ctx->d_xlo[i]);
+    ctx->d_x[i] = nullptr; ctx->d_xhi[i] = ctx->d_xlo[i] = nullptr;
+  }
   cudaFree(ctx->d_row_cell); cudaFree(ctx->d_row_steps); cudaFree(ctx->d_row_src); cudaFree(ctx->d_tile_steps);
   cudaFree(ctx->d_row_base); cudaFree(ctx->d_row_gid);
   ctx->d_row_cell = ctx->d_row_steps = ctx->d_row_src = ctx->d_tile_steps = nullptr;
@@ -243,18 +253,18 @@ EncodeTiledFn encode_tiled_fn() {
   }
   return fn;
 }
-// fp32 matrix [rows][cols], row pitch ld elements, boxes of box_rows x 32 columns, 128-byte swizzle
-int make_tmap(scr_ctx* ctx, CUtensorMap* tm, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// matrix [rows][cols] of fp32 (esize 4) or fp16 (esize 2) elements, row pitch ld elements, boxes of box_rows x 128 bytes,
+// 128-byte swizzle
+int make_tmap(scr_ctx* ctx, CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int esize) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(ctx, SCR_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(scr::dense::BK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esize};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(scr::dense::ROW_BYTES / esize), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, scr::dense::BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = fn(tm, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ctx, SCR_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ")");
   return SCR_OK;
 }
@@ -588,35 +598,119 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
 }
 
 
-// ---- dense path: one tcgen05 GEMM launch per timestep over the phase's working set ----
-// Tile shape per launch: the narrow tile (128 x 64) when the wide one (128 x 256) would leave more than half of the SMs
-// without a tile (small cell batches: config c1, every probe), the wide one otherwise.
-bool dense_use_narrow(const scr_ctx* ctx, int m_tiles, int ld) {
-  const int force = scr::env_int("SCR_DENSE_NARROW", -1);
-  if (force >= 0) return force != 0;
-  return m_tiles * (ld / scr::dense::BN) * 2 <= ctx->sm_count;
+// ---- dense path: tcgen05 GEMM stepper over the phase's working set (dense_kernel.cuh) ----
+// Schedule per launch: when every (cell tile, gene tile) pair can have its own CTA the launch runs all remaining steps
+// ("steps inside": small batches -- config c1, every probe -- take one launch per phase instead of one per timestep; narrow
+// 128 x 64 tiles if those fit the SM count, else wide 128 x 256 ones); otherwise one launch per timestep of wide tiles.
+struct DenseSchedule { bool narrow, inside; };
+DenseSchedule dense_schedule(const scr_ctx* ctx, int m_tiles, int ld) {
+  namespace D = scr::dense;
+  const int force_narrow = scr::env_int("SCR_DENSE_NARROW", -1), force_inside = scr::env_int("SCR_DENSE_INSIDE", -1);
+  const int t_narrow = m_tiles * (ld / D::BN_NARROW), t_wide = m_tiles * (ld / D::BN);
+  DenseSchedule sc;
+  sc.narrow = force_narrow >= 0 ? force_narrow != 0 : t_narrow <= ctx->sm_count;
+  sc.inside = (sc.narrow ? t_narrow : t_wide) <= ctx->sm_count && force_inside != 0;
+  return sc;
+}
+// the working set of one phase / probe: state and operand split, ping-pong, with the A-operand tensor maps
+struct DenseWork {
+  float* x[2];
+  void *hi[2], *lo[2];
+  CUtensorMap tm_hi[2], tm_lo[2];
+};
+int dense_make_maps(scr_ctx* ctx, DenseWork& w, int64_t m_pad, int ld) {
+  namespace D = scr::dense;
+  const bool f16 = ctx->dense_kind == D::kF16;
+  for (int i = 0; i < 2; ++i) {
+    int rc = make_tmap(ctx, &w.tm_hi[i], f16 ? w.hi[i] : static_cast<void*>(w.x[i]), m_pad, ld, ld, D::BM, f16 ? 2 : 4);
+    if (!rc) rc = make_tmap(ctx, &w.tm_lo[i], w.lo[i], m_pad, ld, ld, D::BM, f16 ? 2 : 4);
+    if (rc) return rc;
+  }
+  return SCR_OK;
+}
+size_t dense_split_bytes(const scr_ctx* ctx, int64_t m_pad, int ld) {
+  return static_cast<size_t>(m_pad) * ld * (ctx->dense_kind == scr::dense::kF16 ? 2 : 4);
 }
 int dense_set_attrs(scr_ctx* ctx) {
   namespace D = scr::dense;
   if (ctx->dense_attr_set) return SCR_OK;
-  CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN>::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN_NARROW>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN, D::kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_NARROW, D::kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN_NARROW>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN, D::kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_NARROW, D::kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN_NARROW>::SMEM_BYTES));
   ctx->dense_attr_set = true;
   return SCR_OK;
 }
-void dense_launch(scr_ctx* ctx, bool narrow, int m_tiles, const CUtensorMap& tm_a, const CUtensorMap& tm_alo, scr::dense::Params& p) {
+// one launch: steps p.s0 .. p.s0 + p.nsteps - 1 of the first m_tiles cell tiles
+int dense_launch(scr_ctx* ctx, DenseSchedule sc, int m_tiles, const DenseWork& w, scr::dense::Params& p) {
   namespace D = scr::dense;
-  if (narrow) {
-    p.n_tiles = p.ld / D::BN_NARROW;
-    const int grid = std::min(m_tiles * p.n_tiles, ctx->sm_count);
-    D::dense_step_kernel<D::BN_NARROW><<<grid, D::NUM_THREADS, D::Tile<D::BN_NARROW>::SMEM_BYTES, ctx->stream>>>(tm_a, tm_alo, ctx->tm_bhi_n, ctx->tm_blo_n, p);
+  p.m_tiles = m_tiles;
+  p.n_tiles = p.ld / (sc.narrow ? D::BN_NARROW : D::BN);
+  const int tiles = m_tiles * p.n_tiles;
+  if (sc.inside) {
+    if (tiles > ctx->sm_count) return fail(ctx, SCR_E_STATE, "steps-inside schedule needs one CTA per tile");
+    if (static_cast<size_t>(m_tiles) > ctx->mt_count_cap) {
+      cudaFree(ctx->d_mt_count);
+      ctx->d_mt_count = nullptr;
+      ctx->mt_count_cap = 0;
+      CK(cudaMalloc(&ctx->d_mt_count, static_cast<size_t>(ctx->sm_count) * sizeof(unsigned)));
+      ctx->mt_count_cap = ctx->sm_count;
+    }
+    CK(cudaMemsetAsync(ctx->d_mt_count, 0, static_cast<size_t>(m_tiles) * sizeof(unsigned), ctx->stream));
+    p.mt_count = ctx->d_mt_count;
   } else {
-    p.n_tiles = p.ld / D::BN;
-    const int grid = std::min(m_tiles * p.n_tiles, ctx->sm_count);
-    D::dense_step_kernel<D::BN><<<grid, D::NUM_THREADS, D::Tile<D::BN>::SMEM_BYTES, ctx->stream>>>(tm_a, tm_alo, ctx->tm_bhi, ctx->tm_blo, p);
+    p.mt_count = nullptr;
+    p.nsteps = 1;
   }
+  p.err = ctx->d_err;
+  p.acc_scale = ctx->dense_acc_scale;
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(std::min(tiles, ctx->sm_count)));
+  cfg.blockDim = dim3(D::NUM_THREADS);
+  cfg.dynamicSmemBytes = sc.narrow ? D::Tile<D::BN_NARROW>::SMEM_BYTES : D::Tile<D::BN>::SMEM_BYTES;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;   // co-residency of the CTAs that wait on each other
+  attr[0].val.cooperative = sc.inside ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int cur = p.s0 & 1;   // (the kernel picks the map by step parity: maps are passed in buffer order)
+  (void)cur;
+  const CUtensorMap &bhi = sc.narrow ? ctx->tm_bhi_n : ctx->tm_bhi, &blo = sc.narrow ? ctx->tm_blo_n : ctx->tm_blo;
+  cudaError_t e;
+  if (ctx->dense_kind == D::kF16) {
+    e = sc.narrow ? cudaLaunchKernelEx(&cfg, D::dense_step_kernel<D::BN_NARROW, D::kF16>, w.tm_hi[0], w.tm_hi[1], w.tm_lo[0], w.tm_lo[1], bhi, blo, p)
+                  : cudaLaunchKernelEx(&cfg, D::dense_step_kernel<D::BN, D::kF16>, w.tm_hi[0], w.tm_hi[1], w.tm_lo[0], w.tm_lo[1], bhi, blo, p);
+  } else {
+    e = sc.narrow ? cudaLaunchKernelEx(&cfg, D::dense_step_kernel<D::BN_NARROW, D::kTF32>, w.tm_hi[0], w.tm_hi[1], w.tm_lo[0], w.tm_lo[1], bhi, blo, p)
+                  : cudaLaunchKernelEx(&cfg, D::dense_step_kernel<D::BN, D::kTF32>, w.tm_hi[0], w.tm_hi[1], w.tm_lo[0], w.tm_lo[1], bhi, blo, p);
+  }
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "dense stepper launch");
+  ctx->launches++;
+  ctx->dense_launches++;
+  return SCR_OK;
+}
+void dense_gather(scr_ctx* ctx, int64_t m_pad, const int* d_cell, int live, const DenseWork& w, int ld) {
+  namespace D = scr::dense;
+  if (ctx->dense_kind == D::kF16)
+    D::gather_rows_kernel<D::kF16><<<static_cast<unsigned>(m_pad), 256, 0, ctx->stream>>>(
+        static_cast<const float*>(ctx->d_state), ld, d_cell, live, w.x[0], w.hi[0], w.lo[0], ld, ctx->d_err);
+  else
+    D::gather_rows_kernel<D::kTF32><<<static_cast<unsigned>(m_pad), 256, 0, ctx->stream>>>(
+        static_cast<const float*>(ctx->d_state), ld, d_cell, live, w.x[0], nullptr, w.lo[0], ld, ctx->d_err);
   ctx->launches++;
 }
+// the error word after a dense phase / probe has been synchronised
+int dense_check_err(scr_ctx* ctx) {
+  int code = 0;
+  CK(cudaMemcpy(&code, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (code == scr::dense::kErrDenseRange)
+    return fail(ctx, SCR_E_RESOURCE, "dense stepper: a state left the fp16 operand range (|x| >= 1023); SCR_DENSE_KIND=tf32 selects the tf32 encoding");
+  if (code) return fail(ctx, SCR_E_CUDA, "dense stepper: device error word " + std::to_string(code));
+  return SCR_OK;
+}
+
 int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t* steps, const int64_t* step_base,
                     const double* proj, const double* cnst, double dt, double sigma, double mu, uint64_t seed,
                     const double* noise, int64_t noise_steps) {
@@ -631,7 +725,7 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
   }
   if (noise && smax > noise_steps) return fail(ctx, SCR_E_ARG, "supplied noise shorter than the longest cell");
   if (smax == 0) return SCR_OK;
-  // rows sorted by step count, longest first: tile t is finished after steps[t*128] launches
+  // rows sorted by step count, longest first: tile t is finished after steps[t*128] steps
   std::vector<int64_t> bucket(static_cast<size_t>(smax) + 2, 0);
   for (int64_t i = 0; i < m; ++i) if (steps[i] > 0) bucket[smax - steps[i] + 1]++;
   for (int s = 0; s <= smax; ++s) bucket[s + 1] += bucket[s];
@@ -657,8 +751,12 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
   for (int t = 0; t < m_tiles; ++t) h_tile[t] = h_steps[static_cast<size_t>(t) * D::BM];
   if (m_pad > ctx->rows_cap) {
     free_dense_work(ctx);
-    const size_t bytes = static_cast<size_t>(m_pad) * ld * 4;
-    for (int i = 0; i < 2; ++i) { CK(cudaMalloc(&ctx->d_x[i], bytes)); CK(cudaMalloc(&ctx->d_xlo[i], bytes)); }
+    const size_t bytes = static_cast<size_t>(m_pad) * ld * 4, sbytes = dense_split_bytes(ctx, m_pad, ld);
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaMalloc(&ctx->d_x[i], bytes));
+      CK(cudaMalloc(&ctx->d_xlo[i], sbytes));
+      if (ctx->dense_kind == D::kF16) CK(cudaMalloc(&ctx->d_xhi[i], sbytes));
+    }
     CK(cudaMalloc(&ctx->d_row_cell, m_pad * 4)); CK(cudaMalloc(&ctx->d_row_steps, m_pad * 4));
     CK(cudaMalloc(&ctx->d_row_src, m_pad * 4)); CK(cudaMalloc(&ctx->d_tile_steps, (m_pad / D::BM) * 4));
     CK(cudaMalloc(&ctx->d_row_base, m_pad * 4)); CK(cudaMalloc(&ctx->d_row_gid, m_pad * 8));
@@ -676,11 +774,9 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
   int rc = upload_node<float>(ctx, proj, cnst, mu, sp, 1.0);
   if (rc) return rc;
 
-  CUtensorMap tm_a[2], tm_alo[2];
-  for (int i = 0; i < 2; ++i) {
-    if ((rc = make_tmap(ctx, &tm_a[i], ctx->d_x[i], m_pad, ld, ld, D::BM))) return rc;
-    if ((rc = make_tmap(ctx, &tm_alo[i], ctx->d_xlo[i], m_pad, ld, ld, D::BM))) return rc;
-  }
+  DenseWork w;
+  for (int i = 0; i < 2; ++i) { w.x[i] = ctx->d_x[i]; w.hi[i] = ctx->d_xhi[i]; w.lo[i] = ctx->d_xlo[i]; }
+  if ((rc = dense_make_maps(ctx, w, m_pad, ld))) return rc;
   float* d_noise = nullptr;
   struct FreeOnExit { float*& ptr; ~FreeOnExit() { cudaFree(ptr); } } free_noise{d_noise};   // every return below frees it
   if (noise) {
@@ -689,7 +785,8 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
   }
   D::Params p;
   std::memset(&p, 0, sizeof(p));
-  p.ld = ld; p.n_tiles = ld / D::BN; p.k_blocks = ld / D::BK; p.n = n; p.m_pad = static_cast<int>(m_pad);
+  for (int i = 0; i < 2; ++i) { p.x[i] = w.x[i]; p.hi[i] = w.hi[i]; p.lo[i] = w.lo[i]; }
+  p.ld = ld; p.k_blocks = ld * (ctx->dense_kind == D::kF16 ? 2 : 4) / D::ROW_BYTES; p.n = n; p.m_pad = static_cast<int>(m_pad);
   p.pc = static_cast<const float2*>(ctx->d_pc);
   p.bias = sp.bias;
   p.row_steps = ctx->d_row_steps; p.row_base = ctx->d_row_base; p.row_gid = ctx->d_row_gid; p.row_src = ctx->d_row_src;
@@ -699,21 +796,21 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
   p.noise = d_noise; p.noise_steps = noise_steps;
 
   if ((rc = dense_set_attrs(ctx))) return rc;
+  CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  D::gather_rows_kernel<<<static_cast<unsigned>(m_pad), 256, 0, ctx->stream>>>(
-      static_cast<const float*>(ctx->d_state), ld, ctx->d_row_cell, static_cast<int>(live), ctx->d_x[0], ctx->d_xlo[0], ld);
+  dense_gather(ctx, m_pad, ctx->d_row_cell, static_cast<int>(live), w, ld);
   CK(cudaGetLastError());
-  ctx->launches++;
   int active_tiles = m_tiles;
-  for (int s = 0; s < smax; ++s) {
+  int64_t launches = 0;
+  for (int s = 0; s < smax;) {
     while (active_tiles > 0 && h_tile[active_tiles - 1] <= s) --active_tiles;
-    const int cur = s & 1;
-    p.x_cur = ctx->d_x[cur]; p.x_next = ctx->d_x[cur ^ 1]; p.xlo_next = ctx->d_xlo[cur ^ 1];
-    p.m_tiles = active_tiles; p.s = s;
-    dense_launch(ctx, dense_use_narrow(ctx, active_tiles, ld), active_tiles, tm_a[cur], tm_alo[cur], p);
-    ctx->dense_launches++;
+    const DenseSchedule sc = dense_schedule(ctx, active_tiles, ld);
+    p.s0 = s;
+    p.nsteps = sc.inside ? smax - s : 1;   // (tiles leave a steps-inside launch on their own when their rows are done)
+    if ((rc = dense_launch(ctx, sc, active_tiles, w, p))) return rc;
+    ++launches;
+    s += p.nsteps;
   }
-  CK(cudaGetLastError());
   D::scatter_rows_kernel<<<static_cast<unsigned>(m_pad), 256, 0, ctx->stream>>>(
       static_cast<float*>(ctx->d_state), ld, ctx->d_row_cell, static_cast<int>(live), ctx->d_x[0], ctx->d_x[1], ctx->d_tile_steps, ld);
   CK(cudaGetLastError());
@@ -721,11 +818,12 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return fail_cuda(ctx, e, "dense stepper");
+  if ((rc = dense_check_err(ctx))) return rc;
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_ms = ms;
   ctx->total_step_ms += ms;
-  ctx->total_step_launches += smax;
+  ctx->total_step_launches += launches;
   return SCR_OK;
 }
 
@@ -744,8 +842,8 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   const int n = op.n, ld = op.n_pad;
   const int64_t m_pad = (static_cast<int64_t>(k) + D::BM - 1) / D::BM * D::BM;
   const int m_tiles = static_cast<int>(m_pad / D::BM);
-  const bool narrow = dense_use_narrow(ctx, m_tiles, ld);
-  const int n_tiles = ld / (narrow ? D::BN_NARROW : D::BN);
+  const DenseSchedule sc = dense_schedule(ctx, m_tiles, ld);
+  const int n_parts = 2 * (ld / (sc.narrow ? D::BN_NARROW : D::BN));   // column parts of a row's |x' - x| sum
   std::vector<int> h_cell(m_pad, -1), h_steps(m_pad, 0), h_src(m_pad, 0);
   std::vector<uint32_t> h_base(m_pad, 0);
   std::vector<int64_t> h_gid(m_pad, 0);
@@ -758,26 +856,33 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
     h_gid[i] = ctx->cell_offset + sample_ids[i];
     if (w_div) h_scale[i] = static_cast<float>(1.0 / w_div[i]);
   }
+  // every tile steps until the chunk loop stops: its first row carries the tile's step count
+  for (int t = 0; t < m_tiles; ++t) h_steps[static_cast<size_t>(t) * D::BM] = max_iter;
   // private working set (the phase working set of scr_run_phase is left alone)
-  float *x[2] = {nullptr, nullptr}, *xlo[2] = {nullptr, nullptr}, *d_scale = nullptr, *d_diff = nullptr, *d_noise = nullptr;
+  DenseWork w;
+  float *d_scale = nullptr, *d_diff = nullptr, *d_noise = nullptr;
   int *d_cell = nullptr, *d_steps = nullptr, *d_src = nullptr;
   uint32_t* d_base = nullptr;
   int64_t* d_gid = nullptr;
   const int chunk = 64;
-  const size_t diff_per_step = static_cast<size_t>(n_tiles) * m_pad;
+  const size_t diff_per_step = static_cast<size_t>(n_parts) * m_pad;
   auto cleanup = [&]() { cudaFree(d_noise); };   // (supplied noise only; everything else lives in the context's probe arena)
 #define CKP(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail_cuda(ctx, e__, #call); } } while (0)
   // the working set is carved out of one arena the context keeps between calls (an alpha search probes dozens of times:
   // eleven cudaMalloc / cudaFree pairs per call cost more than a probe's kernels)
-  const size_t bytes = static_cast<size_t>(m_pad) * ld * 4;
+  const size_t bytes = static_cast<size_t>(m_pad) * ld * 4, sbytes = dense_split_bytes(ctx, m_pad, ld);
   {
     auto al = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
-    const size_t need = 4 * al(bytes) + al(m_pad * 4) * 5 + al(diff_per_step * chunk * 4) + al(m_pad * 8);
+    const size_t need = 2 * al(bytes) + 4 * al(sbytes) + al(m_pad * 4) * 5 + al(diff_per_step * chunk * 4) + al(m_pad * 8);
     int rcb = ensure_buf(ctx, ctx->d_parena, ctx->parena_cap, need);
     if (rcb) return rcb;
     unsigned char* at = ctx->d_parena;
     auto take = [&](size_t v) { unsigned char* r = at; at += al(v); return r; };
-    for (int i = 0; i < 2; ++i) { x[i] = reinterpret_cast<float*>(take(bytes)); xlo[i] = reinterpret_cast<float*>(take(bytes)); }
+    for (int i = 0; i < 2; ++i) {
+      w.x[i] = reinterpret_cast<float*>(take(bytes));
+      w.hi[i] = take(sbytes);
+      w.lo[i] = take(sbytes);
+    }
     d_scale = reinterpret_cast<float*>(take(m_pad * 4));
     d_diff = reinterpret_cast<float*>(take(diff_per_step * chunk * 4));
     d_cell = reinterpret_cast<int*>(take(m_pad * 4));
@@ -796,20 +901,15 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   fill_common(ctx, sp);
   int rc = upload_node<float>(ctx, proj, cnst, mu, sp, 1.0);
   if (rc) { cleanup(); return rc; }
-  CUtensorMap tm_a[2], tm_alo[2];
-  for (int i = 0; i < 2; ++i) {
-    if ((rc = make_tmap(ctx, &tm_a[i], x[i], m_pad, ld, ld, D::BM)) || (rc = make_tmap(ctx, &tm_alo[i], xlo[i], m_pad, ld, ld, D::BM))) {
-      cleanup();
-      return rc;
-    }
-  }
+  if ((rc = dense_make_maps(ctx, w, m_pad, ld))) { cleanup(); return rc; }
   if (noise) {
     rc = upload_noise<float>(ctx, noise, static_cast<size_t>(k) * max_iter * n, &d_noise);
     if (rc) { cleanup(); return rc; }
   }
   D::Params p;
   std::memset(&p, 0, sizeof(p));
-  p.ld = ld; p.n_tiles = n_tiles; p.k_blocks = ld / D::BK; p.n = n; p.m_tiles = m_tiles; p.m_pad = static_cast<int>(m_pad);
+  for (int i = 0; i < 2; ++i) { p.x[i] = w.x[i]; p.hi[i] = w.hi[i]; p.lo[i] = w.lo[i]; }
+  p.ld = ld; p.k_blocks = ld * (ctx->dense_kind == D::kF16 ? 2 : 4) / D::ROW_BYTES; p.n = n; p.m_pad = static_cast<int>(m_pad);
   p.pc = static_cast<const float2*>(ctx->d_pc);
   p.bias = sp.bias;
   p.row_steps = d_steps; p.row_base = d_base; p.row_gid = d_gid; p.row_src = d_src; p.row_scale = d_scale;
@@ -818,10 +918,9 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   scr::make_round_keys(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ stream, p.rk);
   p.noise = d_noise; p.noise_steps = max_iter;
   if ((rc = dense_set_attrs(ctx))) { cleanup(); return rc; }
-  D::gather_rows_kernel<<<static_cast<unsigned>(m_pad), 256, 0, ctx->stream>>>(
-      static_cast<const float*>(ctx->d_state), ld, d_cell, k, x[0], xlo[0], ld);
+  CKP(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+  dense_gather(ctx, m_pad, d_cell, k, w, ld);
   CKP(cudaGetLastError());
-  ctx->launches++;
   std::vector<double> nd(static_cast<size_t>(k) * max_iter, 0.0);
   std::vector<int> iters(k, 0);
   std::vector<char> done(k, 0);
@@ -829,13 +928,15 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   int ndone = 0;
   for (int s0 = 0; s0 < max_iter && ndone < k; s0 += chunk) {
     const int cnt = std::min(chunk, max_iter - s0);
-    for (int j = 0; j < cnt; ++j) {
-      const int s = s0 + j, cur = s & 1;
-      p.x_cur = x[cur]; p.x_next = x[cur ^ 1]; p.xlo_next = xlo[cur ^ 1]; p.s = s;
-      p.rowdiff = d_diff + diff_per_step * j;
-      dense_launch(ctx, narrow, m_tiles, tm_a[cur], tm_alo[cur], p);
+    if (sc.inside) {
+      p.s0 = s0; p.nsteps = cnt; p.rowdiff = d_diff;
+      if ((rc = dense_launch(ctx, sc, m_tiles, w, p))) { cleanup(); return rc; }
+    } else {
+      for (int j = 0; j < cnt; ++j) {
+        p.s0 = s0 + j; p.nsteps = 1; p.rowdiff = d_diff + diff_per_step * j;
+        if ((rc = dense_launch(ctx, sc, m_tiles, w, p))) { cleanup(); return rc; }
+      }
     }
-    CKP(cudaGetLastError());
     CKP(cudaMemcpyAsync(h_diff.data(), d_diff, diff_per_step * cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CKP(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < k; ++i) {
@@ -844,7 +945,7 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
       for (int j = 0; j < cnt && !done[i]; ++j) {
         const int s = s0 + j;
         double tot = 0.0;
-        for (int t = 0; t < n_tiles; ++t) tot += static_cast<double>(h_diff[diff_per_step * j + static_cast<size_t>(t) * m_pad + i]);
+        for (int t = 0; t < n_parts; ++t) tot += static_cast<double>(h_diff[diff_per_step * j + static_cast<size_t>(t) * m_pad + i]);
         trace[s] = tot / (static_cast<double>(n) * static_cast<double>(static_cast<float>(dt)));
         iters[i] = s + 1;
         if (s >= avg_num - 1) {
@@ -856,9 +957,10 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
     }
   }
 #undef CKP
+  cleanup();
+  if ((rc = dense_check_err(ctx))) return rc;
   for (int i = 0; i < k; ++i) iters_out[i] = iters[i];
   if (normdiff_out) std::memcpy(normdiff_out, nd.data(), nd.size() * sizeof(double));
-  cleanup();
   return SCR_OK;
 }
 
@@ -1017,7 +1119,7 @@ void scr_destroy(scr_ctx* ctx) {
     free_network(ctx);
     free_dense_work(ctx);
     cudaFree(ctx->d_state); cudaFree(ctx->d_items); cudaFreeHost(ctx->h_items); cudaFree(ctx->d_counter); cudaFree(ctx->d_err); cudaFree(ctx->d_stage);
-    cudaFree(ctx->d_piters); cudaFree(ctx->d_pnd); cudaFree(ctx->d_gscratch); cudaFree(ctx->d_parena);
+    cudaFree(ctx->d_piters); cudaFree(ctx->d_pnd); cudaFree(ctx->d_gscratch); cudaFree(ctx->d_parena); cudaFree(ctx->d_mt_count);
     for (int b = 0; b < 2; ++b) { cudaFreeHost(ctx->h_xfer[b]); cudaFree(ctx->d_xfer[b]); if (ctx->ev_x[b]) cudaEventDestroy(ctx->ev_x[b]); }
     free_counts_scratch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1093,28 +1195,57 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
     CK(cudaMemcpy(ctx->d_perm, o.perm.data(), o.n_pad * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_inv, o.inv.data(), o.n * sizeof(int), cudaMemcpyHostToDevice));
     if (dense) {
-      // B operands of the 3xTF32 GEMM: W (the tensor core truncates it to tf32) and its residual
+      // B operands of the split-precision GEMM (dense_kernel.cuh): hi / lo of W in the chosen encoding
+      namespace D = scr::dense;
+      const char* kind_env = std::getenv("SCR_DENSE_KIND");
+      const int kind = kind_env && std::string(kind_env) == "tf32" ? D::kTF32 : D::kF16;
+      if (kind != ctx->dense_kind) free_dense_work(ctx);   // the working set's split buffers are sized per encoding
+      ctx->dense_kind = kind;
       const size_t ld = o.n_pad, cnt = ld * ld;
-      std::vector<float> whi(cnt, 0.f), wlo(cnt, 0.f);
-      for (int r = 0; r < n; ++r)
-        for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
-          const float w = static_cast<float>(val[e]);
-          uint32_t bits;
-          std::memcpy(&bits, &w, 4);
-          bits &= 0xffffe000u;
-          float hi;
-          std::memcpy(&hi, &bits, 4);
-          whi[r * ld + col[e]] = w;
-          wlo[r * ld + col[e]] = w - hi;
-        }
-      CK(cudaMalloc(&ctx->d_whi, cnt * 4));
-      CK(cudaMalloc(&ctx->d_wlo, cnt * 4));
-      CK(cudaMemcpy(ctx->d_whi, whi.data(), cnt * 4, cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(ctx->d_wlo, wlo.data(), cnt * 4, cudaMemcpyHostToDevice));
-      int rc2 = make_tmap(ctx, &ctx->tm_bhi, ctx->d_whi, ld, ld, ld, scr::dense::BN);
-      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo, ctx->d_wlo, ld, ld, ld, scr::dense::BN);
-      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_bhi_n, ctx->d_whi, ld, ld, ld, scr::dense::BN_NARROW);
-      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo_n, ctx->d_wlo, ld, ld, ld, scr::dense::BN_NARROW);
+      int rc2 = SCR_OK;
+      if (ctx->dense_kind == D::kF16) {
+        // power-of-two scale: max |W| lands in [2^14, 2^15), the products with sx x stay far inside fp32
+        double wmax = 0.0;
+        for (int64_t e = 0; e < nnz; ++e) wmax = std::max(wmax, std::fabs(val[e]));
+        const float wmaxf = static_cast<float>(wmax);
+        const double sw = wmaxf > 0.f && std::isfinite(wmaxf) ? std::ldexp(1.0, 14 - std::ilogb(wmaxf)) : 1.0;
+        ctx->dense_acc_scale = static_cast<float>(1.0 / (static_cast<double>(D::kStateScale) * sw));
+        std::vector<__half> whi(cnt, __float2half_rn(0.f)), wlo(cnt, __float2half_rn(0.f));
+        for (int r = 0; r < n; ++r)
+          for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+            const float ws = static_cast<float>(val[e]) * static_cast<float>(sw);
+            const __half h = __float2half_rn(ws);
+            whi[r * ld + col[e]] = h;
+            wlo[r * ld + col[e]] = __float2half_rn(ws - __half2float(h));
+          }
+        CK(cudaMalloc(&ctx->d_whi, cnt * 2));
+        CK(cudaMalloc(&ctx->d_wlo, cnt * 2));
+        CK(cudaMemcpy(ctx->d_whi, whi.data(), cnt * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_wlo, wlo.data(), cnt * 2, cudaMemcpyHostToDevice));
+      } else {
+        ctx->dense_acc_scale = 1.f;
+        std::vector<float> whi(cnt, 0.f), wlo(cnt, 0.f);
+        for (int r = 0; r < n; ++r)
+          for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+            const float w = static_cast<float>(val[e]);
+            uint32_t bits;
+            std::memcpy(&bits, &w, 4);
+            bits &= 0xffffe000u;
+            float hi;
+            std::memcpy(&hi, &bits, 4);
+            whi[r * ld + col[e]] = w;
+            wlo[r * ld + col[e]] = w - hi;
+          }
+        CK(cudaMalloc(&ctx->d_whi, cnt * 4));
+        CK(cudaMalloc(&ctx->d_wlo, cnt * 4));
+        CK(cudaMemcpy(ctx->d_whi, whi.data(), cnt * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_wlo, wlo.data(), cnt * 4, cudaMemcpyHostToDevice));
+      }
+      const int es = ctx->dense_kind == D::kF16 ? 2 : 4;
+      rc2 = make_tmap(ctx, &ctx->tm_bhi, ctx->d_whi, ld, ld, ld, D::BN, es);
+      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo, ctx->d_wlo, ld, ld, ld, D::BN, es);
+      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_bhi_n, ctx->d_whi, ld, ld, ld, D::BN_NARROW, es);
+      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo_n, ctx->d_wlo, ld, ld, ld, D::BN_NARROW, es);
       if (rc2) return rc2;
     }
   }

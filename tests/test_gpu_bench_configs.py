@@ -111,10 +111,20 @@ def test_bench_network_free_running_fast_path_sampled_cells(net, prec, tol):
     assert abs(z.mean()) < 5 / np.sqrt(z.size) and abs(z.std() - 1) < 5e-3
 
 
-def test_c4_dense_network_on_the_tcgen05_stepper():
+@pytest.mark.parametrize("env,launches", [
+    ({}, 1),                                                       # default: fp16 split, narrow tiles, steps inside the launch
+    ({"SCR_DENSE_NARROW": "0"}, 1),                                # wide tiles, steps inside
+    ({"SCR_DENSE_NARROW": "0", "SCR_DENSE_INSIDE": "0"}, 20),      # wide tiles, one launch per timestep (what 200 k cells run)
+    ({"SCR_DENSE_KIND": "tf32"}, 1),                               # north_star's 3xTF32 encoding
+    ({"SCR_DENSE_KIND": "tf32", "SCR_DENSE_NARROW": "0", "SCR_DENSE_INSIDE": "0"}, 20),
+])
+def test_c4_dense_network_on_the_tcgen05_stepper(env, launches, monkeypatch):
     """Config c4: Random n = 3000, networkSparsity 0.5 (nnz ~4.5 M), alpha 2.21 (what the search returns for it:
-    profiles/r1_final_configs_c1_c4.jsonl); 12 N tiles x 96 K blocks per 128-cell tile."""
+    profiles/r1_final_configs_c1_c4.jsonl); full K extent (48 / 96 K slices) and all gene tiles, on every schedule and
+    operand encoding of the dense stepper."""
     from scrutiny_b200 import engine, network
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     seed_all(1337)
     gc, tf = network.generate_gene_correlation_matrix(3000, "Random", networkSparsity=0.5)
     gc /= 2.21
@@ -131,7 +141,7 @@ def test_c4_dense_network_on_the_tcgen05_stepper():
     e.alloc_cells(cells)
     e.set_states(np.ascontiguousarray(X0.T))
     e.run_phase(np.arange(cells), steps, proj, const, noise=noise)
-    assert e.path_launches()["dense_gemm"] == steps_max
+    assert e.path_launches()["dense_gemm"] == launches
     want = X0.astype(np.float32).astype(np.float64)
     fo.run_phase(gc, want, steps, proj, const, 0.01, noise)
     err = np.max(np.abs(e.get_states().T - want))

@@ -1,6 +1,6 @@
-"""Dense networks: the tcgen05 3xTF32 GEMM stepper (float32 contexts, nnz >= 5 % of n^2) against the
-float64 oracle.  Tolerance 1e-4 absolute on states in [-1, 1]: 3xTF32 carries ~22 mantissa bits per
-operand, the test runs <= 60 steps at moderate gain."""
+"""Dense networks: the tcgen05 split-precision GEMM stepper (float32 contexts, nnz >= 5 % of n^2) against the
+float64 oracle.  Tolerance 1e-4 absolute on states in [-1, 1]: both operand encodings (fp16 split, 3xTF32) carry
+~22 significant bits per operand, the test runs <= 60 steps at moderate gain."""
 import os
 
 import numpy as np
@@ -26,8 +26,11 @@ def engine_for(W, cells, prec="f32", offset=0):
     return e
 
 
+@pytest.mark.parametrize("env", [{}, {"SCR_DENSE_INSIDE": "0"}, {"SCR_DENSE_KIND": "tf32"}], ids=["f16-inside", "f16-per-step", "tf32"])
 @pytest.mark.parametrize("n,cells,smax,density", [(500, 300, 40, 0.99), (200, 131, 25, 0.5), (700, 64, 12, 0.2)])
-def test_dense_stepper_ragged_against_oracle(n, cells, smax, density):
+def test_dense_stepper_ragged_against_oracle(n, cells, smax, density, env, monkeypatch):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     rng = np.random.RandomState(n)
     W = dense_net(n, n + 1, density, alpha=0.02 * n * density)
     X0 = rng.uniform(-1, 1, size=(cells, n))
@@ -110,3 +113,28 @@ def test_probe_works_on_dense_networks():
     want, _, _ = fo.probe(fo.as_operator(W), X.astype(np.float32).astype(np.float64), np.ones(n), np.zeros(n), 0.01,
                           noise, 0.4, 80, 6)
     assert np.max(np.abs(it - want)) <= 1
+
+
+def test_states_outside_the_fp16_operand_range_are_refused_not_saturated():
+    """The default operand encoding scales the state by 64 into fp16: |x| >= 1023 cannot be represented.  The call fails
+    (SCR_E_RESOURCE); the tf32 encoding takes the same input."""
+    from scrutiny_b200 import engine
+    n, cells = 128, 4
+    W = dense_net(n, 5, 0.5, alpha=2.0)
+    X0 = np.zeros((cells, n))
+    X0[2, 17] = 2000.0
+    e = engine_for(W, cells)
+    e.set_states(X0.T.copy())
+    with pytest.raises(engine.ScrutinyError) as ei:
+        e.run_phase(np.arange(cells), np.full(cells, 3), np.ones(n), np.zeros(n), noise=np.zeros((cells, 3, n)))
+    assert "fp16 operand range" in str(ei.value)
+    os.environ["SCR_DENSE_KIND"] = "tf32"
+    try:
+        e2 = engine_for(W, cells)
+    finally:
+        del os.environ["SCR_DENSE_KIND"]
+    e2.set_states(X0.T.copy())
+    e2.run_phase(np.arange(cells), np.full(cells, 3), np.ones(n), np.zeros(n), noise=np.zeros((cells, 3, n)))
+    want = X0.copy()
+    fo.run_phase(fo.as_operator(W), want, np.full(cells, 3), np.ones(n), np.zeros(n), 0.01, np.zeros((cells, 3, n)))
+    assert np.max(np.abs(e2.get_states().T - want)) <= 1e-3   # (values of 2000: fp32 ulp 1.2e-4)
