@@ -63,6 +63,17 @@ template <int BN_> struct Tile {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + BN_ * 8 /*pc tile*/ + 256 /*barriers*/;
 };
 constexpr int BN_NARROW = 64;
+// Resident-B tile (128 x 32 outputs, steps-inside schedule only): the CTA's slice of W -- 32 genes x all of K, hi and lo --
+// is loaded ONCE per launch and stays in shared memory; per step only the A tiles stream through a ring of `stages`
+// 32 KB slots.  Small networks (n_pad <= 1024: config c1) run their whole phase this way: a third fewer bytes per step
+// than the narrow tile, and 16 tiles per 512 genes spread the epilogue over twice as many SMs.
+constexpr int BN_RES = 32;
+constexpr int kMaxStages = 8;
+constexpr int kResBarBytes = 256, kResAlign = 1024;
+inline int res_b_bytes(int k_blocks) { return k_blocks * 2 * BN_RES * ROW_BYTES; }
+inline int res_smem_bytes(int k_blocks, int stages) {
+  return stages * 2 * BM * ROW_BYTES + res_b_bytes(k_blocks) + kResAlign + BN_RES * 8 + kResBarBytes;
+}
 
 struct Params {
   float* x[2];               // state working set [m_pad][ld], ping-pong by step parity (step s reads x[s & 1])
@@ -75,6 +86,7 @@ struct Params {
   const uint32_t* row_base;  // iterations already done (noise key)
   const int64_t* row_gid;    // global cell id (noise key)
   const int* row_src;        // index in the caller's list (supplied noise)
+  int stages;                // resident-B tile: depth of the A ring
   int s0, nsteps;            // this launch computes steps s0 .. s0 + nsteps - 1 (nsteps > 1 only with one CTA per tile)
   unsigned* mt_count;        // steps-inside schedule: arrivals per cell tile (zeroed before the launch), else nullptr
   int* err;                  // context error word
@@ -87,9 +99,27 @@ struct Params {
   const float* row_scale;    // nullptr = 1
   float* rowdiff;            // [nsteps][2 n_tiles][m_pad], or nullptr
   int m_pad;
+  unsigned long long* trace; // SCR_DENSE_TRACE builds only
 };
 constexpr int kErrDenseRange = 901, kErrDenseStall = 902;
+// developer build (-DSCR_DENSE_TRACE=1): CTA 0 stamps %globaltimer at eight points of every step of a steps-inside launch
+// into Params::trace[(s - s0) * 8 + point]; scr_api.cu dumps them to the file named by the SCR_DENSE_TRACE variable
+#ifndef SCR_DENSE_TRACE
+#define SCR_DENSE_TRACE 0
+#endif
+__device__ __forceinline__ void trace_stamp(const struct Params& p, int s, int point);
 
+__device__ __forceinline__ void trace_stamp(const Params& p, int s, int point) {
+#if SCR_DENSE_TRACE
+  if (blockIdx.x == 0 && p.trace && p.mt_count && s - p.s0 < 4096) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[(s - p.s0) * 8 + point] = t;
+  }
+#else
+  (void)p; (void)s; (void)point;
+#endif
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
@@ -156,25 +186,31 @@ __device__ __forceinline__ int step_end(const Params& p, int mt) {
   return p.nsteps > 1 ? min(p.s0 + p.nsteps, p.row_steps[mt * BM]) : p.s0 + 1;
 }
 
-template <int BN_, int KIND>
+template <int BN_, int KIND, bool RESB = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_constant__ CUtensorMap tm_ahi1,
                   const __grid_constant__ CUtensorMap tm_alo0, const __grid_constant__ CUtensorMap tm_alo1,
                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const Params p) {
   using TL = Tile<BN_>;
   using EN = Enc<KIND>;
-  constexpr int BN = TL::BN, STAGES = TL::STAGES, A_BYTES = TL::A_BYTES, B_BYTES = TL::B_BYTES, STAGE_BYTES = TL::STAGE_BYTES;
+  static_assert(!RESB || BN_ == BN_RES, "the resident-B schedule uses the 128 x 32 tile");
+  constexpr int BN = TL::BN, A_BYTES = TL::A_BYTES, B_BYTES = TL::B_BYTES;
+  constexpr int STAGE_BYTES = RESB ? 2 * A_BYTES : TL::STAGE_BYTES;   // resident B: a ring slot holds A-hi and A-lo only
   constexpr int BK = EN::BK;
+  const int STAGES = RESB ? p.stages : TL::STAGES;
   extern __shared__ unsigned char dsmem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   unsigned char* stage_mem = base;
-  float2* pc_tile = reinterpret_cast<float2*>(base + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES + BN * 8);
-  uint64_t* full = bars;                 // [STAGES]
-  uint64_t* empty = bars + STAGES;       // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty = bars + 2 * STAGES + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  unsigned char* b_res = base + STAGES * STAGE_BYTES;                  // [k_blocks][hi | lo][BN rows x 128 bytes] (RESB)
+  unsigned char* after = b_res + (RESB ? p.k_blocks * 2 * B_BYTES : 0);
+  float2* pc_tile = reinterpret_cast<float2*>(after);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after + BN * 8);
+  uint64_t* full = bars;                      // [kMaxStages]
+  uint64_t* empty = bars + kMaxStages;        // [kMaxStages]
+  uint64_t* tfull = bars + 2 * kMaxStages;    // [2]
+  uint64_t* tempty = bars + 2 * kMaxStages + 2;   // [2]
+  uint64_t* bfull = bars + 2 * kMaxStages + 4;    // resident B loaded
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = p.m_tiles * p.n_tiles;
@@ -182,6 +218,7 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * EPI_WARPS); }
+    mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM: two accumulators of BN columns (all 512 columns for the wide tile)
@@ -198,6 +235,14 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
+      if constexpr (RESB) {   // this CTA's slice of W, once
+        const int nt = blockIdx.x % p.n_tiles;
+        mbar_expect_tx(bfull, static_cast<uint32_t>(p.k_blocks) * 2 * B_BYTES);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          tma_load_2d(b_res + kb * 2 * B_BYTES, &tm_bhi, kb * BK, nt * BN, bfull);
+          tma_load_2d(b_res + kb * 2 * B_BYTES + B_BYTES, &tm_blo, kb * BK, nt * BN, bfull);
+        }
+      }
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int mt = t / p.n_tiles, nt = t % p.n_tiles;
         const int s_end = step_end(p, mt);
@@ -209,7 +254,7 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
             // W does not depend on the other CTAs: the B tiles of the first ring stages go out before the wait
             int st2 = st;
             uint32_t ph2 = ph;
-            for (; kb_b < STAGES && kb_b < p.k_blocks; ++kb_b) {
+            for (; !RESB && kb_b < STAGES && kb_b < p.k_blocks; ++kb_b) {
               mbar_wait_parity(&empty[st2], ph2 ^ 1u);
               unsigned char* sm = stage_mem + st2 * STAGE_BYTES;
               mbar_expect_tx(&full[st2], STAGE_BYTES);
@@ -227,18 +272,22 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
             }
             asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of the other CTAs -> our TMA reads
           }
+          trace_stamp(p, s, 0);
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             unsigned char* sm = stage_mem + st * STAGE_BYTES;
             if (kb >= kb_b) {
               mbar_wait_parity(&empty[st], ph ^ 1u);
               mbar_expect_tx(&full[st], STAGE_BYTES);
-              tma_load_2d(sm + 2 * A_BYTES, &tm_bhi, kb * BK, nt * BN, &full[st]);
-              tma_load_2d(sm + 2 * A_BYTES + B_BYTES, &tm_blo, kb * BK, nt * BN, &full[st]);
+              if constexpr (!RESB) {
+                tma_load_2d(sm + 2 * A_BYTES, &tm_bhi, kb * BK, nt * BN, &full[st]);
+                tma_load_2d(sm + 2 * A_BYTES + B_BYTES, &tm_blo, kb * BK, nt * BN, &full[st]);
+              }
             }
             tma_load_2d(sm, ta_hi, kb * BK, mt * BM, &full[st]);
             tma_load_2d(sm + A_BYTES, ta_lo, kb * BK, mt * BM, &full[st]);
             if (++st == STAGES) { st = 0; ph ^= 1u; }
           }
+          trace_stamp(p, s, 1);
         }
       }
     }
@@ -249,6 +298,7 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
     constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
     int st = 0, ab = 0;
     uint32_t ph = 0, aph = 0;
+    if constexpr (RESB) mbar_wait_parity(bfull, 0u);
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int s_end = step_end(p, t / p.n_tiles);
       for (int s = p.s0; s < s_end; ++s) {
@@ -258,10 +308,12 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait_parity(&full[st], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0 && kb == 0) trace_stamp(p, s, 2);
           if (lane == 0) {
             const uint32_t sa = smem_u32(stage_mem + st * STAGE_BYTES);
             const uint64_t ahi = umma_desc(sa), alo = umma_desc(sa + A_BYTES);
-            const uint64_t bhi = umma_desc(sa + 2 * A_BYTES), blo = umma_desc(sa + 2 * A_BYTES + B_BYTES);
+            const uint32_t sb = RESB ? smem_u32(b_res + kb * 2 * B_BYTES) : sa + 2 * A_BYTES;
+            const uint64_t bhi = umma_desc(sb), blo = umma_desc(sb + B_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);   // 32 bytes along K inside the swizzle atom
@@ -270,7 +322,7 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
               umma<KIND>(tmem_d, ahi + adv, bhi + adv, idesc, 1u);
             }
             umma_commit(&empty[st]);                       // frees the smem stage when these MMAs retire
-            if (kb == p.k_blocks - 1) umma_commit(&tfull[ab]);   // accumulator complete
+            if (kb == p.k_blocks - 1) { umma_commit(&tfull[ab]); trace_stamp(p, s, 3); }   // accumulator complete
           }
           __syncwarp();
           if (++st == STAGES) { st = 0; ph ^= 1u; }
@@ -304,7 +356,7 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
       // from step to step (no re-read; in the fp16 encoding the fp32 copy in global memory is only refreshed by the launch's
       // last step of the tile) and the step's noise is drawn BEFORE the accumulator is waited for -- both off the step-to-step critical path
       // of the steps-inside schedule.
-      constexpr bool kRegState = PART == 32;
+      constexpr bool kRegState = PART <= 32;
       float xr[kRegState ? PART : 1];
       if constexpr (kRegState) {
         const float* xrow0 = p.x[p.s0 & 1] + roff;
@@ -343,6 +395,7 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
 
         mbar_wait_parity(&tfull[ab], aph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (etid == 0) trace_stamp(p, s, 4);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + ab * BN + part * PART;
         const bool store_x = !kRegState || KIND == kTF32 /* x IS the A-hi operand */ || s == s_end - 1;
 #pragma unroll
@@ -440,11 +493,14 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
         if (++ab == 2) { ab = 0; aph ^= 1u; }
         if (p.mt_count) {
           // publish this CTA's columns of step s to the other CTAs of the cell tile
-          __threadfence();
+          // (the CTA barrier orders every epilogue thread's stores before thread 0's release, which is cumulative)
+          if (etid == 0) trace_stamp(p, s, 5);
           named_bar_sync(1, ETHREADS);
           if (etid == 0) {
+            trace_stamp(p, s, 6);
             asm volatile("fence.proxy.async;" ::: "memory");
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.mt_count + mt) : "memory");
+            trace_stamp(p, s, 7);
           }
         }
       }

@@ -72,6 +72,7 @@ struct scr_ctx {
   void *d_whi = nullptr, *d_wlo = nullptr;     // [n_pad][n_pad] hi / lo splits of W (fp16 or fp32)
   CUtensorMap tm_bhi, tm_blo;                  // B operands, boxes of the wide tile (256 genes x 128 bytes)
   CUtensorMap tm_bhi_n, tm_blo_n;              // ... of the narrow tile (64 genes x 128 bytes)
+  CUtensorMap tm_bhi_r, tm_blo_r;              // ... of the resident-B tile (32 genes x 128 bytes)
   bool dense_attr_set = false;
   // working set [rows_cap][n_pad], ping-pong: state (fp32) and its operand split (hi only in the fp16 encoding)
   float* d_x[2] = {nullptr, nullptr};
@@ -602,14 +603,23 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
 // Schedule per launch: when every (cell tile, gene tile) pair can have its own CTA the launch runs all remaining steps
 // ("steps inside": small batches -- config c1, every probe -- take one launch per phase instead of one per timestep; narrow
 // 128 x 64 tiles if those fit the SM count, else wide 128 x 256 ones); otherwise one launch per timestep of wide tiles.
-struct DenseSchedule { bool narrow, inside; };
+struct DenseSchedule { bool narrow, inside, resb; int stages; };
 DenseSchedule dense_schedule(const scr_ctx* ctx, int m_tiles, int ld) {
   namespace D = scr::dense;
   const int force_narrow = scr::env_int("SCR_DENSE_NARROW", -1), force_inside = scr::env_int("SCR_DENSE_INSIDE", -1);
-  const int t_narrow = m_tiles * (ld / D::BN_NARROW), t_wide = m_tiles * (ld / D::BN);
+  const int t_narrow = m_tiles * (ld / D::BN_NARROW), t_wide = m_tiles * (ld / D::BN), t_res = m_tiles * (ld / D::BN_RES);
   DenseSchedule sc;
+  sc.resb = false;
+  sc.stages = 0;
   sc.narrow = force_narrow >= 0 ? force_narrow != 0 : t_narrow <= ctx->sm_count;
   sc.inside = (sc.narrow ? t_narrow : t_wide) <= ctx->sm_count && force_inside != 0;
+  // resident-B tiles: W's slice of the CTA stays in shared memory for the whole launch (small networks)
+  if (sc.inside && force_narrow < 0 && t_res <= ctx->sm_count && scr::env_int("SCR_DENSE_RESB", 1)) {
+    const int k_blocks = ld * (ctx->dense_kind == D::kF16 ? 2 : 4) / D::ROW_BYTES;
+    int stages = D::kMaxStages;
+    while (stages >= 2 && D::res_smem_bytes(k_blocks, stages) > ctx->smem_optin) --stages;
+    if (stages >= 2) { sc.resb = true; sc.narrow = false; sc.stages = std::min(stages, k_blocks); }
+  }
   return sc;
 }
 // the working set of one phase / probe: state and operand split, ping-pong, with the A-operand tensor maps
@@ -638,6 +648,8 @@ int dense_set_attrs(scr_ctx* ctx) {
   CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_NARROW, D::kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN_NARROW>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN, D::kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_NARROW, D::kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN_NARROW>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_RES, D::kF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+  CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_RES, D::kTF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
   ctx->dense_attr_set = true;
   return SCR_OK;
 }
@@ -645,7 +657,8 @@ int dense_set_attrs(scr_ctx* ctx) {
 int dense_launch(scr_ctx* ctx, DenseSchedule sc, int m_tiles, const DenseWork& w, scr::dense::Params& p) {
   namespace D = scr::dense;
   p.m_tiles = m_tiles;
-  p.n_tiles = p.ld / (sc.narrow ? D::BN_NARROW : D::BN);
+  p.n_tiles = p.ld / (sc.resb ? D::BN_RES : sc.narrow ? D::BN_NARROW : D::BN);
+  p.stages = sc.stages;
   const int tiles = m_tiles * p.n_tiles;
   if (sc.inside) {
     if (tiles > ctx->sm_count) return fail(ctx, SCR_E_STATE, "steps-inside schedule needs one CTA per tile");
@@ -664,31 +677,56 @@ int dense_launch(scr_ctx* ctx, DenseSchedule sc, int m_tiles, const DenseWork& w
   }
   p.err = ctx->d_err;
   p.acc_scale = ctx->dense_acc_scale;
+#if SCR_DENSE_TRACE
+  {
+    static unsigned long long* d_trace = nullptr;
+    if (!d_trace) cudaMalloc(&d_trace, 4096 * 8 * sizeof(unsigned long long));
+    cudaMemsetAsync(d_trace, 0, 4096 * 8 * sizeof(unsigned long long), ctx->stream);
+    p.trace = d_trace;
+  }
+#endif
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(std::min(tiles, ctx->sm_count)));
   cfg.blockDim = dim3(D::NUM_THREADS);
-  cfg.dynamicSmemBytes = sc.narrow ? D::Tile<D::BN_NARROW>::SMEM_BYTES : D::Tile<D::BN>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = sc.resb ? D::res_smem_bytes(p.k_blocks, sc.stages) : sc.narrow ? D::Tile<D::BN_NARROW>::SMEM_BYTES : D::Tile<D::BN>::SMEM_BYTES;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;   // co-residency of the CTAs that wait on each other
   attr[0].val.cooperative = sc.inside ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const int cur = p.s0 & 1;   // (the kernel picks the map by step parity: maps are passed in buffer order)
-  (void)cur;
-  const CUtensorMap &bhi = sc.narrow ? ctx->tm_bhi_n : ctx->tm_bhi, &blo = sc.narrow ? ctx->tm_blo_n : ctx->tm_blo;
+  const CUtensorMap &bhi = sc.resb ? ctx->tm_bhi_r : sc.narrow ? ctx->tm_bhi_n : ctx->tm_bhi;
+  const CUtensorMap &blo = sc.resb ? ctx->tm_blo_r : sc.narrow ? ctx->tm_blo_n : ctx->tm_blo;
   cudaError_t e;
-  if (ctx->dense_kind == D::kF16) {
-    e = sc.narrow ? cudaLaunchKernelEx(&cfg, D::dense_step_kernel<D::BN_NARROW, D::kF16>, w.tm_hi[0], w.tm_hi[1], w.tm_lo[0], w.tm_lo[1], bhi, blo, p)
-                  : cudaLaunchKernelEx(&cfg, D::dense_step_kernel<D::BN, D::kF16>, w.tm_hi[0], w.tm_hi[1], w.tm_lo[0], w.tm_lo[1], bhi, blo, p);
-  } else {
-    e = sc.narrow ? cudaLaunchKernelEx(&cfg, D::dense_step_kernel<D::BN_NARROW, D::kTF32>, w.tm_hi[0], w.tm_hi[1], w.tm_lo[0], w.tm_lo[1], bhi, blo, p)
-                  : cudaLaunchKernelEx(&cfg, D::dense_step_kernel<D::BN, D::kTF32>, w.tm_hi[0], w.tm_hi[1], w.tm_lo[0], w.tm_lo[1], bhi, blo, p);
-  }
+#define SCR_DENSE_GO(BN_, KIND_, RESB_) \
+  cudaLaunchKernelEx(&cfg, D::dense_step_kernel<BN_, KIND_, RESB_>, w.tm_hi[0], w.tm_hi[1], w.tm_lo[0], w.tm_lo[1], bhi, blo, p)
+  if (ctx->dense_kind == D::kF16)
+    e = sc.resb ? SCR_DENSE_GO(D::BN_RES, D::kF16, true) : sc.narrow ? SCR_DENSE_GO(D::BN_NARROW, D::kF16, false) : SCR_DENSE_GO(D::BN, D::kF16, false);
+  else
+    e = sc.resb ? SCR_DENSE_GO(D::BN_RES, D::kTF32, true) : sc.narrow ? SCR_DENSE_GO(D::BN_NARROW, D::kTF32, false) : SCR_DENSE_GO(D::BN, D::kTF32, false);
+#undef SCR_DENSE_GO
   if (e != cudaSuccess) return fail_cuda(ctx, e, "dense stepper launch");
   ctx->launches++;
   ctx->dense_launches++;
+#if SCR_DENSE_TRACE
+  if (const char* path = std::getenv("SCR_DENSE_TRACE")) {   // developer build: per-step time stamps of CTA 0 of this launch
+    if (sc.inside && p.trace) {
+      const int ns = std::min(p.nsteps, 4096);
+      std::vector<unsigned long long> h(static_cast<size_t>(ns) * 8);
+      cudaStreamSynchronize(ctx->stream);
+      cudaMemcpy(h.data(), p.trace, h.size() * 8, cudaMemcpyDeviceToHost);
+      if (FILE* f = std::fopen(path, "a")) {
+        std::fprintf(f, "# launch m_tiles=%d n_tiles=%d nsteps=%d\n", m_tiles, p.n_tiles, p.nsteps);
+        for (int i = 0; i < ns; ++i) {
+          for (int k = 0; k < 8; ++k) std::fprintf(f, "%llu ", h[i * 8 + k]);
+          std::fprintf(f, "\n");
+        }
+        std::fclose(f);
+      }
+    }
+  }
+#endif
   return SCR_OK;
 }
 void dense_gather(scr_ctx* ctx, int64_t m_pad, const int* d_cell, int live, const DenseWork& w, int ld) {
@@ -843,7 +881,7 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   const int64_t m_pad = (static_cast<int64_t>(k) + D::BM - 1) / D::BM * D::BM;
   const int m_tiles = static_cast<int>(m_pad / D::BM);
   const DenseSchedule sc = dense_schedule(ctx, m_tiles, ld);
-  const int n_parts = 2 * (ld / (sc.narrow ? D::BN_NARROW : D::BN));   // column parts of a row's |x' - x| sum
+  const int n_parts = 2 * (ld / (sc.resb ? D::BN_RES : sc.narrow ? D::BN_NARROW : D::BN));   // column parts of a row's |x' - x| sum
   std::vector<int> h_cell(m_pad, -1), h_steps(m_pad, 0), h_src(m_pad, 0);
   std::vector<uint32_t> h_base(m_pad, 0);
   std::vector<int64_t> h_gid(m_pad, 0);
@@ -1246,6 +1284,8 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
       if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo, ctx->d_wlo, ld, ld, ld, D::BN, es);
       if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_bhi_n, ctx->d_whi, ld, ld, ld, D::BN_NARROW, es);
       if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo_n, ctx->d_wlo, ld, ld, ld, D::BN_NARROW, es);
+      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_bhi_r, ctx->d_whi, ld, ld, ld, D::BN_RES, es);
+      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo_r, ctx->d_wlo, ld, ld, ld, D::BN_RES, es);
       if (rc2) return rc2;
     }
   }
