@@ -599,40 +599,52 @@ def run_extras(args, env, rig, counts_dev, want, peak, peak_source, dev):
     block("module_api", module_block)
     env["barrier"]()
 
-    # -- config c4 on the tcgen05 3xTF32 stepper -------------------------------------------------------------------
+    # -- config c4 on the tcgen05 split-precision stepper ------------------------------------------------------------
     def dense_block():
         cells = min(200000, args.cells)
         r = Rig(env, "dense_c4", cells)
         try:
             assert r.layout["dense_stepper"] == 1
-            # denominator: a plain TF32 matmul timed here, on this GPU, now
+            f16 = r.layout.get("dense_encoding", 2) == 1
+            # denominator: a plain cuBLAS matmul in the stepper's operand type (fp16 / tf32), timed here, on this GPU, now,
+            # back to back for about a second (the sustained figure under the power cap, like the stepper's own launches)
             torch.backends.cuda.matmul.allow_tf32 = True
-            a = torch.randn(8192, 8192, device=dev)
-            b = torch.randn(8192, 8192, device=dev)
+            mdt = torch.float16 if f16 else torch.float32
+            a = torch.randn(8192, 8192, device=dev).to(mdt)
+            b = torch.randn(8192, 8192, device=dev).to(mdt)
             for _ in range(3):
                 torch.matmul(a, b)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            best = None
-            for _ in range(5):
-                ev0.record()
-                for _ in range(4):
-                    torch.matmul(a, b)
-                ev1.record()
-                torch.cuda.synchronize()
-                ms = ev0.elapsed_time(ev1) / 4
-                best = ms if best is None or ms < best else best
-            tf32_peak = 2.0 * 8192 ** 3 / (best / 1e3) / 1e12
+            reps = 1200 if f16 else 600
+            ev0.record()
+            for _ in range(reps):
+                torch.matmul(a, b)
+            ev1.record()
+            torch.cuda.synchronize()
+            mm_peak = 2.0 * 8192 ** 3 / (ev0.elapsed_time(ev1) / reps / 1e3) / 1e12
             del a, b
             t = r.timed(1, 1, seed0=9000, do_counts=False)
             ks = t["local_steps"] / (t["kernel_ms"] / 1e3)
             issued = ks * 6.0 * r.n * r.n / 1e12
+            enc = "3 x fp16 split (kind::f16)" if f16 else "3xTF32 (kind::tf32)"
+            measured = {}
+            try:
+                mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                measured = {"bf16_tflops_sustained": mp.get("bf16_tflops_sustained"), "bf16_tflops_burst": mp.get("bf16_tflops")}
+            except Exception:
+                pass
             return {"metric": "cell_steps_per_sec", "workload": "c4: Random n=3000 networkSparsity=0.5 (alpha 2.21), %d cells per GPU, "
                     "single type, stepping only" % cells, "value": t["value"], "ms_per_step": t["ms_per_step"], "n_gpus": world,
-                    "genes": r.n, "nnz": r.nnz, "dtype": "f32 via 3xTF32", "node_iterations": t["node_iterations"],
+                    "genes": r.n, "nnz": r.nnz, "dtype": "f32 via " + enc, "node_iterations": t["node_iterations"],
                     "kernel_launches": t["kernel_launches"], "kernel_cell_steps_per_s": ks,
-                    "roofline": {"bound": "tensor", "kernel": "scr::dense::dense_step_kernel (tcgen05 3xTF32, fused update)",
-                                 "achieved": issued, "useful": issued / 3.0, "peak": tf32_peak, "unit": "TFLOP/s",
-                                 "frac": issued / tf32_peak, "peak_source": "torch.matmul TF32 8192^3 timed in this run (best of 5 x 4)",
+                    "roofline": {"bound": "tensor", "kernel": "scr::dense::dense_step_kernel (tcgen05 %s, fused update)" % enc,
+                                 "achieved": issued, "useful": issued / 3.0, "peak": mm_peak, "unit": "TFLOP/s",
+                                 "frac": issued / mm_peak,
+                                 "peak_source": "torch.matmul %s 8192^3 timed in this run, %d back to back (sustained)" % (
+                                     "fp16" if f16 else "TF32", reps),
+                                 "measured_peaks_json": measured,
+                                 "frac_of_measured_bf16_sustained": (issued / measured["bf16_tflops_sustained"]
+                                                                     if f16 and measured.get("bf16_tflops_sustained") else None),
                                  "flops_per_cell_step_issued": 6.0 * r.n * r.n},
                     "clocks": t["clocks"]}
         finally:

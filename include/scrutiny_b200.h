@@ -63,7 +63,7 @@ int scr_sync(scr_ctx* ctx);
 /* ---- regulatory network: the `gc` argument of developCell (MS:503-504), already divided by
  * alpha (EX:49).  CSR over rows = regulated gene.  Builds the on-chip operator (gene
  * permutation, blocked-ELL tiles, long-row chunks).  Any density is accepted; float32 contexts
- * switch scr_run_phase to the tcgen05 3xTF32 GEMM stepper when nnz >= 5 % of n^2 (the sparse
+ * switch scr_run_phase to the tcgen05 split-precision GEMM stepper (fp16 split by default, SCR_DENSE_KIND=tf32 for 3xTF32) when nnz >= 5 % of n^2 (the sparse
  * operator is still built: the probe and float64 contexts use it). */
 int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* rowptr,
                         const int32_t* col, const double* val);
@@ -98,7 +98,8 @@ int scr_debug_gene_order(const scr_ctx* ctx, int32_t* perm_out, int32_t count);
  * [10]=cells per group, [11]=dense (tcgen05 GEMM) stepper selected (0/1), [12]=operator bytes staged in
  * smem when it is only partly resident, [13]=operator bytes in total, [14]=modelled shared-memory wavefronts of one
  * step's gathers (LDS.128 bank model, csrc/operator_pack.h), [15]=their conflict-free floor, [16]=cell groups held in
- * global memory (0/1: the large-n fallback, n above ~7 000 genes in float32; any n up to 32 768 is accepted). */
+ * global memory (0/1: the large-n fallback, n above ~7 000 genes in float32; any n up to 32 768 is accepted),
+ * [17]=operand encoding of the dense stepper (0 = sparse stepper, 1 = fp16 split, 2 = 3xTF32: csrc/dense_kernel.cuh). */
 int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count);
 
 /* ---- cell states: `currentStates` of findAllNextStates (MS:540-554) --------------------------- */

@@ -73,7 +73,7 @@ def run(name):
                         probe_kernel_ms=pms, probe_launches=plaunches, overflow=len(res["overflow"]))
     cs = best["cell_steps"]
     line = {"config": name, "genes": n, "nnz": int(np.count_nonzero(gc)), "cells": cells, "alpha": alpha,
-            "path": "dense tcgen05 3xTF32" if lay["dense_stepper"] else "sparse smem-resident",
+            "path": ("dense tcgen05 " + {1: "fp16 split", 2: "3xTF32"}.get(lay.get("dense_encoding"), "")) if lay["dense_stepper"] else "sparse smem-resident",
             "node_iterations": sim.node_iterations, "cell_steps": cs,
             "cell_steps_per_s_whole_job": cs / best["wall_s"], "cell_steps_per_s_kernel": cs / (best["kernel_ms"] / 1e3),
             "wall_s": best["wall_s"], "kernel_ms": best["kernel_ms"], "kernel_launches": best["kernel_launches"],
@@ -81,7 +81,7 @@ def run(name):
             "whole_job_over_kernel": (best["kernel_ms"] / 1e3) / best["wall_s"], "overflow_entries": best["overflow"],
             "alpha_search_s": t_alpha, "setup_s": t_setup, "counts_sum_bytes": int(out.sum(dtype=np.int64)), "zero_fraction": float((out == 0).mean())}
     if lay["dense_stepper"]:
-        line["tflops_3xtf32_issued"] = cs * 6.0 * n * n / (best["kernel_ms"] / 1e3) / 1e12
+        line["tflops_split_issued"] = cs * 6.0 * n * n / (best["kernel_ms"] / 1e3) / 1e12
     else:
         line["algorithmic_GBps"] = cs * 8.0 * n / (best["kernel_ms"] / 1e3) / 1e9
         line["frac_of_hbm_6556"] = line["algorithmic_GBps"] / 6556.2

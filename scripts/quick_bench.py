@@ -55,7 +55,7 @@ def main():
         ms, _ = e.step_kernel_stats()
         cs = float(steps.sum())
         print("rep %d: kernel %.2f ms  wall %.2f ms  %.1f M cell-steps/s  algorithmic %.0f GB/s (%.1f%% of 6556)  "
-              "3xTF32-issued %.1f TFLOP/s" % (r, ms, wall * 1e3, cs / ms / 1e3, cs * 8 * n / ms / 1e6,
+              "3-product-issued %.1f TFLOP/s" % (r, ms, wall * 1e3, cs / ms / 1e3, cs * 8 * n / ms / 1e6,
                                             cs * 8 * n / ms / 1e6 / 65.562, cs * 6.0 * n * n / ms / 1e9), flush=True)
     s = e.get_states(0, 4)
     print("finite:", np.isfinite(s).all(), "range", s.min(), s.max())

@@ -550,6 +550,16 @@ __global__ void scatter_rows_kernel(float* __restrict__ state, int64_t ld_state,
     state[static_cast<int64_t>(cell) * ld_state + g] = src[static_cast<int64_t>(row) * ld + g];
 }
 
+// probe: per-(step, row) sum of the column parts of |x' - x| in index order, in float64 (what the host's stopping rule reads)
+__global__ void rowdiff_sum_kernel(const float* __restrict__ parts, int n_parts, int m_pad, int nsteps, int k, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nsteps * k) return;
+  const int s = i / k, row = i % k;
+  double tot = 0.0;
+  for (int t = 0; t < n_parts; ++t) tot += static_cast<double>(parts[(static_cast<int64_t>(s) * n_parts + t) * m_pad + row]);
+  out[i] = tot;
+}
+
 // noise of the dense path for (global cell, step): word v of counter (gene/4) -> gene
 __global__ void debug_noise_dense_kernel(int n, uint32_t gid_lo, uint32_t gid_hi, uint32_t step, float rscale,
                                          RoundKeys rk, double* __restrict__ out) {

@@ -125,6 +125,8 @@ struct scr_ctx {
   double* d_pnd = nullptr;
   size_t piters_cap = 0, pnd_cap = 0;
   unsigned char* d_parena = nullptr;         // dense probe: one arena for its private working set
+  double* h_psum = nullptr;                  // dense probe: pinned landing buffer of a chunk's per-(step, cell) sums
+  size_t h_psum_cap = 0;
   size_t parena_cap = 0;
   // stepper launch configuration per kernel variant [probe][supplied]: the dynamic shared-memory opt-in and the
   // occupancy query are made once per size, not per launch
@@ -962,7 +964,17 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   std::vector<double> nd(static_cast<size_t>(k) * max_iter, 0.0);
   std::vector<int> iters(k, 0);
   std::vector<char> done(k, 0);
-  std::vector<float> h_diff(diff_per_step * chunk);
+  // per chunk the device sums the column parts of every (step, row) in index order; only those k doubles per step cross PCIe
+  const size_t sum_elems = static_cast<size_t>(chunk) * k;
+  if ((rc = ensure_buf(ctx, ctx->d_pnd, ctx->pnd_cap, sum_elems))) { cleanup(); return rc; }
+  if (ctx->h_psum_cap < sum_elems) {
+    cudaFreeHost(ctx->h_psum);
+    ctx->h_psum = nullptr;
+    ctx->h_psum_cap = 0;
+    CKP(cudaMallocHost(&ctx->h_psum, sum_elems * sizeof(double)));
+    ctx->h_psum_cap = sum_elems;
+  }
+  const double* h_sum = ctx->h_psum;
   int ndone = 0;
   for (int s0 = 0; s0 < max_iter && ndone < k; s0 += chunk) {
     const int cnt = std::min(chunk, max_iter - s0);
@@ -975,16 +987,17 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
         if ((rc = dense_launch(ctx, sc, m_tiles, w, p))) { cleanup(); return rc; }
       }
     }
-    CKP(cudaMemcpyAsync(h_diff.data(), d_diff, diff_per_step * cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    D::rowdiff_sum_kernel<<<(cnt * k + 127) / 128, 128, 0, ctx->stream>>>(d_diff, n_parts, static_cast<int>(m_pad), cnt, k, ctx->d_pnd);
+    CKP(cudaGetLastError());
+    ctx->launches++;
+    CKP(cudaMemcpyAsync(ctx->h_psum, ctx->d_pnd, static_cast<size_t>(cnt) * k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CKP(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < k; ++i) {
       if (done[i]) continue;
       double* trace = nd.data() + static_cast<size_t>(i) * max_iter;
       for (int j = 0; j < cnt && !done[i]; ++j) {
         const int s = s0 + j;
-        double tot = 0.0;
-        for (int t = 0; t < n_parts; ++t) tot += static_cast<double>(h_diff[diff_per_step * j + static_cast<size_t>(t) * m_pad + i]);
-        trace[s] = tot / (static_cast<double>(n) * static_cast<double>(static_cast<float>(dt)));
+        trace[s] = h_sum[static_cast<size_t>(j) * k + i] / (static_cast<double>(n) * static_cast<double>(static_cast<float>(dt)));
         iters[i] = s + 1;
         if (s >= avg_num - 1) {
           double acc = 0.0;
@@ -1157,7 +1170,7 @@ void scr_destroy(scr_ctx* ctx) {
     free_network(ctx);
     free_dense_work(ctx);
     cudaFree(ctx->d_state); cudaFree(ctx->d_items); cudaFreeHost(ctx->h_items); cudaFree(ctx->d_counter); cudaFree(ctx->d_err); cudaFree(ctx->d_stage);
-    cudaFree(ctx->d_piters); cudaFree(ctx->d_pnd); cudaFree(ctx->d_gscratch); cudaFree(ctx->d_parena); cudaFree(ctx->d_mt_count);
+    cudaFree(ctx->d_piters); cudaFree(ctx->d_pnd); cudaFree(ctx->d_gscratch); cudaFree(ctx->d_parena); cudaFree(ctx->d_mt_count); cudaFreeHost(ctx->h_psum);
     for (int b = 0; b < 2; ++b) { cudaFreeHost(ctx->h_xfer[b]); cudaFree(ctx->d_xfer[b]); if (ctx->ev_x[b]) cudaEventDestroy(ctx->ev_x[b]); }
     free_counts_scratch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1373,12 +1386,13 @@ int scr_get_layout(const scr_ctx* ctx, int64_t* out, int count) {
   if (!ctx->has_net) return fail(ctx, SCR_E_STATE, "network not set");
   const PackedOperator& o = ctx->op;
   const size_t per_group = ctx->gstate ? static_cast<size_t>(scr::group_hdr(false)) : ctx->gbytes;
-  const int64_t v[17] = {o.n_pad, o.npp, static_cast<int64_t>(o.tile_val.size()), o.nv, o.lv, o.cap, o.wq, ctx->q,
+  const int64_t v[18] = {o.n_pad, o.npp, static_cast<int64_t>(o.tile_val.size()), o.nv, o.lv, o.cap, o.wq, ctx->q,
                          static_cast<int64_t>(ctx->fixed_bytes + (ctx->w_smem ? ctx->w_bytes : 0) + ctx->q * per_group +
                                               w_prefix_bytes(ctx, ctx->q)),
                          ctx->w_smem ? 1 : 0, ctx->cpg(), ctx->dense_mode ? 1 : 0, w_prefix_bytes(ctx, ctx->q), ctx->w_bytes,
-                         o.gather_wavefronts, o.gather_wavefronts_floor, ctx->gstate ? 1 : 0};
-  for (int i = 0; i < count && i < 17; ++i) out[i] = v[i];
+                         o.gather_wavefronts, o.gather_wavefronts_floor, ctx->gstate ? 1 : 0,
+                         ctx->dense_mode ? (ctx->dense_kind == scr::dense::kF16 ? 1 : 2) : 0};
+  for (int i = 0; i < count && i < 18; ++i) out[i] = v[i];
   return SCR_OK;
 }
 

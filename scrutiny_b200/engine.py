@@ -132,12 +132,13 @@ class Engine:
         return int(self._lib.scr_noise_stream_version())
 
     def layout(self):
-        out = np.zeros(17, dtype=np.int64)
-        self._check(self._lib.scr_get_layout(self._ctx, _ptr(out, C.c_int64), 17))
+        out = np.zeros(18, dtype=np.int64)
+        self._check(self._lib.scr_get_layout(self._ctx, _ptr(out, C.c_int64), 18))
         keys = ("n_pad", "pingpong_genes", "tile_slots", "chunks", "chunk_len", "row_cap",
                 "warps_per_group", "groups_per_cta", "smem_bytes", "operator_in_smem",
                 "cells_per_group", "dense_stepper", "operator_prefix_bytes", "operator_bytes",
-                "gather_wavefronts_model", "gather_wavefronts_floor", "state_in_global")
+                "gather_wavefronts_model", "gather_wavefronts_floor", "state_in_global",
+                "dense_encoding")                                   # 0 = sparse stepper, 1 = fp16 split, 2 = 3xTF32
         return dict(zip(keys, (int(v) for v in out)))
 
     # -- states -----------------------------------------------------------------------------
