@@ -16,6 +16,7 @@
 
 #include "aux_kernels.cuh"
 #include "dense_kernel.cuh"
+#include "dense_pair_kernel.cuh"
 #include "operator_pack.h"
 #include "regnet_kernels.cuh"
 #include "step_kernel.cuh"
@@ -73,6 +74,7 @@ struct scr_ctx {
   CUtensorMap tm_bhi, tm_blo;                  // B operands, boxes of the wide tile (256 genes x 128 bytes)
   CUtensorMap tm_bhi_n, tm_blo_n;              // ... of the narrow tile (64 genes x 128 bytes)
   CUtensorMap tm_bhi_r, tm_blo_r;              // ... of the resident-B tile (32 genes x 128 bytes)
+  CUtensorMap tm_bhi_p, tm_blo_p;              // ... of the CTA-pair schedule (each CTA's 128 genes x 128 bytes)
   bool dense_attr_set = false;
   // working set [rows_cap][n_pad], ping-pong: state (fp32) and its operand split (hi only in the fp16 encoding)
   float* d_x[2] = {nullptr, nullptr};
@@ -605,7 +607,7 @@ int run_phase_t(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int32_t*
 // Schedule per launch: when every (cell tile, gene tile) pair can have its own CTA the launch runs all remaining steps
 // ("steps inside": small batches -- config c1, every probe -- take one launch per phase instead of one per timestep; narrow
 // 128 x 64 tiles if those fit the SM count, else wide 128 x 256 ones); otherwise one launch per timestep of wide tiles.
-struct DenseSchedule { bool narrow, inside, resb; int stages; };
+struct DenseSchedule { bool narrow, inside, resb, pair; int stages; };
 DenseSchedule dense_schedule(const scr_ctx* ctx, int m_tiles, int ld) {
   namespace D = scr::dense;
   const int force_narrow = scr::env_int("SCR_DENSE_NARROW", -1), force_inside = scr::env_int("SCR_DENSE_INSIDE", -1);
@@ -613,6 +615,7 @@ DenseSchedule dense_schedule(const scr_ctx* ctx, int m_tiles, int ld) {
   DenseSchedule sc;
   sc.resb = false;
   sc.stages = 0;
+  sc.pair = false;
   sc.narrow = force_narrow >= 0 ? force_narrow != 0 : t_narrow <= ctx->sm_count;
   sc.inside = (sc.narrow ? t_narrow : t_wide) <= ctx->sm_count && force_inside != 0;
   // resident-B tiles: W's slice of the CTA stays in shared memory for the whole launch (small networks)
@@ -622,6 +625,8 @@ DenseSchedule dense_schedule(const scr_ctx* ctx, int m_tiles, int ld) {
     while (stages >= 2 && D::res_smem_bytes(k_blocks, stages) > ctx->smem_optin) --stages;
     if (stages >= 2) { sc.resb = true; sc.narrow = false; sc.stages = std::min(stages, k_blocks); }
   }
+  // large batches, one launch per timestep of wide tiles: CTA pairs (cta_group::2) halve the W bytes each CTA stages
+  sc.pair = !sc.inside && !sc.narrow && scr::env_int("SCR_DENSE_PAIR", 1) != 0;
   return sc;
 }
 // the working set of one phase / probe: state and operand split, ping-pong, with the A-operand tensor maps
@@ -650,6 +655,8 @@ int dense_set_attrs(scr_ctx* ctx) {
   CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_NARROW, D::kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN_NARROW>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN, D::kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_NARROW, D::kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::Tile<D::BN_NARROW>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(D::dense_pair_kernel<D::kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::PAIR_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(D::dense_pair_kernel<D::kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::PAIR_SMEM_BYTES));
   CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_RES, D::kF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
   CK(cudaFuncSetAttribute(D::dense_step_kernel<D::BN_RES, D::kTF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
   ctx->dense_attr_set = true;
@@ -698,6 +705,19 @@ int dense_launch(scr_ctx* ctx, DenseSchedule sc, int m_tiles, const DenseWork& w
   attr[0].val.cooperative = sc.inside ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (sc.pair) {   // clusters of two CTAs (compile-time cluster dimensions), one 256 x 256 tile per pair at a time
+    const int pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles;
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * std::min(pair_tiles, ctx->sm_count / 2)));
+    cfg.dynamicSmemBytes = D::PAIR_SMEM_BYTES;
+    cfg.numAttrs = 0;
+    const cudaError_t ep = ctx->dense_kind == D::kF16
+        ? cudaLaunchKernelEx(&cfg, D::dense_pair_kernel<D::kF16>, w.tm_hi[0], w.tm_hi[1], w.tm_lo[0], w.tm_lo[1], ctx->tm_bhi_p, ctx->tm_blo_p, p)
+        : cudaLaunchKernelEx(&cfg, D::dense_pair_kernel<D::kTF32>, w.tm_hi[0], w.tm_hi[1], w.tm_lo[0], w.tm_lo[1], ctx->tm_bhi_p, ctx->tm_blo_p, p);
+    if (ep != cudaSuccess) return fail_cuda(ctx, ep, "dense stepper launch (CTA pairs)");
+    ctx->launches++;
+    ctx->dense_launches++;
+    return SCR_OK;
+  }
   const CUtensorMap &bhi = sc.resb ? ctx->tm_bhi_r : sc.narrow ? ctx->tm_bhi_n : ctx->tm_bhi;
   const CUtensorMap &blo = sc.resb ? ctx->tm_blo_r : sc.narrow ? ctx->tm_blo_n : ctx->tm_blo;
   cudaError_t e;
@@ -775,9 +795,9 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
     std::vector<int64_t> pos(bucket.begin(), bucket.end() - 1);
     for (int64_t i = 0; i < m; ++i) if (steps[i] > 0) order[pos[smax - steps[i]]++] = i;
   }
-  const int64_t m_pad = (live + D::BM - 1) / D::BM * D::BM;
-  const int m_tiles = static_cast<int>(m_pad / D::BM);
-  std::vector<int> h_cell(m_pad, -1), h_steps(m_pad, 0), h_src(m_pad, 0), h_tile(m_tiles, 0);
+  const int m_tiles = static_cast<int>((live + D::BM - 1) / D::BM);
+  const int64_t m_pad = static_cast<int64_t>((m_tiles + 1) / 2) * 2 * D::BM;   // whole CTA-pair tiles (256 rows)
+  std::vector<int> h_cell(m_pad, -1), h_steps(m_pad, 0), h_src(m_pad, 0), h_tile(m_pad / D::BM, 0);
   std::vector<uint32_t> h_base(m_pad, 0);
   std::vector<int64_t> h_gid(m_pad, 0);
   for (int64_t r = 0; r < live; ++r) {
@@ -805,7 +825,7 @@ int run_phase_dense(scr_ctx* ctx, int64_t m, const int64_t* cell_ids, const int3
   CK(cudaMemcpyAsync(ctx->d_row_cell, h_cell.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_row_steps, h_steps.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_row_src, h_src.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_tile_steps, h_tile.data(), m_tiles * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_tile_steps, h_tile.data(), h_tile.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_row_base, h_base.data(), m_pad * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_row_gid, h_gid.data(), m_pad * 8, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -882,7 +902,8 @@ int probe_dense(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double
   const int n = op.n, ld = op.n_pad;
   const int64_t m_pad = (static_cast<int64_t>(k) + D::BM - 1) / D::BM * D::BM;
   const int m_tiles = static_cast<int>(m_pad / D::BM);
-  const DenseSchedule sc = dense_schedule(ctx, m_tiles, ld);
+  DenseSchedule sc = dense_schedule(ctx, m_tiles, ld);
+  sc.pair = false;   // (the pair kernel has no probe outputs: a probe too large for the steps-inside schedule takes single-CTA wide tiles)
   const int n_parts = 2 * (ld / (sc.resb ? D::BN_RES : sc.narrow ? D::BN_NARROW : D::BN));   // column parts of a row's |x' - x| sum
   std::vector<int> h_cell(m_pad, -1), h_steps(m_pad, 0), h_src(m_pad, 0);
   std::vector<uint32_t> h_base(m_pad, 0);
@@ -1299,6 +1320,8 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
       if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo_n, ctx->d_wlo, ld, ld, ld, D::BN_NARROW, es);
       if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_bhi_r, ctx->d_whi, ld, ld, ld, D::BN_RES, es);
       if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo_r, ctx->d_wlo, ld, ld, ld, D::BN_RES, es);
+      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_bhi_p, ctx->d_whi, ld, ld, ld, D::PAIR_B_ROWS, es);
+      if (!rc2) rc2 = make_tmap(ctx, &ctx->tm_blo_p, ctx->d_wlo, ld, ld, ld, D::PAIR_B_ROWS, es);
       if (rc2) return rc2;
     }
   }

@@ -114,7 +114,8 @@ def test_bench_network_free_running_fast_path_sampled_cells(net, prec, tol):
 @pytest.mark.parametrize("env,launches", [
     ({}, 1),                                                       # default: fp16 split, narrow tiles, steps inside the launch
     ({"SCR_DENSE_NARROW": "0"}, 1),                                # wide tiles, steps inside
-    ({"SCR_DENSE_NARROW": "0", "SCR_DENSE_INSIDE": "0"}, 20),      # wide tiles, one launch per timestep (what 200 k cells run)
+    ({"SCR_DENSE_NARROW": "0", "SCR_DENSE_INSIDE": "0"}, 20),      # CTA pairs (cta_group::2), one launch per timestep (what 200 k cells run)
+    ({"SCR_DENSE_NARROW": "0", "SCR_DENSE_INSIDE": "0", "SCR_DENSE_PAIR": "0"}, 20),   # single-CTA wide tiles per timestep
     ({"SCR_DENSE_KIND": "tf32"}, 1),                               # north_star's 3xTF32 encoding
     ({"SCR_DENSE_KIND": "tf32", "SCR_DENSE_NARROW": "0", "SCR_DENSE_INSIDE": "0"}, 20),
 ])

@@ -26,8 +26,12 @@ def engine_for(W, cells, prec="f32", offset=0):
     return e
 
 
-@pytest.mark.parametrize("env", [{}, {"SCR_DENSE_RESB": "0"}, {"SCR_DENSE_INSIDE": "0"}, {"SCR_DENSE_KIND": "tf32"}],
-                         ids=["f16-resident-W", "f16-narrow-inside", "f16-per-step", "tf32"])
+@pytest.mark.parametrize("env", [{}, {"SCR_DENSE_RESB": "0"}, {"SCR_DENSE_INSIDE": "0"}, {"SCR_DENSE_KIND": "tf32"},
+                                 {"SCR_DENSE_NARROW": "0", "SCR_DENSE_INSIDE": "0"},
+                                 {"SCR_DENSE_NARROW": "0", "SCR_DENSE_INSIDE": "0", "SCR_DENSE_KIND": "tf32"},
+                                 {"SCR_DENSE_NARROW": "0", "SCR_DENSE_INSIDE": "0", "SCR_DENSE_PAIR": "0"}],
+                         ids=["f16-resident-W", "f16-narrow-inside", "f16-per-step", "tf32", "f16-cta-pairs", "tf32-cta-pairs",
+                              "f16-wide-single-cta"])
 @pytest.mark.parametrize("n,cells,smax,density", [(500, 300, 40, 0.99), (200, 131, 25, 0.5), (700, 64, 12, 0.2)])
 def test_dense_stepper_ragged_against_oracle(n, cells, smax, density, env, monkeypatch):
     for k, v in env.items():
