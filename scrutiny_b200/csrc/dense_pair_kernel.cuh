@@ -73,13 +73,22 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
-// bounded wait: ~2 s of 10 ms suspended tries, then the error word is raised and every later wait of the CTA returns at once
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* err) {
-  if (*abort_flag) return;
-  for (int tries = 0; tries < 200; ++tries)
-    if (mbar_try_wait(bar, parity)) return;
+// bounded wait: the phase, or 4 s of wall clock (%globaltimer; the suspend-time hint of try_wait is only a hint, so tries
+// are not counted).  On a timeout the error word is raised, the CTA's flag is set and the caller leaves its role loop:
+// nothing more is issued or arrived on (a stray arrival on a completed barrier would be a fault of its own).
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* err) {
+  if (*abort_flag) return false;
+  if (mbar_try_wait(bar, parity)) return true;
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    if (mbar_try_wait(bar, parity)) return true;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 4000000000ULL || *abort_flag) break;
+  }
   *abort_flag = 1;
   atomicMax(err, kErrDensePair);
+  return false;
 }
 
 template <int KIND>
@@ -136,7 +145,7 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
         const int arow = mp * 2 * BM + static_cast<int>(rank) * BM;
         const int brow = nt * BN + static_cast<int>(rank) * PAIR_B_ROWS;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait_bounded(&empty[st], ph ^ 1u, abort_flag, p.err);
+          if (!mbar_wait_bounded(&empty[st], ph ^ 1u, abort_flag, p.err)) { t = ntiles; break; }
           unsigned char* sm = stage_mem + st * PAIR_STAGE_BYTES;
           const uint32_t lbar = mapa_u32(smem_u32(&full[st]), 0);
           if (leader) mbar_expect_tx(&full[st], 2 * PAIR_STAGE_BYTES);
@@ -156,11 +165,11 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
       int st = 0, ab = 0;
       uint32_t ph = 0, aph = 0;
       for (int t = pair; t < ntiles; t += npairs) {
-        mbar_wait_bounded(&tempty[ab], aph ^ 1u, abort_flag, p.err);
+        if (!mbar_wait_bounded(&tempty[ab], aph ^ 1u, abort_flag, p.err)) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + ab * BN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait_bounded(&full[st], ph, abort_flag, p.err);
+          if (!mbar_wait_bounded(&full[st], ph, abort_flag, p.err)) { t = ntiles; break; }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (lane == 0) {
             const uint32_t sa = smem_u32(stage_mem + st * PAIR_STAGE_BYTES);
@@ -206,7 +215,8 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
       const float* nrow = p.noise ? p.noise + (static_cast<int64_t>(p.row_src[row]) * p.noise_steps + s) * p.n : nullptr;
       float amax = 0.f;
 
-      mbar_wait_bounded(&tfull[ab], aph, abort_flag, p.err);
+      mbar_wait_bounded(&tfull[ab], aph, abort_flag, p.err);   // (after a timeout the loop runs on without waiting or arriving:
+                                                               //  every thread still meets the CTA's named barriers)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + ab * BN + part * PART;
 #pragma unroll 1
@@ -280,7 +290,7 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
       // hand the accumulator back: one arrival per warp on the leader's barrier
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[ab]), 0));
+      if (lane == 0 && !*abort_flag) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[ab]), 0));
       if (++ab == 2) { ab = 0; aph ^= 1u; }
     }
   }
