@@ -6,7 +6,9 @@
         - supplied noise (step_kernel<.., SUPPLIED>), ragged 0..30 steps, every cell against oracle/fast_oracle.py;
         - free-running noise (the packed fast path bench.py times), ragged 0..60 steps, a sample of cells replayed through
           the oracle with the noise scr_debug_noise dumps for them;
-  (b) config c4 -- Random n = 3000, sparsity 0.5, alpha 2.21 -- 256 cells x 20 steps on the tcgen05 3xTF32 stepper;
+  (b) config c4 -- Random n = 3000, sparsity 0.5, alpha 2.21 -- 256 cells x 20 steps on every schedule and operand encoding
+      of the tcgen05 stepper, and 4 000 free-running cells on the CTA-pair schedule bench.py's c4 block runs (sampled cells
+      replayed through the oracle, shard invariance, agreement with the single-CTA kernel);
   (c) a c2-shaped prepared run (TRRUST, 7-type tree, 10 000 cells, run_all with fixed iterations): sampled cells replayed
       phase by phase through the oracle with their dumped noise;
   (d) transformData through the public module: lambda against the port with the same seed.
@@ -147,6 +149,55 @@ def test_c4_dense_network_on_the_tcgen05_stepper(env, launches, monkeypatch):
     fo.run_phase(gc, want, steps, proj, const, 0.01, noise)
     err = np.max(np.abs(e.get_states().T - want))
     assert err <= 1e-4, err
+
+
+def test_c4_large_batch_takes_the_cta_pair_schedule_free_running(monkeypatch):
+    """What bench.py's dense_c4 block runs, at a size the oracle can follow: 4 000 cells (32 cell tiles > SMs / 12 gene tiles,
+    so the launch per timestep takes CTA pairs; 4 000 is not a multiple of 128 or 256: padding rows), ragged 0..12 steps,
+    free-running Philox noise.  (i) a sample of cells replayed through the float64 oracle with the noise scr_debug_noise
+    dumps for them; (ii) two shards with global offsets reproduce the single context bit for bit; (iii) the single-CTA
+    kernel (SCR_DENSE_PAIR=0) agrees to rounding."""
+    from scrutiny_b200 import engine, network
+    seed_all(1337)
+    gc, tf = network.generate_gene_correlation_matrix(3000, "Random", networkSparsity=0.5)
+    gc /= 2.21
+    n, cells, smax, seed, sigma, off = 3000, 4000, 12, 0xC4C4, 0.05, 2 ** 33 + 5
+    rng = np.random.RandomState(23)
+    proj, const = node_vectors(n, tf, rng)
+    x0 = rng.uniform(-1, 1, size=n)
+    steps = rng.randint(0, smax + 1, size=cells)
+    steps[:3] = [smax, 0, smax]
+    base = rng.randint(0, 50, size=cells)
+
+    def run(lo, hi):
+        e = engine.Engine(0, "f32")
+        e.set_network(gc)
+        assert e.layout()["dense_stepper"] == 1 and e.layout()["dense_encoding"] == 1
+        e.alloc_cells(hi - lo, off + lo)
+        e.set_states_broadcast(x0)
+        e.run_phase(np.arange(hi - lo), steps[lo:hi], proj, const, step_base=base[lo:hi], sigma=sigma, seed=seed)
+        return e, e.get_states().T
+
+    e, full = run(0, cells)
+    # one CTA-pair launch per timestep while more than 12 cell tiles are live (steps 0..6 here); the steps after that share
+    # one steps-inside launch of wide tiles
+    assert 6 <= e.path_launches()["dense_gemm"] <= smax
+    assert np.isfinite(full).all() and np.abs(full).max() <= 2.0
+    sample = np.concatenate([[0, 1, 2], rng.choice(cells, size=5, replace=False)])
+    noise = np.zeros((len(sample), smax, n))
+    for i, c in enumerate(sample):
+        for s in range(steps[c]):
+            noise[i, s] = e.debug_noise(off + int(c), int(base[c]) + s, sigma, seed)
+    want = np.repeat(x0.astype(np.float32).astype(np.float64)[None, :], len(sample), axis=0)
+    fo.run_phase(gc, want, steps[sample], proj, const, 0.01, noise)
+    err = np.max(np.abs(full[sample] - want))
+    assert err <= 1e-4, err
+    _, a = run(0, 2432)
+    _, b = run(2432, cells)
+    assert np.array_equal(full[:2432], a) and np.array_equal(full[2432:], b)
+    monkeypatch.setenv("SCR_DENSE_PAIR", "0")
+    _, single = run(0, cells)
+    assert np.max(np.abs(single - full)) <= 1e-6
 
 
 @pytest.mark.parametrize("prec,tol", [("f32", 1e-4), ("f64", 1e-9)])

@@ -143,3 +143,33 @@ def test_states_outside_the_fp16_operand_range_are_refused_not_saturated():
     want = X0.copy()
     fo.run_phase(fo.as_operator(W), want, np.full(cells, 3), np.ones(n), np.zeros(n), 0.01, np.zeros((cells, 3, n)))
     assert np.max(np.abs(e2.get_states().T - want)) <= 1e-3   # (values of 2000: fp32 ulp 1.2e-4)
+
+
+@pytest.mark.parametrize("kind", ["f16", "tf32"])
+def test_dense_stepper_against_the_reference_outputs(golden, kind, monkeypatch):
+    """The committed outputs of the UNMODIFIED reference (tests/golden, oracle/make_golden.py) through the GEMM stepper
+    (forced with SCR_DENSE=1: the golden networks are small), both operand encodings: one developCell step with
+    non-trivial proj / const / geneMeanLevels (MS:503-537) and 40 steps of findCellNextState at gain 50 with the
+    reference's own noise (MS:683-736)."""
+    from scrutiny_b200 import engine
+    monkeypatch.setenv("SCR_DENSE", "1")
+    monkeypatch.setenv("SCR_DENSE_KIND", kind)
+    g = golden("step")
+    e = engine.Engine(0, "f32")
+    e.set_network(g["gc"])
+    assert e.layout()["dense_stepper"] == 1 and e.layout()["dense_encoding"] == (1 if kind == "f16" else 2)
+    e.alloc_cells(3)
+    e.set_states(np.stack([g["x0"]] * 3, axis=1))
+    e.run_phase([0, 1, 2], [1, 1, 0], g["proj"], g["const"], dt=float(g["dt"]), sigma=float(g["sigma"]),
+                mu=float(g["mu"]), noise=np.stack([g["noise"][None, :]] * 3))
+    out = e.get_states()
+    assert np.max(np.abs(out[:, 0] - g["x1"])) <= 2e-6 and np.max(np.abs(out[:, 1] - g["x1"])) <= 2e-6
+    assert np.array_equal(out[:, 2], g["x0"].astype(np.float32).astype(np.float64))   # zero steps: untouched
+    g = golden("cellsteps")
+    e = engine.Engine(0, "f32")
+    e.set_network(g["gc"])
+    assert e.layout()["dense_stepper"] == 1
+    e.alloc_cells(1)
+    e.set_states(g["x0"][:, None])
+    e.run_phase([0], [int(g["steps"])], g["proj"], g["const"], noise=g["noise"][None])
+    assert np.max(np.abs(e.get_states()[:, 0] - g["xT"])) <= 1e-4
