@@ -134,6 +134,16 @@ int scr_probe(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* 
               const double* noise /* (k, max_iter, n) or NULL */, int32_t* iters_out,
               double* normdiff_out);
 
+/* The same probe for `nprobes` lineage nodes at once (findAllNextStates probes each node right before its phase, MS:583-586;
+ * the sampled cells of SIBLING nodes are final as soon as the parent's phase is, so their probes are independent).
+ * Identical results to nprobes scr_probe calls (w_div = noise = NULL); the launches run side by side on separate streams
+ * where the path allows it (sparse stepper), one after the other otherwise.
+ *   k[nprobes] samples per node; sample_ids / iters_out: concatenated; proj, cnst: (nprobes, n); seeds[nprobes]. */
+int scr_probe_multi(scr_ctx* ctx, int32_t nprobes, const int32_t* k, const int64_t* sample_ids,
+                    const double* proj, const double* cnst, double dt, double sigma, double mu,
+                    double thresh, int32_t max_iter, int32_t avg_num, const uint64_t* seeds, uint32_t stream,
+                    int32_t* iters_out);
+
 /* ---- read-out: transformData (MS:816-891) --------------------------------------------------- */
 /* per-gene SUM over this context's cells (MS:851 needs the mean over ALL cells: all-reduce
  * these n doubles across ranks, divide by the global cell count). */

@@ -26,7 +26,7 @@ def wrap(obj, name):
     def g(*a, **k):
         t0 = time.perf_counter(); r = f(*a, **k); acc[name] = acc.get(name, 0.0) + time.perf_counter() - t0; return r
     setattr(obj, name, g)
-for name in ("probe", "run_phase", "gene_sums", "counts", "counts_compact"):
+for name in ("probe", "probe_multi", "run_phase", "gene_sums", "counts", "counts_compact"):
     wrap(eng, name)
 for rep in range(4):
     acc.clear()

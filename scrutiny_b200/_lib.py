@@ -40,6 +40,8 @@ SIGNATURES = {
     "scr_probe": (C.c_int, [c_ctx, C.c_int32, _i64p, _f64p, _f64p, _f64p, C.c_double, C.c_double,
                             C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32,
                             _f64p, _i32p, _f64p]),
+    "scr_probe_multi": (C.c_int, [c_ctx, C.c_int32, _i32p, _i64p, _f64p, _f64p, C.c_double, C.c_double, C.c_double,
+                                  C.c_double, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_uint32, _i32p]),
     "scr_gene_sums": (C.c_int, [c_ctx, _f64p]),
     "scr_counts": (C.c_int, [c_ctx, _f64p, C.c_double, _f64p, C.c_uint64, _f64p, C.c_int32,
                              C.c_void_p, C.c_int, _f64p]),

@@ -130,6 +130,21 @@ struct scr_ctx {
   double* h_psum = nullptr;                  // dense probe: pinned landing buffer of a chunk's per-(step, cell) sums
   size_t h_psum_cap = 0;
   size_t parena_cap = 0;
+  // scr_probe_multi: probes of sibling lineage nodes run side by side, each on its own stream with its own per-launch
+  // buffers (work items, proj/const, bias, work-queue counter, outputs); installed into the fields above for the duration
+  // of one probe_t call (defer_sync: launch only, the caller synchronises and collects)
+  struct ProbeSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Item* d_items = nullptr; Item* h_items = nullptr; size_t items_cap = 0;
+    void *d_pc = nullptr, *d_bias = nullptr;
+    int* d_counter = nullptr;
+    int* d_piters = nullptr; double* d_pnd = nullptr; size_t piters_cap = 0, pnd_cap = 0;
+  };
+  static constexpr int kProbeSlots = 8;
+  ProbeSlot probe_slots[kProbeSlots];
+  bool defer_sync = false;
+  int probe_share = 1;
   // stepper launch configuration per kernel variant [probe][supplied]: the dynamic shared-memory opt-in and the
   // occupancy query are made once per size, not per launch
   struct LaunchCfg { size_t smem = 0; int threads = 0, per_sm = 0, mode = -1; };
@@ -222,8 +237,11 @@ void build_blobs(const PackedOperator& op, std::vector<unsigned char>& tab, std:
   }
 }
 
+void free_probe_slots(scr_ctx* ctx);
+
 void free_network(scr_ctx* ctx) {
   if (ctx->host_only) return;
+  free_probe_slots(ctx);   // (their proj / const buffers are sized by the network)
   cudaFree(ctx->d_tab); cudaFree(ctx->d_tab_wide); cudaFree(ctx->d_w); cudaFree(ctx->d_perm); cudaFree(ctx->d_inv);
   ctx->d_tab_wide = nullptr;
   cudaFree(ctx->d_pc); cudaFree(ctx->d_bias); cudaFree(ctx->d_whi); cudaFree(ctx->d_wlo);
@@ -380,6 +398,7 @@ int launch_step_t(scr_ctx* ctx, scr::StepParams<T>& p, int nitems) {
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->launches++;
+  if (ctx->defer_sync) return SCR_OK;   // scr_probe_multi: the caller synchronises, times and collects
   CK(cudaStreamSynchronize(ctx->stream));
 #if SCR_DEBUG_CHECKS
   {
@@ -1047,8 +1066,8 @@ int probe_t(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_
   // the per-step work each: 8.0 -> ms per 7 probes, profiles/r2_experiments.txt); the alpha ladder's ~1250 samples keep 4.
   // (the divisor check below keeps the documented contract: constant within each run of CPG consecutive samples)
   int per = CPG;
-  if (scr::env_int("SCR_PROBE_SPREAD", 1))
-    while (per > 1 && (k + per / 2 - 1) / (per / 2) <= ctx->sm_count) per /= 2;
+  if (scr::env_int("SCR_PROBE_SPREAD", 1))   // (probes launched side by side share the SMs: probe_share = how many)
+    while (per > 1 && (k + per / 2 - 1) / (per / 2) * ctx->probe_share <= ctx->sm_count) per /= 2;
   const int nitems = (k + per - 1) / per;
   std::vector<Item> items(nitems);
   for (int g = 0; g < nitems; ++g) {
@@ -1105,13 +1124,99 @@ int probe_t(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* w_
     p.noise_steps = max_iter;
   }
   rc = launch_step<T>(ctx, p, nitems, true, noise != nullptr);
-  if (rc == SCR_OK) {
+  if (rc == SCR_OK && !ctx->defer_sync) {
     cudaError_t e = cudaMemcpy(iters_out, ctx->d_piters, k * sizeof(int), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && normdiff_out) e = cudaMemcpy(normdiff_out, ctx->d_pnd, nd_count * sizeof(double), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = fail_cuda(ctx, e, "probe result copy");
   }
   cudaFree(d_noise);
   return rc;
+}
+
+// Probes of several lineage nodes at once (siblings: their sampled cells are final as soon as the parent's phase is).
+// Each probe is the launch scr_probe would make -- same kernel, same items, same noise keys, hence the same iteration
+// counts -- but on its own stream with its own per-launch buffers, so the launches (a node's 50 samples occupy 50 SMs
+// for up to max_iter strictly sequential steps) run side by side instead of one after the other.
+template <typename T>
+int probe_multi_t(scr_ctx* ctx, int32_t nprobes, const int32_t* k, const int64_t* sample_ids, const double* proj,
+                  const double* cnst, double dt, double sigma, double mu, double thresh, int32_t max_iter, int32_t avg_num,
+                  const uint64_t* seeds, uint32_t stream, int32_t* iters_out) {
+  const int n = ctx->op.n;
+  // saved per-launch fields of the context
+  struct Saved {
+    cudaStream_t stream; cudaEvent_t ev0, ev1; Item *d_items, *h_items; size_t items_cap; void *d_pc, *d_bias; int* d_counter;
+    int* d_piters; double* d_pnd; size_t piters_cap, pnd_cap;
+  } sv{ctx->stream, ctx->ev0, ctx->ev1, ctx->d_items, ctx->h_items, ctx->items_cap, ctx->d_pc, ctx->d_bias, ctx->d_counter,
+       ctx->d_piters, ctx->d_pnd, ctx->piters_cap, ctx->pnd_cap};
+  auto install = [&](scr_ctx::ProbeSlot& sl) {
+    ctx->stream = sl.stream; ctx->ev0 = sl.ev0; ctx->ev1 = sl.ev1; ctx->d_items = sl.d_items; ctx->h_items = sl.h_items;
+    ctx->items_cap = sl.items_cap; ctx->d_pc = sl.d_pc; ctx->d_bias = sl.d_bias; ctx->d_counter = sl.d_counter;
+    ctx->d_piters = sl.d_piters; ctx->d_pnd = sl.d_pnd; ctx->piters_cap = sl.piters_cap; ctx->pnd_cap = sl.pnd_cap;
+  };
+  auto take_back = [&](scr_ctx::ProbeSlot& sl) {   // buffers the call may have grown
+    sl.d_items = ctx->d_items; sl.h_items = ctx->h_items; sl.items_cap = ctx->items_cap;
+    sl.d_piters = ctx->d_piters; sl.d_pnd = ctx->d_pnd; sl.piters_cap = ctx->piters_cap; sl.pnd_cap = ctx->pnd_cap;
+  };
+  auto restore = [&]() {
+    ctx->stream = sv.stream; ctx->ev0 = sv.ev0; ctx->ev1 = sv.ev1; ctx->d_items = sv.d_items; ctx->h_items = sv.h_items;
+    ctx->items_cap = sv.items_cap; ctx->d_pc = sv.d_pc; ctx->d_bias = sv.d_bias; ctx->d_counter = sv.d_counter;
+    ctx->d_piters = sv.d_piters; ctx->d_pnd = sv.d_pnd; ctx->piters_cap = sv.piters_cap; ctx->pnd_cap = sv.pnd_cap;
+    ctx->defer_sync = false;
+    ctx->probe_share = 1;
+  };
+  int rc = SCR_OK;
+  int64_t off = 0;
+  std::vector<int64_t> offs(nprobes);
+  ctx->defer_sync = true;
+  ctx->probe_share = nprobes;
+  for (int i = 0; i < nprobes && rc == SCR_OK; ++i) {
+    scr_ctx::ProbeSlot& sl = ctx->probe_slots[i];
+    if (!sl.stream) {
+      cudaError_t e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreate(&sl.ev0);
+      if (e == cudaSuccess) e = cudaEventCreate(&sl.ev1);
+      if (e == cudaSuccess) e = cudaMalloc(&sl.d_counter, sizeof(int));
+      if (e == cudaSuccess) e = cudaMalloc(&sl.d_pc, static_cast<size_t>(ctx->op.n_pad) * 2 * ctx->esize());
+      if (e == cudaSuccess) e = cudaMalloc(&sl.d_bias, static_cast<size_t>(ctx->op.n_pad) * ctx->esize());
+      if (e != cudaSuccess) { restore(); return fail_cuda(ctx, e, "probe slot"); }
+    }
+    install(sl);
+    offs[i] = off;
+    rc = probe_t<T>(ctx, k[i], sample_ids + off, nullptr, proj + static_cast<size_t>(i) * n, cnst + static_cast<size_t>(i) * n, dt,
+                    sigma, mu, thresh, max_iter, avg_num, seeds[i], stream, nullptr, iters_out + off, nullptr);
+    take_back(sl);
+    off += k[i];
+  }
+  // collect: every launched probe is waited for even after an error
+  double ms_max = 0.0;
+  for (int i = 0; i < nprobes; ++i) {
+    scr_ctx::ProbeSlot& sl = ctx->probe_slots[i];
+    if (!sl.stream) continue;
+    cudaError_t e = cudaStreamSynchronize(sl.stream);
+    if (e != cudaSuccess && rc == SCR_OK) rc = fail_cuda(ctx, e, "probe (multi)");
+    if (rc == SCR_OK && sl.d_piters) {
+      e = cudaMemcpy(iters_out + offs[i], sl.d_piters, k[i] * sizeof(int), cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = fail_cuda(ctx, e, "probe result copy");
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sl.ev0, sl.ev1) == cudaSuccess) ms_max = std::max(ms_max, static_cast<double>(ms));
+    }
+  }
+  restore();
+  ctx->total_probe_ms += ms_max;     // the probes overlap: the longest one is what the batch took
+  ctx->total_probe_launches += nprobes;
+  ctx->last_ms = ms_max;
+  return rc;
+}
+
+void free_probe_slots(scr_ctx* ctx) {
+  for (auto& sl : ctx->probe_slots) {
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+    if (sl.ev0) cudaEventDestroy(sl.ev0);
+    if (sl.ev1) cudaEventDestroy(sl.ev1);
+    cudaFree(sl.d_items); cudaFreeHost(sl.h_items); cudaFree(sl.d_pc); cudaFree(sl.d_bias); cudaFree(sl.d_counter);
+    cudaFree(sl.d_piters); cudaFree(sl.d_pnd);
+    sl = scr_ctx::ProbeSlot();
+  }
 }
 
 void free_counts_scratch(scr_ctx* ctx) {
@@ -1194,6 +1299,7 @@ void scr_destroy(scr_ctx* ctx) {
     cudaFree(ctx->d_piters); cudaFree(ctx->d_pnd); cudaFree(ctx->d_gscratch); cudaFree(ctx->d_parena); cudaFree(ctx->d_mt_count); cudaFreeHost(ctx->h_psum);
     for (int b = 0; b < 2; ++b) { cudaFreeHost(ctx->h_xfer[b]); cudaFree(ctx->d_xfer[b]); if (ctx->ev_x[b]) cudaEventDestroy(ctx->ev_x[b]); }
     free_counts_scratch(ctx);
+    free_probe_slots(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]); if (ctx->ev_c[i]) cudaEventDestroy(ctx->ev_c[i]); }
@@ -1584,6 +1690,35 @@ int scr_probe(scr_ctx* ctx, int32_t k, const int64_t* sample_ids, const double* 
   if (ctx->prec == SCR_F64)
     return probe_t<double>(ctx, k, sample_ids, w_div, proj, cnst, dt, sigma, mu, thresh, max_iter, avg_num, seed, stream, noise, iters_out, normdiff_out);
   return probe_t<float>(ctx, k, sample_ids, w_div, proj, cnst, dt, sigma, mu, thresh, max_iter, avg_num, seed, stream, noise, iters_out, normdiff_out);
+}
+
+int scr_probe_multi(scr_ctx* ctx, int32_t nprobes, const int32_t* k, const int64_t* sample_ids, const double* proj,
+                    const double* cnst, double dt, double sigma, double mu, double thresh, int32_t max_iter, int32_t avg_num,
+                    const uint64_t* seeds, uint32_t stream, int32_t* iters_out) {
+  NEED_GPU();
+  NvtxRange nvtx("scr_probe_multi (sibling lineage nodes)", nprobes, max_iter);
+  if (!ctx->d_state) return fail(ctx, SCR_E_STATE, "cells not allocated");
+  if (nprobes <= 0 || !k || !sample_ids || !proj || !cnst || !seeds || !iters_out || max_iter <= 0 || avg_num <= 0)
+    return fail(ctx, SCR_E_ARG, "bad arguments");
+  if (ctx->readout_only) return fail(ctx, SCR_E_STATE, "read-out context (scr_set_genes): no network to step with");
+  for (int i = 0; i < nprobes; ++i)
+    if (k[i] <= 0) return fail(ctx, SCR_E_ARG, "empty probe");
+  const bool dense = ctx->dense_mode && scr::env_int("SCR_DENSE_PROBE", 1);
+  // side by side only where the launches are independent of shared scratch: the sparse stepper with on-chip cell groups
+  if (dense || ctx->gstate || nprobes == 1 || nprobes > scr_ctx::kProbeSlots || scr::env_int("SCR_PROBE_MULTI", 1) == 0) {
+    int64_t off = 0;
+    const int n = ctx->op.n;
+    for (int i = 0; i < nprobes; ++i) {
+      const int rc = scr_probe(ctx, k[i], sample_ids + off, nullptr, proj + static_cast<size_t>(i) * n, cnst + static_cast<size_t>(i) * n,
+                               dt, sigma, mu, thresh, max_iter, avg_num, seeds[i], stream, nullptr, iters_out + off, nullptr);
+      if (rc) return rc;
+      off += k[i];
+    }
+    return SCR_OK;
+  }
+  if (ctx->prec == SCR_F64)
+    return probe_multi_t<double>(ctx, nprobes, k, sample_ids, proj, cnst, dt, sigma, mu, thresh, max_iter, avg_num, seeds, stream, iters_out);
+  return probe_multi_t<float>(ctx, nprobes, k, sample_ids, proj, cnst, dt, sigma, mu, thresh, max_iter, avg_num, seeds, stream, iters_out);
 }
 
 int scr_gene_sums(scr_ctx* ctx, double* sums_out) {

@@ -212,6 +212,27 @@ class Engine:
             self._clear_bias()
         return (iters, trace) if want_trace else iters
 
+    def probe_multi(self, samples, projs, consts, seeds, dt=0.01, sigma=0.05, mu=0.0, thresh=0.1, max_iter=500,
+                    avg_num=20, stream=STREAM_PROBE):
+        """``probe`` for several lineage nodes at once (scr_probe_multi): ``samples`` is a list of id arrays, ``projs`` /
+        ``consts`` the nodes' vectors, ``seeds`` one per node.  Returns the list of iteration arrays -- what separate
+        ``probe`` calls return; the launches of sibling nodes run side by side on the GPU."""
+        if np.ndim(mu) != 0:                                   # per-gene mean levels: the drive bias is a context-wide setting
+            return [self.probe(s, p, c, dt=dt, sigma=sigma, mu=mu, thresh=thresh, max_iter=max_iter, avg_num=avg_num,
+                               seed=sd, stream=stream) for s, p, c, sd in zip(samples, projs, consts, seeds)]
+        ids = [np.ascontiguousarray(s, dtype=np.int64) for s in samples]
+        k = np.array([len(s) for s in ids], dtype=np.int32)
+        allids = np.ascontiguousarray(np.concatenate(ids))
+        P = np.ascontiguousarray(np.stack([_f64(p) for p in projs]))
+        Cn = np.ascontiguousarray(np.stack([_f64(c) for c in consts]))
+        sd = np.array([int(v) & (2 ** 64 - 1) for v in seeds], dtype=np.uint64)
+        iters = np.zeros(len(allids), dtype=np.int32)
+        self._check(self._lib.scr_probe_multi(self._ctx, len(ids), _ptr(k, C.c_int32), _ptr(allids, C.c_int64),
+                                              _ptr(P, C.c_double), _ptr(Cn, C.c_double), dt, sigma, float(mu), thresh,
+                                              int(max_iter), int(avg_num), sd.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                              int(stream), _ptr(iters, C.c_int32)))
+        return np.split(iters, np.cumsum(k)[:-1])
+
     def gene_sums(self):
         out = np.zeros(self.n)
         self._check(self._lib.scr_gene_sums(self._ctx, _ptr(out, C.c_double)))

@@ -190,7 +190,12 @@ class LineageSimulation:
             mem_glob = mem[(mem >= self.lo) & (mem < self.hi)]
             below_loc = below[(below >= self.lo) & (below < self.hi)] - self.lo
             self.plan.append(dict(node=node, members=mem, mem_glob=mem_glob, mem_loc=mem_glob - self.lo, below_loc=below_loc,
-                                  ids=np.concatenate([mem_glob - self.lo, below_loc])))
+                                  ids=np.concatenate([mem_glob - self.lo, below_loc]), parent=None))
+        by_id = {int(p["node"].identifier): p for p in self.plan}
+        for p in self.plan:
+            for child in p["node"].children:
+                if int(child) in by_id:
+                    by_id[int(child)]["parent"] = int(p["node"].identifier)
         return self
 
     def _member_uniforms(self, p):
@@ -252,22 +257,48 @@ class LineageSimulation:
             draws = [pool.submit(self._member_uniforms, p) for p in live]
             size_f = pool.submit(self._size_factors, cellRadiusDisp) if do_counts else None
             base_f = None
+            # Probe samples of every node, drawn in the order the reference draws them (MS:644 inside the depth-first walk).
+            # The probes themselves are batched: a node's sampled cells are final as soon as its PARENT's phase is, so when
+            # the walk reaches the first child of a node the probes of all its children go out together (scr_probe_multi:
+            # side by side on the GPU).  Same samples, same noise keys, same T as probing each node right before its phase.
+            picks, T_of, stepped = None, {}, set()
+            if fixed_iterations is None:
+                picks = [p["members"][random.sample(range(len(p["members"])), cellsToSample)] for p in live]
+
+            live_ids = {int(p["node"].identifier) for p in live}
+
+            def probe_ready(first):
+                # ready = not probed yet and nothing above it is still to be stepped (an empty parent type never steps: MS:579-580)
+                batch = [j for j in range(first, len(live)) if j not in T_of
+                         and (live[j]["parent"] not in live_ids or live[j]["parent"] in stepped)]
+                mine = [picks[j][(picks[j] >= self.lo) & (picks[j] < self.hi)] - self.lo for j in batch]
+                totals = np.zeros(len(batch))
+                have = [b for b, m in enumerate(mine) if len(m)]
+                if have:
+                    kw = dict(dt=timeStep, sigma=noiseDisp, mu=geneMeanLevels, thresh=convergenceThreshold,
+                              max_iter=maxNumIterations, avg_num=convDistAvgNum, stream=STREAM_PROBE)
+                    nodes = [live[batch[b]]["node"] for b in have]
+                    seeds = [self.seed + 7919 * (int(nd.identifier) + 1) for nd in nodes]
+                    if len(have) == 1 or getattr(self.eng, "probe_multi", None) is None:
+                        its = [self.eng.probe(mine[b], nd.proj, nd.const, seed=sd, **kw) for b, nd, sd in zip(have, nodes, seeds)]
+                    else:
+                        its = self.eng.probe_multi([mine[b] for b in have], [nd.proj for nd in nodes],
+                                                   [nd.const for nd in nodes], seeds, **kw)
+                    for b, it in zip(have, its):
+                        totals[b] = float(it.sum())
+                totals = self.comm.allreduce_sum(totals)
+                for b, j in enumerate(batch):
+                    T_of[j] = int(float(totals[b]) / cellsToSample) - convDistAvgNum
+
             for i, (p, draw) in enumerate(zip(live, draws)):
                 node, mem = p["node"], p["members"]
                 if fixed_iterations is None:
-                    pick = mem[random.sample(range(len(mem)), cellsToSample)]    # same stream as MS:644
-                    mine = pick[(pick >= self.lo) & (pick < self.hi)] - self.lo
-                    total = 0.0
-                    if len(mine):
-                        it = self.eng.probe(mine, node.proj, node.const, dt=timeStep, sigma=noiseDisp, mu=geneMeanLevels,
-                                            thresh=convergenceThreshold, max_iter=maxNumIterations,
-                                            avg_num=convDistAvgNum, seed=self.seed + 7919 * (int(node.identifier) + 1),
-                                            stream=STREAM_PROBE)
-                        total = float(it.sum())
-                    total = float(self.comm.allreduce_sum(np.array([total]))[0])
-                    T = int(total / cellsToSample) - convDistAvgNum
+                    if i not in T_of:
+                        probe_ready(i)
+                    T = T_of[i]
                 else:
                     T = int(fixed_iterations)
+                stepped.add(int(node.identifier))
                 self.node_iterations[int(node.identifier)] = T
                 ids, nmem = p["ids"], len(p["mem_loc"])
                 steps = np.full(len(ids), T, dtype=np.int32)                     # descendants step T (MS:599-605)

@@ -354,3 +354,36 @@ def test_large_gene_count_falls_back_to_global_state(prec, tol):
         s.run_phase(np.arange(50), st, np.ones(300), np.zeros(300), seed=8)
         outs.append(s.get_states())
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_probes_of_sibling_nodes_side_by_side_equal_separate_probes(prec):
+    """scr_probe_multi: the probes of several lineage nodes (own proj / const / seed each) launched together return the
+    iteration counts of separate scr_probe calls, sample for sample; a dense context takes the sequential fallback."""
+    from scrutiny_b200 import engine
+    from test_gpu_parity import sparse_net
+    n, cells = 700, 400
+    rng = np.random.RandomState(12)
+    W = sparse_net(n, 5, gain=1.0 / 0.3)
+    e = engine.Engine(0, prec)
+    e.set_network(W)
+    e.alloc_cells(cells, 2 ** 32 + 9)
+    e.set_states(rng.uniform(-1, 1, size=(n, cells)))
+    samples = [rng.choice(cells, size=k, replace=False) for k in (50, 50, 7, 33)]
+    projs, consts = [], []
+    for _ in samples:
+        proj = (rng.rand(n) > 0.05).astype(float)
+        projs.append(proj)
+        consts.append(np.where(proj == 0, rng.choice([-1.0, 1.0], size=n), 0.0))
+    seeds = [1337 + 7919 * (i + 1) for i in range(len(samples))]
+    kw = dict(thresh=0.25, max_iter=300, avg_num=10)
+    want = [e.probe(s, p, c, seed=sd, **kw) for s, p, c, sd in zip(samples, projs, consts, seeds)]
+    e.probe_kernel_stats(reset=True)
+    got = e.probe_multi(samples, projs, consts, seeds, **kw)
+    assert e.probe_kernel_stats()[1] == len(samples)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert max(int(w.max()) for w in want) > 20 and len({int(w.sum()) for w in want}) > 1
+    again = [e.probe(s, p, c, seed=sd, **kw) for s, p, c, sd in zip(samples, projs, consts, seeds)]   # per-launch buffers were restored
+    for g, w in zip(again, want):
+        assert np.array_equal(g, w)

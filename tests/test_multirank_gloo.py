@@ -41,6 +41,10 @@ class OracleEngine:
         it, _, _ = self.fo.probe(self.W, self.X[np.asarray(sample_ids)], proj, const, dt, noise, thresh, max_iter, avg_num, mu)
         return it.astype(np.int32)
 
+    def probe_multi(self, samples, projs, consts, seeds, **kw):
+        self.multi_calls = getattr(self, "multi_calls", 0) + 1
+        return [self.probe(s, p, c, seed=sd, **kw) for s, p, c, sd in zip(samples, projs, consts, seeds)]
+
     def gene_sums(self):
         return self.X.sum(axis=0)
 
@@ -187,3 +191,29 @@ def test_two_ranks_reproduce_one_rank(tmp_path):
         assert np.allclose(np.concatenate([parts[0][key], parts[1][key]]), one[key], rtol=1e-13, atol=1e-13), key
     assert float(parts[0]["glob"]) == float(one["glob"]) == float(one["iters"].sum())
     assert one["iters"].max() > 0 and len(np.unique(one["types"])) == 3
+
+
+def test_batched_sibling_probes_give_the_sequential_schedule(tmp_path):
+    """run_all probes the children of a node together right after the parent's phase (scr_probe_multi).  An engine without
+    probe_multi is probed node by node in the same order; an engine with it gets the siblings in one call.  Iteration
+    counts, states and bookkeeping are identical, and both equal probing each node right before its own phase (run_node,
+    the reference's order) in the T they find."""
+    sys.path.insert(0, ROOT)
+    from scrutiny_b200.simulate import Comm, LineageSimulation
+    n, cells, W, tree, x0 = build_case()
+    kw = dict(seed=99, cellsToSample=6, maxNumIterations=60, convDistAvgNum=5, convergenceThreshold=0.6)
+
+    class NodeByNodeEngine(OracleEngine):
+        probe_multi = None
+
+    def run(with_multi):
+        eng = (OracleEngine if with_multi else NodeByNodeEngine)(W, cells, 0)
+        eng.set_states_broadcast(x0)
+        sim = LineageSimulation(eng, cells, 0, cells, comm=Comm(single=True), seed=99)
+        return eng, sim, sim.run_all(tree, **kw)
+
+    e1, s1, r1 = run(True)
+    e2, s2, r2 = run(False)
+    assert getattr(e1, "multi_calls", 0) == 1 and getattr(e2, "multi_calls", 0) == 0   # nodes 1 and 2 are siblings
+    assert s1.node_iterations == s2.node_iterations and len(s1.node_iterations) == 3
+    assert np.array_equal(e1.X, e2.X) and np.array_equal(r1["iterations"], r2["iterations"])
