@@ -57,7 +57,8 @@ def run(name):
         node.cellTypeMembers = np.asarray(node.cellTypeMembers, dtype=np.int64)
         node.childCellTypeMembers = np.asarray(node.childCellTypeMembers, dtype=np.int64)
     sim.prepare(tree)
-    out = np.empty((cells, n), dtype=np.uint8)                # compact read-out: bytes + overflow list (scr_counts_compact)
+    import torch                                              # (only for a page-locked host buffer, like bench.py's e2e leg)
+    out = torch.empty((cells, n), dtype=torch.uint8, pin_memory=True).numpy()   # compact read-out: bytes + overflow list (scr_counts_compact)
     best = None
     for rep in range(4):
         e.set_states_broadcast(x0)
