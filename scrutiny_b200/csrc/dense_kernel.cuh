@@ -265,10 +265,15 @@ dense_step_kernel(const __grid_constant__ CUtensorMap tm_ahi0, const __grid_cons
             // every CTA of this cell tile has stored step s - 1 (and is done reading the buffer step s overwrites)
             const unsigned want = static_cast<unsigned>(p.n_tiles) * static_cast<unsigned>(s - p.s0);
             unsigned seen, spins = 0;
+            unsigned long long t0 = 0, t1;
             for (;;) {
               asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.mt_count + mt) : "memory");
               if (seen >= want) break;
-              if (++spins > (1u << 26)) { atomicMax(p.err, kErrDenseStall); break; }   // never hang the device
+              if ((++spins & 1023u) == 0) {   // never hang the device: 4 s of wall clock, then the error word
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t0 == 0) t0 = t1;
+                if (t1 - t0 > 4000000000ULL) { atomicMax(p.err, kErrDenseStall); break; }
+              }
             }
             asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of the other CTAs -> our TMA reads
           }
