@@ -184,6 +184,17 @@ int fail_cuda(const scr_ctx* ctx, cudaError_t e, const char* what) {
 
 int align16(int x) { return (x + 15) & ~15; }
 
+// Upload from pageable host memory, ordered before everything the context launches afterwards.  A plain cudaMemcpy is NOT
+// enough here: it returns once the data is staged, the DMA into device memory may still be in flight, and the context's
+// streams are non-blocking (they do not synchronise with the legacy default stream the copy runs on) -- a kernel launched
+// right after could read the old bytes.  The copy is therefore issued on the context's stream and waited for, which also
+// orders it before the work of the context's other streams.
+cudaError_t upload_sync(scr_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  return e;
+}
+
 // table blob for one block-to-warp assignment (wq warps, list bounds wblk_ptr, blocks wblk)
 void build_tab(const PackedOperator& op, int wq, const std::vector<int>& wblk_ptr, const std::vector<int>& wblk,
                std::vector<unsigned char>& tab, bool large) {
@@ -491,7 +502,7 @@ int upload_noise(scr_ctx* ctx, const double* noise, size_t count, T** d_noise) {
   std::vector<T> h(count);
   for (size_t i = 0; i < count; ++i) h[i] = static_cast<T>(noise[i]);
   CK(cudaMalloc(d_noise, std::max<size_t>(count, 1) * sizeof(T)));
-  CK(cudaMemcpy(*d_noise, h.data(), count * sizeof(T), cudaMemcpyHostToDevice));
+  CK(upload_sync(ctx, *d_noise, h.data(), count * sizeof(T)));
   return SCR_OK;
 }
 
@@ -1362,16 +1373,16 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
     CK(cudaMalloc(&ctx->d_inv, o.n * sizeof(int)));
     CK(cudaMalloc(&ctx->d_pc, static_cast<size_t>(o.n_pad) * 2 * ctx->esize()));
     CK(cudaMalloc(&ctx->d_bias, static_cast<size_t>(o.n_pad) * ctx->esize()));
-    CK(cudaMemcpy(ctx->d_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+    CK(upload_sync(ctx, ctx->d_tab, tab.data(), tab.size()));
     if (o.wq_wide == 16) {
       std::vector<unsigned char> tab_wide;
       build_tab(o, 16, o.wblk_ptr_wide, o.wblk_wide, tab_wide, ctx->gstate);
       CK(cudaMalloc(&ctx->d_tab_wide, tab_wide.size()));
-      CK(cudaMemcpy(ctx->d_tab_wide, tab_wide.data(), tab_wide.size(), cudaMemcpyHostToDevice));
+      CK(upload_sync(ctx, ctx->d_tab_wide, tab_wide.data(), tab_wide.size()));
     }
-    CK(cudaMemcpy(ctx->d_w, w.data(), w.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_perm, o.perm.data(), o.n_pad * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_inv, o.inv.data(), o.n * sizeof(int), cudaMemcpyHostToDevice));
+    CK(upload_sync(ctx, ctx->d_w, w.data(), w.size()));
+    CK(upload_sync(ctx, ctx->d_perm, o.perm.data(), o.n_pad * sizeof(int)));
+    CK(upload_sync(ctx, ctx->d_inv, o.inv.data(), o.n * sizeof(int)));
     if (dense) {
       // B operands of the split-precision GEMM (dense_kernel.cuh): hi / lo of W in the chosen encoding
       namespace D = scr::dense;
@@ -1398,8 +1409,8 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
           }
         CK(cudaMalloc(&ctx->d_whi, cnt * 2));
         CK(cudaMalloc(&ctx->d_wlo, cnt * 2));
-        CK(cudaMemcpy(ctx->d_whi, whi.data(), cnt * 2, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(ctx->d_wlo, wlo.data(), cnt * 2, cudaMemcpyHostToDevice));
+        CK(upload_sync(ctx, ctx->d_whi, whi.data(), cnt * 2));
+        CK(upload_sync(ctx, ctx->d_wlo, wlo.data(), cnt * 2));
       } else {
         ctx->dense_acc_scale = 1.f;
         std::vector<float> whi(cnt, 0.f), wlo(cnt, 0.f);
@@ -1416,8 +1427,8 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
           }
         CK(cudaMalloc(&ctx->d_whi, cnt * 4));
         CK(cudaMalloc(&ctx->d_wlo, cnt * 4));
-        CK(cudaMemcpy(ctx->d_whi, whi.data(), cnt * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(ctx->d_wlo, wlo.data(), cnt * 4, cudaMemcpyHostToDevice));
+        CK(upload_sync(ctx, ctx->d_whi, whi.data(), cnt * 4));
+        CK(upload_sync(ctx, ctx->d_wlo, wlo.data(), cnt * 4));
       }
       const int es = ctx->dense_kind == D::kF16 ? 2 : 4;
       rc2 = make_tmap(ctx, &ctx->tm_bhi, ctx->d_whi, ld, ld, ld, D::BN, es);
@@ -1455,8 +1466,8 @@ int scr_set_genes(scr_ctx* ctx, int32_t n) {
     const PackedOperator& o = ctx->op;
     CK(cudaMalloc(&ctx->d_perm, o.n_pad * sizeof(int)));
     CK(cudaMalloc(&ctx->d_inv, o.n * sizeof(int)));
-    CK(cudaMemcpy(ctx->d_perm, o.perm.data(), o.n_pad * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_inv, o.inv.data(), o.n * sizeof(int), cudaMemcpyHostToDevice));
+    CK(upload_sync(ctx, ctx->d_perm, o.perm.data(), o.n_pad * sizeof(int)));
+    CK(upload_sync(ctx, ctx->d_inv, o.inv.data(), o.n * sizeof(int)));
   }
   ctx->readout_only = true;
   ctx->has_net = true;
@@ -1783,7 +1794,7 @@ int counts_impl(scr_ctx* ctx, int64_t cell_begin, int64_t cell_count, const doub
     std::vector<float> lg(scr::kLgamTable);
     for (int k = 0; k < scr::kLgamTable; ++k) lg[k] = static_cast<float>(std::lgamma(static_cast<double>(k) + 1.0));
     CK(cudaMalloc(&ctx->d_lgam, lg.size() * sizeof(float)));
-    CK(cudaMemcpy(ctx->d_lgam, lg.data(), lg.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(upload_sync(ctx, ctx->d_lgam, lg.data(), lg.size() * sizeof(float)));
   }
   const unsigned long long dev_ovf_cap = esz < 4 ? static_cast<unsigned long long>(std::max<int64_t>(ovf_cap, 0)) : 0ULL;
   if (esz < 4) {
@@ -1930,7 +1941,7 @@ int scr_debug_philox(scr_ctx* ctx, int64_t count, const uint32_t* ctr4, uint32_t
   uint32_t *d_in = nullptr, *d_out = nullptr;
   CK(cudaMalloc(&d_in, count * 16));
   CK(cudaMalloc(&d_out, count * 16));
-  CK(cudaMemcpy(d_in, ctr4, count * 16, cudaMemcpyHostToDevice));
+  CK(upload_sync(ctx, d_in, ctr4, count * 16));
   scr::debug_philox_kernel<<<static_cast<unsigned>((count + 127) / 128), 128, 0, ctx->stream>>>(count, d_in, k0, k1, d_out);
   ctx->launches++;
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
