@@ -637,7 +637,8 @@ def run_extras(args, env, rig, counts_dev, want, peak, peak_source, dev):
                     "single type, stepping only" % cells, "value": t["value"], "ms_per_step": t["ms_per_step"], "n_gpus": world,
                     "genes": r.n, "nnz": r.nnz, "dtype": "f32 via " + enc, "node_iterations": t["node_iterations"],
                     "kernel_launches": t["kernel_launches"], "kernel_cell_steps_per_s": ks,
-                    "roofline": {"bound": "tensor", "kernel": "scr::dense::dense_step_kernel (tcgen05 %s, fused update)" % enc,
+                    "roofline": {"bound": "tensor", "kernel": "scr::dense::dense_pair_kernel (tcgen05 cta_group::2, %s, fused update; "
+                                 "the phase's last steps: dense_step_kernel, steps inside the launch)" % enc,
                                  "achieved": issued, "useful": issued / 3.0, "peak": mm_peak, "unit": "TFLOP/s",
                                  "frac": issued / mm_peak,
                                  "peak_source": "torch.matmul %s 8192^3 timed in this run, %d back to back (sustained)" % (
