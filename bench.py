@@ -16,7 +16,7 @@ over all cells / time.
 `value`: inputs resident in HBM.  `e2e`: the same pass through the C ABI with HOST buffers (network, initial state and
 schedules copied in, this rank's count shard copied out to pinned memory).  `extra`: the other paths north_star names,
 measured after the headline in the same process -- TRRUST and the reference's default exponent 2.05 on the sparse stepper,
-the float64 parity context, config c4 on the tcgen05 3xTF32 stepper (with a TF32 matmul timed in-run as its denominator),
+the float64 parity context, config c4 on the tcgen05 split-precision stepper (with a cuBLAS matmul of its operand type timed in-run as its denominator),
 the count kernel alone, the alpha search, and (N > 1) the strong-scaling point: 10^6 cells in TOTAL split over the ranks.
 """
 import argparse
