@@ -1397,7 +1397,7 @@ int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* row
         double wmax = 0.0;
         for (int64_t e = 0; e < nnz; ++e) wmax = std::max(wmax, std::fabs(val[e]));
         const float wmaxf = static_cast<float>(wmax);
-        const double sw = wmaxf > 0.f && std::isfinite(wmaxf) ? std::ldexp(1.0, 14 - std::ilogb(wmaxf)) : 1.0;
+        const double sw = wmaxf > 0.f && std::isfinite(wmaxf) ? std::ldexp(1.0, std::max(-100, std::min(100, 14 - std::ilogb(wmaxf)))) : 1.0;
         ctx->dense_acc_scale = static_cast<float>(1.0 / (static_cast<double>(D::kStateScale) * sw));
         std::vector<__half> whi(cnt, __float2half_rn(0.f)), wlo(cnt, __float2half_rn(0.f));
         for (int r = 0; r < n; ++r)
