@@ -84,3 +84,61 @@ def test_random_case_against_oracle(seed):
         e.set_states(X0.T.copy())
         e.run_phase(ids, steps, proj, const, step_base=base, noise=dump, mu=mu)
         assert np.max(np.abs(e.get_states().T - free)) <= (1e-12 if prec == "f64" else 2e-6)
+
+
+DENSE_SCHEDULES = [
+    {},                                                                        # resident-W / narrow tiles, steps inside the launch
+    {"SCR_DENSE_RESB": "0"},                                                   # narrow (or wide) tiles, steps inside
+    {"SCR_DENSE_INSIDE": "0"},                                                 # one launch per timestep (narrow tiles or CTA pairs)
+    {"SCR_DENSE_NARROW": "0"},                                                 # wide tiles, steps inside
+    {"SCR_DENSE_NARROW": "0", "SCR_DENSE_INSIDE": "0"},                        # CTA pairs
+    {"SCR_DENSE_NARROW": "0", "SCR_DENSE_INSIDE": "0", "SCR_DENSE_PAIR": "0"},  # single-CTA wide tiles per timestep
+]
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_dense_case_on_every_schedule_against_oracle(seed, monkeypatch):
+    """The GEMM stepper on shapes the fixed cases do not hit -- n and cell counts around the tile sizes (32 / 64 / 128 / 256),
+    one cell, odd numbers of cell tiles (the CTA-pair kernel's half-empty last pair), K extents shorter than the ring --
+    cycling through the schedules and both operand encodings, supplied noise, ragged steps; then the probe of the same
+    context against the oracle's (iteration counts within one step: float32 traces against float64)."""
+    from scrutiny_b200 import engine
+    rng = np.random.RandomState(7000 + seed)
+    for k, v in DENSE_SCHEDULES[seed % len(DENSE_SCHEDULES)].items():
+        monkeypatch.setenv(k, v)
+    if (seed // len(DENSE_SCHEDULES)) % 2:
+        monkeypatch.setenv("SCR_DENSE_KIND", "tf32")
+    n = int(rng.choice([64, 65, 127, 128, 200, 256, 257, 500, 513, 700, 1000, 1100]))
+    cells = int(rng.choice([1, 50, 128, 129, 255, 256, 257, 400, 700]))
+    W = rng.randn(n, n) * (rng.rand(n, n) < rng.uniform(0.06, 0.9))
+    W *= rng.uniform(0.5, 4.0) / np.abs(W).sum(axis=1).max()
+    smax = int(rng.randint(1, 9))
+    X0 = rng.uniform(-1, 1, size=(cells, n))
+    proj = (rng.rand(n) > 0.15).astype(float)
+    const = np.where(proj == 0, rng.uniform(-1, 1, size=n), 0.0)
+    mu = float(rng.choice([0.0, 0.0, 0.1]))
+    ids = rng.permutation(cells)[: rng.randint(1, cells + 1)]
+    steps = rng.randint(0, smax + 1, size=len(ids))
+    steps[rng.randint(len(ids))] = smax
+    noise = (0.05 * rng.randn(len(ids), smax, n)).astype(np.float32).astype(np.float64)
+    e = engine.Engine(device=0, precision="f32")
+    e.set_network(W)
+    assert e.layout()["dense_stepper"] == 1
+    e.alloc_cells(cells, int(rng.randint(0, 10 ** 6)))
+    e.set_states(X0.T.copy())
+    e.run_phase(ids, steps, proj, const, step_base=rng.randint(0, 1000, size=len(ids)), noise=noise, mu=mu)
+    got = e.get_states().T
+    want = X0.astype(np.float32).astype(np.float64)
+    Xp = want[ids]
+    op = fo.as_operator(W)
+    fo.run_phase(op, Xp, steps, proj, const, 0.01, noise, mu=mu)
+    want[ids] = Xp
+    err = np.max(np.abs(got - want))
+    assert err <= 1e-4, (n, cells, len(ids), smax, e.layout(), err)
+    if seed % 4 == 0:
+        k = min(cells, 9)
+        pn = (0.05 * rng.randn(k, 40, n)).astype(np.float32).astype(np.float64)
+        e.set_states(X0.T.copy())
+        it = e.probe(np.arange(k), proj, const, thresh=0.5, max_iter=40, avg_num=5, noise=pn, mu=mu)
+        ref, _, _ = fo.probe(op, X0[:k].astype(np.float32).astype(np.float64), proj, const, 0.01, pn, 0.5, 40, 5, mu)
+        assert np.max(np.abs(it - ref)) <= 1, (it, ref)
