@@ -404,3 +404,8 @@ def analyzeDataBeforeTransformation(*args, **kwargs):
 
 def analyzeSCRNAseqData(*args, **kwargs):
     """MS:894-1032 only draws plots / PCA diagnostics; out of scope (no-op)."""
+
+
+def plotSCRNAseqData(*args, **kwargs):
+    """MS:970-1032 only draws PCA / t-SNE plots of the count matrix; out of scope (no-op, kept so that a script written
+    against the reference runs unchanged)."""

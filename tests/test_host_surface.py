@@ -138,3 +138,35 @@ def test_scalable_tree_assignment():
     assert sorted(tree[0].childCellTypeMembers.tolist()) == sorted(np.concatenate([tree[k].cellTypeMembers for k in (1, 2, 3, 4)]).tolist())
     assert np.array_equal((projM == 0).sum(axis=1) >= 0, np.ones(5, bool)) and np.all((projM == 0) | (projM == 1))
     assert np.array_equal(constM[projM == 1], np.zeros((projM == 1).sum()))
+
+
+def test_module_surface_matches_the_reference():
+    """Drop-in boundary: every public function of the reference's MatriSeq module (tests/golden/
+    matriseq_signatures.json, written from the unmodified module by oracle/make_signatures.py) exists here; the functions of
+    the simulation path take the reference's parameters first, in order, with the reference's defaults, and anything added
+    comes after them with a default.  The plotting functions are accepted with any arguments (documented no-ops);
+    ``addTreeChildren`` is the reference's private recursion helper of ``formCellTypeTree`` (a closure here)."""
+    import inspect
+    import json
+    import os
+    import scrutiny_b200.MatriSeq as ms
+    table = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "matriseq_signatures.json")))
+    no_ops = {"analyzeDataBeforeTransformation", "analyzeSCRNAseqData", "plotSCRNAseqData"}
+    private = {"addTreeChildren"}
+    assert len(table) == 16
+    for name, ref in table.items():
+        if name in private:
+            continue
+        assert hasattr(ms, name), name
+        if name in no_ops:
+            assert getattr(ms, name)(*range(len(ref["params"]))) is None
+            continue
+        ours = list(inspect.signature(getattr(ms, name)).parameters.values())
+        for i, (pname, pdefault) in enumerate(ref["params"]):
+            assert ours[i].name == pname, (name, i, ours[i].name, pname)
+            if pdefault is None:
+                assert ours[i].default is inspect.Parameter.empty, (name, pname)
+            else:
+                assert repr(ours[i].default) == pdefault, (name, pname, ours[i].default, pdefault)
+        for extra in ours[len(ref["params"]):]:
+            assert extra.default is not inspect.Parameter.empty, (name, extra.name)
