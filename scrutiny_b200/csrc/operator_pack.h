@@ -330,6 +330,100 @@ struct OrderCache {
   }
 };
 
+// Entry order inside the rows under the FINAL gene order (positions fixed): which of a row's entries sits in which slot is
+// free, and the eight entries one LDS.128 gathers for a quarter warp should fall into eight different bank groups (or be
+// the same row).  Two deterministic descents over exchanges of two entries of one row, accepted when the affected read
+// sets get cheaper under BankModel's cost:
+//   tiles   the first min(in-degree, cap) entries of the eight rows of a quarter warp, slot against slot;
+//   chunks  the entries beyond the cap of a long row, chunk slot against chunk slot (a hub target with 300 regulators is
+//           38 chunks: its eight-chunk groups read 8 x 8 entries that can be dealt out one bank group per read).
+inline void entry_bank_pass(int n, const int32_t* rowptr, int32_t* col, double* val, const std::vector<int>& order,
+                            const std::vector<int>& indeg, int cap, int lv, int nlong) {
+  std::vector<int> pos(n);
+  for (int i = 0; i < n; ++i) pos[order[i]] = i;
+  auto mult = [&](const int* p, int cnt) {   // most distinct positions sharing a bank group (BankModel::cost)
+    int best = cnt > 0 ? 1 : 0;
+    for (int a = 0; a < cnt; ++a) {
+      int same = 1;
+      bool first = true;
+      for (int b = 0; b < a; ++b) if (p[b] == p[a]) first = false;
+      if (!first) continue;
+      for (int b = a + 1; b < cnt; ++b) {
+        if ((p[b] & 7) != (p[a] & 7) || p[b] == p[a]) continue;
+        bool dup = false;
+        for (int c = a + 1; c < b; ++c) dup |= p[c] == p[b];
+        if (!dup) ++same;
+      }
+      best = std::max(best, same);
+    }
+    return best;
+  };
+  auto swap_entries = [&](int64_t a, int64_t b) { std::swap(col[a], col[b]); std::swap(val[a], val[b]); };
+  // ---- tiles ----
+  for (int m = 0; m * 8 < n; ++m) {
+    const int i0 = m * 8, i1 = std::min(n, i0 + 8);
+    auto slot_cost = [&](int k) {
+      int p[8], cnt = 0;
+      for (int i = i0; i < i1; ++i) {
+        const int r = order[i];
+        if (k < std::min(indeg[r], cap)) p[cnt++] = pos[col[rowptr[r] + k]];
+      }
+      return mult(p, cnt);
+    };
+    for (int pass = 0; pass < 4; ++pass) {
+      bool improved = false;
+      for (int i = i0; i < i1; ++i) {
+        const int r = order[i], d = std::min(indeg[r], cap);
+        for (int k1 = 0; k1 < d; ++k1)
+          for (int k2 = k1 + 1; k2 < d; ++k2) {
+            const int before = slot_cost(k1) + slot_cost(k2);
+            if (before <= 2) continue;
+            swap_entries(rowptr[r] + k1, rowptr[r] + k2);
+            if (slot_cost(k1) + slot_cost(k2) < before) improved = true;
+            else swap_entries(rowptr[r] + k1, rowptr[r] + k2);
+          }
+      }
+      if (!improved) break;
+    }
+  }
+  // ---- chunks of the long rows (order positions 0 .. nlong-1) ----
+  std::vector<std::pair<int, int>> chunks;   // (row gene, first entry)
+  for (int i = 0; i < nlong; ++i)
+    for (int e = cap; e < indeg[order[i]]; e += lv) chunks.emplace_back(order[i], e);
+  const int nch = static_cast<int>(chunks.size());
+  auto set_cost = [&](int g, int k) {        // read set: chunks 8g .. 8g+7 at slot k
+    int p[8], cnt = 0;
+    for (int v = g * 8; v < std::min(nch, g * 8 + 8); ++v)
+      if (chunks[v].second + k < indeg[chunks[v].first]) p[cnt++] = pos[col[rowptr[chunks[v].first] + chunks[v].second + k]];
+    return mult(p, cnt);
+  };
+  std::vector<int> first_chunk(n, -1);
+  for (int v = nch - 1; v >= 0; --v) first_chunk[chunks[v].first] = v;
+  for (int i = 0; i < nlong; ++i) {
+    const int r = order[i], extra = indeg[r] - cap;
+    if (extra < 2 || first_chunk[r] < 0) continue;
+    auto where = [&](int e, int& g, int& k) { const int v = first_chunk[r] + e / lv; g = v / 8; k = e % lv; };
+    for (int pass = 0; pass < 3; ++pass) {
+      bool improved = false;
+      for (int a = 0; a < extra; ++a) {
+        int ga, ka;
+        where(a, ga, ka);
+        if (set_cost(ga, ka) <= 1) continue;
+        for (int b = 0; b < extra; ++b) {
+          int gb, kb;
+          where(b, gb, kb);
+          if (b == a || (ga == gb && ka == kb)) continue;
+          const int before = set_cost(ga, ka) + set_cost(gb, kb);
+          swap_entries(rowptr[r] + cap + a, rowptr[r] + cap + b);
+          if (set_cost(ga, ka) + set_cost(gb, kb) < before) { improved = true; if (set_cost(ga, ka) <= 1) break; }
+          else swap_entries(rowptr[r] + cap + a, rowptr[r] + cap + b);
+        }
+      }
+      if (!improved) break;
+    }
+  }
+}
+
 // identity_order: keep the caller's gene order and no row cap (dense networks: every row is long and
 // every gene is read, so sorting buys nothing and the GEMM path needs the natural order);
 // pad_to: n_pad is rounded up to a multiple of this (128 for the sparse path, 256 for the GEMM tiles)
@@ -352,6 +446,39 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
   for (int r = 0; r < n; ++r) indeg[r] = rowptr[r + 1] - rowptr[r];
   for (int64_t e = 0; e < nnz; ++e) outdeg[col[e]]++;
 
+  // Entry order inside a row (SCR_ROW_SORT, default on).  The k-th entries of the eight rows of a quarter warp are gathered
+  // by ONE LDS.128: lanes that read the SAME state row cost one wavefront together (a broadcast).  Regulatory networks have
+  // hubs -- a few regulators with hundreds of targets -- so every row lists its regulators hub first (by out-degree), and
+  // the gene order below puts rows with the same leading regulators next to each other: whole quarter warps then read one
+  // or two rows per slot instead of eight scattered ones.
+  std::vector<int> hub_rank(n, 0);
+  std::vector<int32_t> col_sorted;
+  std::vector<double> val_sorted;
+  const bool row_sort = !identity_order && nnz > 0 && env_int("SCR_ROW_SORT", 1) != 0;
+  if (row_sort) {
+    std::vector<int> by_out(n);
+    std::iota(by_out.begin(), by_out.end(), 0);
+    std::stable_sort(by_out.begin(), by_out.end(), [&](int a, int b) { return outdeg[a] > outdeg[b]; });
+    for (int i = 0; i < n; ++i) hub_rank[by_out[i]] = i;
+    col_sorted.assign(col, col + nnz);
+    val_sorted.assign(val, val + nnz);
+    std::vector<int> idx;
+    for (int r = 0; r < n; ++r) {
+      const int d = indeg[r];
+      if (d < 2) continue;
+      idx.resize(d);
+      std::iota(idx.begin(), idx.end(), 0);
+      const int32_t* c0 = col + rowptr[r];
+      std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return hub_rank[c0[a]] < hub_rank[c0[b]]; });
+      for (int k = 0; k < d; ++k) {
+        col_sorted[rowptr[r] + k] = c0[idx[k]];
+        val_sorted[rowptr[r] + k] = val[rowptr[r] + idx[k]];
+      }
+    }
+    col = col_sorted.data();
+    val = val_sorted.data();
+  }
+
   const double mean_in = static_cast<double>(nnz) / n;
   int cap = std::max(8, static_cast<int>(2.0 * mean_in + 0.999));
   cap = env_int("SCR_ROW_CAP", cap);
@@ -371,7 +498,13 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
       const int ca = cls(a), cb = cls(b);
       if (ca != cb) return ca < cb;
-      return indeg[a] > indeg[b];
+      if (indeg[a] != indeg[b]) return indeg[a] > indeg[b];
+      if (!row_sort || ca == 0) return false;
+      // same class, same in-degree: by the regulators they read, hub first (rows sharing them become neighbours)
+      const int32_t *pa = col + rowptr[a], *pb = col + rowptr[b];
+      for (int k = 0; k < indeg[a]; ++k)
+        if (pa[k] != pb[k]) return hub_rank[pa[k]] < hub_rank[pb[k]];
+      return false;
     });
   if (!identity_order && nnz > 0) {
     BankModel bm;
@@ -417,6 +550,8 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
       if (OrderCache::get().orders.size() > 64) OrderCache::get().orders.clear();
       OrderCache::get().orders[okey] = order;
     }
+    if (row_sort && searchable && env_int("SCR_ENTRY_BANKS", 1) != 0)
+      entry_bank_pass(n, rowptr, col_sorted.data(), val_sorted.data(), order, indeg, cap, op.lv, nlong);
     bm.build(order, indeg, nlong);
     op.gather_wavefronts = bm.total();
     op.gather_wavefronts_floor = static_cast<int64_t>(bm.sets.size());
