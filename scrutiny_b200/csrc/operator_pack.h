@@ -13,6 +13,7 @@
 //                 at k*nv_pad + v; ovf_start/ovf_cnt give each long row its chunk range
 //   wblk          128-gene blocks assigned to the wq warps of a cell group (LPT on a cost model)
 #pragma once
+#include <cstdio>
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -555,6 +556,15 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
     bm.build(order, indeg, nlong);
     op.gather_wavefronts = bm.total();
     op.gather_wavefronts_floor = static_cast<int64_t>(bm.sets.size());
+    if (env_int("SCR_PACK_STATS", 0)) {   // developer aid: modelled cost of the read sets by size
+      int64_t cnt[9][9] = {};
+      for (size_t s2 = 0; s2 < bm.sets.size(); ++s2) cnt[std::min<size_t>(8, bm.sets[s2].size())][std::min(8, bm.cost(static_cast<int>(s2)))]++;
+      for (int sz = 0; sz <= 8; ++sz) {
+        std::fprintf(stderr, "read sets with %d entries:", sz);
+        for (int c = 1; c <= 8; ++c) std::fprintf(stderr, " cost%d=%lld", c, static_cast<long long>(cnt[sz][c]));
+        std::fprintf(stderr, "\n");
+      }
+    }
   }
   op.perm.assign(op.n_pad, -1);
   op.inv.assign(n, -1);
