@@ -557,12 +557,22 @@ inline bool pack_operator(int n, int64_t nnz, const int32_t* rowptr, const int32
     op.gather_wavefronts = bm.total();
     op.gather_wavefronts_floor = static_cast<int64_t>(bm.sets.size());
     if (env_int("SCR_PACK_STATS", 0)) {   // developer aid: modelled cost of the read sets by size
-      int64_t cnt[9][9] = {};
-      for (size_t s2 = 0; s2 < bm.sets.size(); ++s2) cnt[std::min<size_t>(8, bm.sets[s2].size())][std::min(8, bm.cost(static_cast<int>(s2)))]++;
-      for (int sz = 0; sz <= 8; ++sz) {
-        std::fprintf(stderr, "read sets with %d entries:", sz);
-        for (int c = 1; c <= 8; ++c) std::fprintf(stderr, " cost%d=%lld", c, static_cast<long long>(cnt[sz][c]));
-        std::fprintf(stderr, "\n");
+      // (the chunk read sets come last: one per 8 chunks and chunk slot)
+      int64_t nchunk_sets = 0;
+      {
+        int64_t nchunks = 0;
+        for (int i = 0; i < nlong; ++i) nchunks += (indeg[order[i]] - cap + op.lv - 1) / op.lv;
+        nchunk_sets = (nchunks + 7) / 8 * op.lv;
+      }
+      for (int part = 0; part < 2; ++part) {
+        int64_t cnt[9][9] = {};
+        const size_t s_lo = part == 0 ? 0 : bm.sets.size() - nchunk_sets, s_hi = part == 0 ? bm.sets.size() - nchunk_sets : bm.sets.size();
+        for (size_t s2 = s_lo; s2 < s_hi; ++s2) cnt[std::min<size_t>(8, bm.sets[s2].size())][std::min(8, bm.cost(static_cast<int>(s2)))]++;
+        for (int sz = 0; sz <= 8; ++sz) {
+          std::fprintf(stderr, "%s read sets with %d entries:", part == 0 ? "tile " : "chunk", sz);
+          for (int c = 1; c <= 8; ++c) std::fprintf(stderr, " cost%d=%lld", c, static_cast<long long>(cnt[sz][c]));
+          std::fprintf(stderr, "\n");
+        }
       }
     }
   }
