@@ -1189,7 +1189,12 @@ int probe_multi_t(scr_ctx* ctx, int32_t nprobes, const int32_t* k, const int64_t
       if (e == cudaSuccess) e = cudaMalloc(&sl.d_counter, sizeof(int));
       if (e == cudaSuccess) e = cudaMalloc(&sl.d_pc, static_cast<size_t>(ctx->op.n_pad) * 2 * ctx->esize());
       if (e == cudaSuccess) e = cudaMalloc(&sl.d_bias, static_cast<size_t>(ctx->op.n_pad) * ctx->esize());
-      if (e != cudaSuccess) { restore(); return fail_cuda(ctx, e, "probe slot"); }
+      if (e != cudaSuccess) {   // (a half-built slot must not be found "ready" by the next call)
+        restore();
+        for (int j = 0; j < i; ++j) cudaStreamSynchronize(ctx->probe_slots[j].stream);
+        free_probe_slots(ctx);
+        return fail_cuda(ctx, e, "probe slot");
+      }
     }
     install(sl);
     offs[i] = off;
