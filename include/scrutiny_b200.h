@@ -63,8 +63,9 @@ int scr_sync(scr_ctx* ctx);
 /* ---- regulatory network: the `gc` argument of developCell (MS:503-504), already divided by
  * alpha (EX:49).  CSR over rows = regulated gene.  Builds the on-chip operator (gene
  * permutation, blocked-ELL tiles, long-row chunks).  Any density is accepted; float32 contexts
- * switch scr_run_phase to the tcgen05 split-precision GEMM stepper (fp16 split by default, SCR_DENSE_KIND=tf32 for 3xTF32) when nnz >= 5 % of n^2 (the sparse
- * operator is still built: the probe and float64 contexts use it). */
+ * switch scr_run_phase to the tcgen05 split-precision GEMM stepper (fp16 split by default,
+ * SCR_DENSE_KIND=tf32 for 3xTF32) when nnz >= 5 % of n^2 (the sparse operator is still built:
+ * float64 contexts use it). */
 int scr_set_network_csr(scr_ctx* ctx, int32_t n, int64_t nnz, const int32_t* rowptr,
                         const int32_t* col, const double* val);
 /* same from a dense row-major (n, n) float64 matrix (what the reference passes around) */
@@ -204,7 +205,8 @@ int scr_debug_noise(scr_ctx* ctx, int64_t global_cell, uint32_t step, double sig
                     uint32_t stream, double* out /* n */);
 /* kernel launches issued by this context so far (bench.py reports gpu_launches) */
 int64_t scr_launch_count(const scr_ctx* ctx);
-/* launches of a specific stepper so far: which = 0 persistent sparse stepper (phases), 1 dense GEMM stepper (steps) */
+/* launches of a specific stepper so far: which = 0 persistent sparse stepper (one per phase), 1 dense GEMM stepper (one per
+ * timestep of a large batch; one per phase or probe chunk when the steps run inside the launch) */
 int64_t scr_debug_path_launches(const scr_ctx* ctx, int which);
 /* device-time of the last scr_run_phase stepping kernel in milliseconds (CUDA events on the
  * context's stream); < 0 if none yet */
