@@ -14,6 +14,7 @@ probe's iteration sum is the only value exchanged per node, the per-gene sums th
 exchanged in the read-out.  Noise is keyed by global cell id, so the result does not depend on
 the number of ranks.
 """
+import os
 import random
 from concurrent.futures import ThreadPoolExecutor
 
@@ -267,9 +268,23 @@ class LineageSimulation:
 
             live_ids = {int(p["node"].identifier) for p in live}
 
+            # Order of the phases: the reference walks the tree depth first (MS:607-612); subtrees touch disjoint cells and all
+            # per-cell randomness is keyed by (seed, node, cell, iterations done), so any order that steps a node after its
+            # parent gives the same states.  Level order (default; SCR_LEVEL_ORDER=0 keeps the depth-first walk) makes ALL
+            # nodes of a tree level ready together: one round of side-by-side probes per level instead of one per parent.
+            by_id = {int(p["node"].identifier): j for j, p in enumerate(live)}
+            depth = []
+            for p in live:
+                d, up = 0, p["parent"]
+                while up in by_id:
+                    d, up = d + 1, live[by_id[up]]["parent"]
+                depth.append(d)
+            level_order = os.environ.get("SCR_LEVEL_ORDER", "1") != "0"
+            sched = sorted(range(len(live)), key=lambda j: (depth[j], j)) if level_order else list(range(len(live)))
+
             def probe_ready(first):
                 # ready = not probed yet and nothing above it is still to be stepped (an empty parent type never steps: MS:579-580)
-                batch = [j for j in range(first, len(live)) if j not in T_of
+                batch = [j for j in sched if j not in T_of
                          and (live[j]["parent"] not in live_ids or live[j]["parent"] in stepped)]
                 mine = [picks[j][(picks[j] >= self.lo) & (picks[j] < self.hi)] - self.lo for j in batch]
                 totals = np.zeros(len(batch))
@@ -290,7 +305,8 @@ class LineageSimulation:
                 for b, j in enumerate(batch):
                     T_of[j] = int(float(totals[b]) / cellsToSample) - convDistAvgNum
 
-            for i, (p, draw) in enumerate(zip(live, draws)):
+            for at, i in enumerate(sched):
+                p, draw = live[i], draws[i]
                 node, mem = p["node"], p["members"]
                 if fixed_iterations is None:
                     if i not in T_of:
@@ -307,7 +323,7 @@ class LineageSimulation:
                 else:
                     steps[:nmem] = poisson_quantile(draw.result(), T)                          # members k ~ Poisson(T) (MS:591)
                 base = base_f.result() if base_f is not None else iters[ids]
-                next_ids = live[i + 1]["ids"] if i + 1 < len(live) else None
+                next_ids = live[sched[at + 1]]["ids"] if at + 1 < len(sched) else None
                 base_f = pool.submit(bookkeeping, ids, steps, next_ids)
                 if len(ids) and T > 0:
                     self.eng.run_phase(ids, steps, node.proj, node.const, step_base=base, dt=timeStep,

@@ -217,3 +217,47 @@ def test_batched_sibling_probes_give_the_sequential_schedule(tmp_path):
     assert getattr(e1, "multi_calls", 0) == 1 and getattr(e2, "multi_calls", 0) == 0   # nodes 1 and 2 are siblings
     assert s1.node_iterations == s2.node_iterations and len(s1.node_iterations) == 3
     assert np.array_equal(e1.X, e2.X) and np.array_equal(r1["iterations"], r2["iterations"])
+
+
+def test_level_order_of_the_phases_gives_the_depth_first_result(monkeypatch):
+    """run_all steps the nodes level by level (all probes of a level side by side) instead of the reference's depth-first
+    walk (MS:607-612): subtrees touch disjoint cells and the noise is keyed by (seed, node, cell, iterations done), so
+    states, iteration counts, types and the probes' T are those of the depth-first order (SCR_LEVEL_ORDER=0)."""
+    sys.path.insert(0, ROOT)
+    from scrutiny_b200.lineage import Tree
+    from scrutiny_b200.simulate import Comm, LineageSimulation
+    rng = np.random.RandomState(8)
+    n, cells = 20, 70
+    W = (rng.rand(n, n) < 0.2) * rng.randn(n, n) / 0.7
+    parents = [-1, 0, 0, 1, 1, 2, 2]
+    bounds = [0, 10, 20, 30, 40, 50, 60, 70]
+    tree = Tree()
+    tree.add_head(-1, [], np.zeros(n), np.ones(n), 0)
+    for k, par in enumerate(parents):
+        proj = np.ones(n)
+        const = np.zeros(n)
+        proj[k] = 0
+        const[k] = 1.0 if k % 2 else -1.0
+        tree.add_node(k, np.arange(bounds[k], bounds[k + 1]), const, proj, 0, par)
+    below = {3: [], 4: [], 5: [], 6: [], 1: [3, 4], 2: [5, 6], 0: [1, 2, 3, 4, 5, 6]}
+    for k, kids in below.items():
+        tree[k].setChildCellTypeMembers(np.concatenate([np.arange(bounds[c], bounds[c + 1]) for c in kids]) if kids
+                                        else np.zeros(0, dtype=np.int64))
+    tree[-1].setChildCellTypeMembers(np.arange(cells))
+    x0 = rng.uniform(-1, 1, n)
+    kw = dict(seed=5, cellsToSample=4, maxNumIterations=40, convDistAvgNum=4, convergenceThreshold=0.7, do_counts=False)
+
+    def run(level):
+        monkeypatch.setenv("SCR_LEVEL_ORDER", "1" if level else "0")
+        eng = OracleEngine(W, cells, 0)
+        eng.set_states_broadcast(x0)
+        sim = LineageSimulation(eng, cells, 0, cells, comm=Comm(single=True), seed=5)
+        res = sim.run_all(tree, **kw)
+        return eng, sim, res
+
+    e1, s1, r1 = run(True)
+    e0, s0, r0 = run(False)
+    assert getattr(e1, "multi_calls", 0) == 2 and getattr(e0, "multi_calls", 0) == 3    # {1,2},{3,4,5,6} vs {1,2},{3,4},{5,6}
+    assert s1.node_iterations == s0.node_iterations and len(s1.node_iterations) == 7
+    assert np.array_equal(e1.X, e0.X) and np.array_equal(r1["iterations"], r0["iterations"])
+    assert np.array_equal(r1["types"], r0["types"]) and r1["local_cell_steps"] == r0["local_cell_steps"]
