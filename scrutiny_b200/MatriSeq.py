@@ -342,7 +342,9 @@ def transformData(n, cells, finalCellStates, dropoutProportion=0.0, cellRadiusDi
     ``artefacts.CountMatrix`` (unsigned bytes + overflow list on the host, 1/8 of the bytes, reads like the reference's
     array); None (default) -> dense up to ``artefacts.DENSE_LIMIT`` bytes (2 GiB), compact above.
     ``capture`` (extension, parity aid): a dict that receives the Poisson rate matrix ``lambda`` (n, cells) and the
-    per-gene ``shift`` the read-out used."""
+    per-gene ``shift`` the read-out used.
+    Like the reference (MS:858-862) the dense path leaves ``finalCellStates`` shifted to the new gene levels in place; the
+    compact path (10^6-cell runs) leaves it untouched."""
     key = ("readout", __device, precision or __precision)
     slot = _engine_cache.get(key)
     if slot is None or slot[0] != n:                                             # the read-out needs no network: a context
@@ -368,6 +370,10 @@ def transformData(n, cells, finalCellStates, dropoutProportion=0.0, cellRadiusDi
         eng.close()
         raise
     if dense:
+        # MS:858-862 shifts the caller's matrix in place before rebinding the name at MS:873: same side effect here
+        if (isinstance(finalCellStates, np.ndarray) and finalCellStates.flags.writeable
+                and np.issubdtype(finalCellStates.dtype, np.floating)):
+            finalCellStates += sim.last_shift[:, None]
         return np.ascontiguousarray(counts.T, dtype=np.float64), size
     return _artefacts.CountMatrix([counts[0]], [counts[1]], n), size
 

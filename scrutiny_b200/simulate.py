@@ -154,7 +154,7 @@ class LineageSimulation:
         """transformData (MS:816-891) for this rank's cells.  Returns (counts (cells_local, n) int32,
         all cellSizeFactors); with ``dtype`` "uint8" / "uint16" the first item is ``(compact counts, overflow rows)``.
         ``capture`` (dict, parity aid) receives ``lambda`` (n, cells_local) and ``shift``."""
-        shift = self.gene_shift(expScale=expScale, **kw)
+        shift = self.last_shift = self.gene_shift(expScale=expScale, **kw)
         size = np.random.normal(loc=1, scale=cellRadiusDisp, size=self.cells) ** 3   # MS:875-876
         if nb_dispersion or dropout:                                             # default-off extensions (scr_counts_ext)
             got = self.eng.counts_ext(shift, size[self.lo:self.hi], nb_dispersion=nb_dispersion, dropout=dropout,

@@ -170,3 +170,60 @@ def test_module_surface_matches_the_reference():
                 assert repr(ours[i].default) == pdefault, (name, pname, ours[i].default, pdefault)
         for extra in ours[len(ref["params"]):]:
             assert extra.default is not inspect.Parameter.empty, (name, extra.name)
+
+
+class _ReadoutDouble:
+    """Stand-in for engine.Engine on the read-out path only (no GPU here): what the host code of
+    MatriSeq.transformData asks of the library -- per-gene sums in, lambda = exp(expScale (S + shift)) size out."""
+
+    def __init__(self, device=0, precision="f32"):
+        self.cells, self.n = 0, 0
+
+    def set_genes(self, n):
+        self.n = n
+
+    def alloc_cells(self, cells, global_offset=0):
+        self.cells = cells
+
+    def set_states(self, S, cell0=0):
+        self.X = np.array(S, dtype=np.float64).T.copy()
+
+    def gene_sums(self):
+        return self.X.sum(axis=0)
+
+    def counts(self, shift, size_factors, exp_scale=1.0, seed=0, out=None, out_device_ptr=None, want_lambda=False, **kw):
+        lam = np.maximum(np.exp(exp_scale * (self.X + shift[None, :])) * np.asarray(size_factors)[:, None], 0.0)
+        got = np.floor(lam).astype(np.int32)
+        return (got, lam) if want_lambda else got
+
+    def close(self):
+        pass
+
+
+def test_transform_data_host_side_follows_the_reference(monkeypatch):
+    """Host half of transformData (MS:851-878) through the module function with the library replaced by a double:
+    the same gamma / normal draws from numpy's stream, the same per-gene shift, the same Poisson rates, and the
+    reference's side effect on its argument (MS:858-862 shift the caller's matrix in place)."""
+    import scrutiny_b200.MatriSeq as ms
+    from oracle import matriseq_port as port
+    monkeypatch.setattr(ms, "Engine", _ReadoutDouble)
+    n, cells = 23, 17
+    rng = np.random.RandomState(5)
+    S = rng.uniform(-1, 1, size=(n, cells))
+    for kw in (dict(), dict(gammaDistMean=False, geneScale=0.3, expLambda=0.7), dict(expScale=1.7, cellRadiusDisp=0.3)):
+        ms.init(outputDir=None, seed=11, verbose=False)
+        mine, cap = S.copy(), {}
+        counts, size = ms.transformData(n, cells, mine, capture=cap, **kw)
+        seed_all(11)
+        theirs, ref = S.copy(), {}
+
+        class NoDraw(port.Draws):
+            def poisson(self, lam):
+                return np.floor(lam)
+        ref_counts, ref_size = port.transform_data(n, cells, theirs, draws=NoDraw(), capture=ref, **kw)
+        assert np.array_equal(size, ref_size)
+        assert np.allclose(mine, theirs, rtol=0, atol=1e-12) and not np.allclose(mine, S)       # in-place shift
+        assert np.allclose(cap["lambda"], ref["lambda"], rtol=1e-12)
+        assert counts.shape == (n, cells) and counts.dtype == np.float64
+        assert np.abs(counts - ref_counts).max() <= 1                                           # floor of rates 1e-12 apart
+    ms.init(outputDir=None, seed=1337, verbose=False)                                           # drops the double
