@@ -182,6 +182,85 @@ def case_regnet():
     np.savez_compressed(os.path.join(OUT, "regnet.npz"), **out)
 
 
+# ---- round 2 additions: deeper lineages, two roots, per-gene mean levels -------------------------------------
+TREE7 = dict(n=30, parents=[-1, 0, 0, 1, 1, 2, 2], num=[50, 52, 51, 55, 50, 53, 50], props=[0.05, 0.1, 0.1, 0.15, 0.15, 0.2, 0.2])
+TWO_ROOTS = dict(n=26, parents=[-1, -1, 0, 1], num=[51, 50, 52, 50], props=[0.1, 0.1, 0.2, 0.2])
+
+
+def case_pipeline7(ms):
+    """The example.py call sequence on config c2's tree shape (4 leaves, 7 types, depth 3) with a 'Random' network and a
+    per-gene geneMeanLevels VECTOR in generateInitialStates / findOptimalAlpha (MS:340, 368; the reference broadcasts
+    x - geneMeanLevels at MS:530).  Children run with the defaults of MS:546-554 (quirk R1), so every type holds >= 50 cells."""
+    seed_all(ms, 77)
+    n, cells = TREE7["n"], sum(TREE7["num"])
+    gc, tf = ms.generateGeneCorrelationMatrix(n, "Random", networkSparsity=0.85)
+    tree, projM, constM = ms.formCellTypeTree(n, cells, TREE7["parents"], TREE7["num"], TREE7["props"], tf, [0] * 7)
+    mu = 0.001 * np.cos(np.arange(n))    # MS:535 adds mu EVERY step: |mu| / dt must stay below the threshold
+    init = ms.generateInitialStates(n, cells, geneMeanLevels=mu)
+    init0 = init.copy()
+    alpha = ms.findOptimalAlpha(n, gc, tree, init, numToSample=8, maxNumIterations=300, convDistAvgNum=10,
+                                convergenceThreshold=0.25, geneMeanLevels=mu)
+    gc_unscaled = gc.copy()
+    gc = gc / alpha
+    types = np.zeros(cells, dtype="int64")
+    iters = np.zeros(cells, dtype="int64")
+    ms.findAllNextStates(gc, tree.head(), tree, init, types, iters)
+    final_states = init.copy()
+    counts, size = ms.transformData(n, cells, init)
+    out = dict(gc_unscaled=gc_unscaled, tf=tf, projM=projM, constM=constM, mu=mu, init=init0, alpha=alpha,
+               final_states=final_states, types=types, iters=iters, counts=counts, size=size,
+               head_children=np.array(tree.head().children))
+    for t in range(7):
+        out["members%d" % t] = np.array(tree[t].cellTypeMembers)
+        out["below%d" % t] = np.array(tree[t].childCellTypeMembers, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "pipeline7.npz"), **out)
+
+
+def case_two_roots(ms):
+    """Two root types (parents [-1, -1, 0, 1]): findOptimalAlpha probes with proj = const = 0 (MS:433-435, quirk R2), the
+    walk visits both subtrees (MS:607-612)."""
+    seed_all(ms, 88)
+    n, cells = TWO_ROOTS["n"], sum(TWO_ROOTS["num"])
+    gc, tf = ms.generateGeneCorrelationMatrix(n, "SimulatedPowerLaw", powerLawExponent=2.2, normalizeWRows=True)
+    tree, projM, constM = ms.formCellTypeTree(n, cells, TWO_ROOTS["parents"], TWO_ROOTS["num"], TWO_ROOTS["props"], tf,
+                                              [0] * 4)
+    init = ms.generateInitialStates(n, cells, sameInitialCell=False)
+    init0 = init.copy()
+    alpha = ms.findOptimalAlpha(n, gc, tree, init, numToSample=6, maxNumIterations=200, convDistAvgNum=20)
+    gc_unscaled = gc.copy()
+    gc = gc / 0.3                                             # the walk itself at a gentler gain than the search's 0.02
+    types = np.zeros(cells, dtype="int64")
+    iters = np.zeros(cells, dtype="int64")
+    ms.findAllNextStates(gc, tree.head(), tree, init, types, iters)
+    out = dict(gc_unscaled=gc_unscaled, tf=tf, projM=projM, constM=constM, init=init0, alpha=alpha, final_states=init.copy(),
+               types=types, iters=iters, head_children=np.array(tree.head().children))
+    for t in range(4):
+        out["members%d" % t] = np.array(tree[t].cellTypeMembers)
+        out["below%d" % t] = np.array(tree[t].childCellTypeMembers, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "two_roots.npz"), **out)
+
+
+def case_mu_vector(ms):
+    """findAllNextStates started AT a type node (so its keyword arguments apply, quirk R1) with a per-gene geneMeanLevels
+    vector and non-default step / noise / thresholds."""
+    seed_all(ms, 99)
+    n, cells = 28, 40
+    gc, tf = ms.generateGeneCorrelationMatrix(n, "Random", networkSparsity=0.8)
+    gc = gc / 1.2
+    tree, projM, constM = ms.formCellTypeTree(n, cells, [-1], [40], [0.2], tf, [0])
+    mu = np.linspace(-0.003, 0.003, n)     # small for the same reason (MS:535)
+    states = ms.generateInitialStates(n, cells, sameInitialCell=False, geneMeanLevels=mu)
+    init = states.copy()
+    types = np.zeros(cells, dtype="int64"); iters = np.zeros(cells, dtype="int64")
+    ms.findAllNextStates(gc, tree[0], tree, states, types, iters, maxNumIterations=160, convDistAvgNum=8, cellsToSample=9,
+                         convergenceThreshold=0.18, noiseDisp=0.03, timeStep=0.02, geneMeanLevels=mu)
+    np.savez_compressed(os.path.join(OUT, "mu_vector.npz"), gc=gc, mu=mu, init=init, final=states, types=types, iters=iters,
+                        proj=tree[0].proj, const=tree[0].const)
+
+
+ROUND2_CASES = (case_pipeline7, case_two_roots, case_mu_vector)
+
+
 def main():
     if not rh.available():
         sys.exit("reference not available; fixtures can only be regenerated in the build container")
@@ -193,6 +272,9 @@ def main():
         print("wrote", fn.__name__)
     case_regnet()
     print("wrote case_regnet")
+    for fn in ROUND2_CASES:
+        fn(ms)
+        print("wrote", fn.__name__)
 
 
 if __name__ == "__main__":

@@ -227,3 +227,32 @@ def test_transform_data_host_side_follows_the_reference(monkeypatch):
         assert counts.shape == (n, cells) and counts.dtype == np.float64
         assert np.abs(counts - ref_counts).max() <= 1                                           # floor of rates 1e-12 apart
     ms.init(outputDir=None, seed=1337, verbose=False)                                           # drops the double
+
+
+def test_deeper_trees_match_reference(golden):
+    """formCellTypeTree / generateInitialStates of the module on config c2's tree shape (7 types, depth 3, 'Random'
+    network, per-gene mean levels) and on a two-root tree with a row-normalised power-law network: gene for gene and
+    member for member what the unmodified reference built (tests/golden/pipeline7.npz, two_roots.npz)."""
+    import scrutiny_b200.MatriSeq as ms
+    from test_oracle_golden import TREE7, TWO_ROOTS
+    for name, seed, spec, net in (("pipeline7", 77, TREE7, dict(networkStructure="Random", networkSparsity=0.85)),
+                                  ("two_roots", 88, TWO_ROOTS, dict(networkStructure="SimulatedPowerLaw", powerLawExponent=2.2,
+                                                                    normalizeWRows=True))):
+        g = golden(name)
+        ms.init(outputDir=None, seed=seed, verbose=False)
+        n, cells, kinds = spec["n"], sum(spec["num"]), len(spec["num"])
+        gc, tf = ms.generateGeneCorrelationMatrix(n, **net)
+        assert np.array_equal(gc, g["gc_unscaled"]) and np.array_equal(tf, g["tf"])
+        tree, projM, constM = ms.formCellTypeTree(n, cells, spec["parents"], spec["num"], spec["props"], tf, [0] * kinds)
+        assert np.array_equal(projM, g["projM"]) and np.array_equal(constM, g["constM"])
+        assert list(tree.head().children) == list(g["head_children"])
+        for t in range(kinds):
+            assert list(tree[t].cellTypeMembers) == list(g["members%d" % t])
+            assert list(tree[t].childCellTypeMembers) == list(g["below%d" % t])
+        if name == "pipeline7":
+            init = ms.generateInitialStates(n, cells, geneMeanLevels=g["mu"])
+        else:
+            init = ms.generateInitialStates(n, cells, sameInitialCell=False)
+        assert np.array_equal(init, g["init"])
+        want = [-1, 0, 1, 3, 4, 2, 5, 6] if kinds == 7 else [-1, 0, 2, 1, 3]             # depth first, MS:607-612
+        assert [nd.identifier for nd in tree.walk()] == want

@@ -142,3 +142,107 @@ def test_poisson_development_mode(golden):
                          maxNumIterations=90, convDistAvgNum=6, cellsToSample=7,
                          convergenceThreshold=0.4, noiseDisp=0.02, timeStep=0.05)
     assert np.array_equal(iters, g["iters"]) and np.array_equal(states, g["final"])
+
+
+# ---- round 2 fixtures: deeper lineage (config c2's tree shape), two roots, per-gene mean levels ---------------------------
+TREE7 = dict(n=30, parents=[-1, 0, 0, 1, 1, 2, 2], num=[50, 52, 51, 55, 50, 53, 50], props=[0.05, 0.1, 0.1, 0.15, 0.15, 0.2, 0.2])
+TWO_ROOTS = dict(n=26, parents=[-1, -1, 0, 1], num=[51, 50, 52, 50], props=[0.1, 0.1, 0.2, 0.2])
+
+
+def replay_pipeline7(draws=None, log=None, read_out=True):
+    """oracle/make_golden.py case_pipeline7 through the port."""
+    draws = draws or port.Draws()
+    seed_all(77)
+    n, cells = TREE7["n"], sum(TREE7["num"])
+    gc, tf = port.generate_network(n, "Random", networkSparsity=0.85)
+    tree, projM, constM = port.form_tree(n, cells, TREE7["parents"], TREE7["num"], TREE7["props"], tf, [0] * 7)
+    mu = 0.001 * np.cos(np.arange(n))
+    init = port.initial_states(n, cells, geneMeanLevels=mu)
+    alpha = port.optimal_alpha(n, gc, tree, init, 8, maxNumIterations=300, convDistAvgNum=10, convergenceThreshold=0.25,
+                               geneMeanLevels=mu)
+    out = dict(n=n, cells=cells, gc_unscaled=gc.copy(), tf=tf, tree=tree, projM=projM, constM=constM, mu=mu, init=init.copy(),
+               alpha=alpha)
+    gc = gc / alpha
+    types = np.zeros(cells, dtype="int64")
+    iters = np.zeros(cells, dtype="int64")
+    port.all_next_states(gc, tree.head(), tree, init, types, iters, draws=draws, log=log)
+    out.update(gc=gc, final_states=init.copy(), types=types, iters=iters)
+    if read_out:
+        out["counts"], out["size"] = port.transform_data(n, cells, init)
+    return out
+
+
+def replay_two_roots(draws=None, log=None):
+    """oracle/make_golden.py case_two_roots through the port."""
+    draws = draws or port.Draws()
+    seed_all(88)
+    n, cells = TWO_ROOTS["n"], sum(TWO_ROOTS["num"])
+    gc, tf = port.generate_network(n, "SimulatedPowerLaw", powerLawExponent=2.2, normalizeWRows=True)
+    tree, projM, constM = port.form_tree(n, cells, TWO_ROOTS["parents"], TWO_ROOTS["num"], TWO_ROOTS["props"], tf, [0] * 4)
+    init = port.initial_states(n, cells, sameInitialCell=False)
+    alpha = port.optimal_alpha(n, gc, tree, init, 6, maxNumIterations=200, convDistAvgNum=20)
+    out = dict(n=n, cells=cells, gc_unscaled=gc.copy(), tf=tf, tree=tree, projM=projM, constM=constM, init=init.copy(), alpha=alpha)
+    gc = gc / 0.3
+    types = np.zeros(cells, dtype="int64")
+    iters = np.zeros(cells, dtype="int64")
+    port.all_next_states(gc, tree.head(), tree, init, types, iters, draws=draws, log=log)
+    out.update(gc=gc, final_states=init.copy(), types=types, iters=iters)
+    return out
+
+
+MU_KW = dict(maxNumIterations=160, convDistAvgNum=8, cellsToSample=9, convergenceThreshold=0.18, noiseDisp=0.03, timeStep=0.02)
+
+
+def replay_mu_vector(draws=None, log=None):
+    """oracle/make_golden.py case_mu_vector through the port."""
+    draws = draws or port.Draws()
+    seed_all(99)
+    n, cells = 28, 40
+    gc, tf = port.generate_network(n, "Random", networkSparsity=0.8)
+    gc = gc / 1.2
+    tree, _, _ = port.form_tree(n, cells, [-1], [40], [0.2], tf, [0])
+    mu = np.linspace(-0.003, 0.003, n)
+    states = port.initial_states(n, cells, sameInitialCell=False, geneMeanLevels=mu)
+    out = dict(n=n, cells=cells, gc=gc, tree=tree, mu=mu, init=states.copy())
+    types = np.zeros(cells, dtype="int64")
+    iters = np.zeros(cells, dtype="int64")
+    port.all_next_states(gc, tree[0], tree, states, types, iters, geneMeanLevels=mu, draws=draws, log=log, **MU_KW)
+    out.update(final_states=states.copy(), types=types, iters=iters)
+    return out
+
+
+def _same_tree(o, g, kinds):
+    assert np.array_equal(o["gc_unscaled"], g["gc_unscaled"]) and np.array_equal(o["tf"], g["tf"])
+    assert np.array_equal(o["projM"], g["projM"]) and np.array_equal(o["constM"], g["constM"])
+    assert list(o["tree"].head().children) == list(g["head_children"])
+    for t in range(kinds):
+        assert list(o["tree"][t].cellTypeMembers) == list(g["members%d" % t])
+        assert list(o["tree"][t].childCellTypeMembers) == list(g["below%d" % t])
+    assert np.array_equal(o["init"], g["init"])
+    assert o["alpha"] == float(g["alpha"])
+
+
+def test_seven_type_pipeline(golden):
+    g = golden("pipeline7")
+    o = replay_pipeline7()
+    _same_tree(o, g, 7)
+    assert np.array_equal(o["types"], g["types"]) and np.array_equal(o["iters"], g["iters"])
+    assert np.array_equal(o["final_states"], g["final_states"])
+    assert np.array_equal(o["size"], g["size"]) and np.array_equal(o["counts"], g["counts"])
+
+
+def test_two_root_lineage(golden):
+    g = golden("two_roots")
+    o = replay_two_roots()
+    _same_tree(o, g, 4)
+    assert abs(o["alpha"] - 0.02) < 1e-15                      # quirk R2: proj = const = 0 converges on the first rung
+    assert np.array_equal(o["types"], g["types"]) and np.array_equal(o["iters"], g["iters"])
+    assert np.array_equal(o["final_states"], g["final_states"])
+
+
+def test_per_gene_mean_levels(golden):
+    g = golden("mu_vector")
+    o = replay_mu_vector()
+    assert np.array_equal(o["gc"], g["gc"]) and np.array_equal(o["init"], g["init"]) and np.array_equal(o["mu"], g["mu"])
+    assert np.array_equal(o["tree"][0].proj, g["proj"]) and np.array_equal(o["tree"][0].const, g["const"])
+    assert np.array_equal(o["iters"], g["iters"]) and np.array_equal(o["final_states"], g["final"])
