@@ -7,9 +7,10 @@ against the final states the reference produced.
   * mu_vector: findAllNextStates started at a type node with a per-gene geneMeanLevels vector (MS:530, 535), dt = 0.02.
 
 Tolerances: float64 context <= 1e-9 (a numpy replay in another summation order lands at 1e-14); float32 context <= 1e-4 where
-the run is short or the gain low (two_roots, mu_vector: a float32 numpy emulation lands at 1e-6), <= 5e-3 for pipeline7 (1200
+the run is short or the gain low (two_roots, mu_vector: a float32 numpy emulation lands at 1e-6), <= 5e-4 for pipeline7 (1200
 steps at gain 10: the emulation lands at 1.5e-5, the device's approximate tanh adds to it; the float64 context is the parity path
-for such runs).  The module-level run (free-running device noise) is checked on what does not depend on the
+for such runs).  Measured on B200 (profiles/r2s3_pytest_golden_lineages.log): float64 1.8e-14 / 3.3e-16 /
+1.7e-16, float32 4.7e-5 / 3.1e-6 / 1.5e-6.  The module-level run (free-running device noise) is checked on what does not depend on the
 noise: types, the tree bookkeeping, and iteration counts inside the reference's range."""
 import numpy as np
 import pytest
@@ -55,7 +56,7 @@ def test_seven_type_lineage_against_reference_output(golden):
     rec, log = port.RecordingDraws(), []
     o = tg.replay_pipeline7(draws=rec, log=log, read_out=False)
     assert np.array_equal(o["final_states"], g["final_states"])          # the port run that recorded the noise IS the reference run
-    _replay(o, rec, log, g["final_states"], (("f64", 1e-9), ("f32", 5e-3)))
+    _replay(o, rec, log, g["final_states"], (("f64", 1e-9), ("f32", 5e-4)))
 
 
 def test_two_root_lineage_against_reference_output(golden):
