@@ -1,6 +1,7 @@
 """Host-side pieces of the MatriSeq-compatible module against the reference's golden outputs
 (tree construction, initial states) and the multi-rank bookkeeping of the scheduler."""
 import numpy as np
+import pytest
 
 from conftest import seed_all
 
@@ -256,3 +257,94 @@ def test_deeper_trees_match_reference(golden):
         assert np.array_equal(init, g["init"])
         want = [-1, 0, 1, 3, 4, 2, 5, 6] if kinds == 7 else [-1, 0, 2, 1, 3]             # depth first, MS:607-612
         assert [nd.identifier for nd in tree.walk()] == want
+
+
+def _ladder_noise(rung, pos, step, n, sigma):
+    rs = np.random.RandomState((rung * 1000003 + pos * 7919 + step * 31 + 5) % (2 ** 32))
+    return sigma * rs.randn(n)
+
+
+class _LadderDouble:
+    """Stand-in for engine.Engine on the alpha search only: probes every slot with the port's own loop on gc / w_div, noise
+    a pure function of (rung of the ladder, position in the rung's sample, step) -- what the device generator is keyed by."""
+
+    def __init__(self, device=0, precision="f32"):
+        self.cells = 0
+
+    def set_network(self, gc):
+        self.gc = np.array(gc, dtype=np.float64)
+        self.n = self.gc.shape[0]
+
+    def alloc_cells(self, cells, global_offset=0):
+        self.cells = cells
+
+    def set_states(self, S, cell0=0):
+        self.X = np.array(S, dtype=np.float64)
+
+    def probe(self, sample_ids, proj, const, dt=0.01, sigma=0.05, mu=0.0, thresh=0.1, max_iter=500, avg_num=20, seed=0,
+              stream=0, w_div=None, **kw):
+        from oracle import matriseq_port as port
+        from scrutiny_b200.engine import STREAM_ALPHA
+        per = self.per
+        out = np.zeros(len(sample_ids), dtype=np.int32)
+        for s in sample_ids:
+            rung, pos = (stream - STREAM_ALPHA) + s // per, s % per
+
+            class Keyed(port.Draws):
+                def normal_vec(self, scale, n, tag=None):
+                    return _ladder_noise(rung, pos, tag[2], n, scale)
+            out[s], _ = port.probe_one_cell(self.n, self.gc / w_div[s], dt, self.X[:, s].copy(), proj, const, sigma, mu, thresh,
+                                            max_iter, avg_num, Keyed(), cell=s, stream="alpha")
+        return out
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize("batch", [1, 3, 24])
+def test_batched_alpha_ladder_is_the_sequential_search(monkeypatch, batch):
+    """findOptimalAlpha evaluates ``batch`` rungs per device call; the candidates, the per-rung samples, the switch to 0.01
+    steps after the first partial success (MS:449-451), the stopping rung and the final state of ``random`` must be those of
+    the reference's one-rung-at-a-time loop (MS:438-497) -- here with per-cell initial states so that partial success occurs."""
+    import random
+    import scrutiny_b200.MatriSeq as ms
+    from oracle import matriseq_port as port
+    n, cells, num = 24, 40, 7
+    per = -(-num // 4) * 4
+    _LadderDouble.per = per
+    monkeypatch.setattr(ms, "Engine", _LadderDouble)
+    kw = dict(maxNumIterations=140, convDistAvgNum=10, convergenceThreshold=0.3)
+
+    def inputs(mod_init):
+        mod_init()
+        gc, tf = port.generate_network(n, "Random", networkSparsity=0.7)
+        tree, _, _ = port.form_tree(n, cells, [-1], [cells], [0.1], tf, [0])
+        return gc, tree, port.initial_states(n, cells, sameInitialCell=False)
+
+    gc, tree, states = inputs(lambda: seed_all(123))
+    rungs, samples = [], []
+
+    class Seq(port.Draws):
+        def sample(self, population, k):
+            samples.append(random.sample(population, k))
+            return samples[-1]
+
+        def normal_vec(self, scale, n_, tag=None):
+            return _ladder_noise(len(samples) - 1, samples[-1].index(tag[1]), tag[2], n_, scale)
+    want = port.optimal_alpha(n, gc, tree, states, num, draws=Seq(), log=rungs, **kw)
+    want_state = random.getstate()
+    assert any(0 < r < 1 for _, r in rungs), rungs                    # the case exercises the 0.01 steps
+    assert abs(rungs[-1][0] - rungs[-2][0] - 0.01) < 1e-12
+
+    gc2, tree2, states2 = inputs(lambda: ms.init(outputDir=None, seed=123, verbose=False))
+
+    class ModTree:                                                    # the module reads head().children / [child].proj, .const
+        def head(self):
+            return tree2.head()
+
+        def __getitem__(self, k):
+            return tree2[k]
+    got = ms.findOptimalAlpha(n, gc2, ModTree(), states2, num, batch=batch, **kw)
+    assert got == want
+    assert random.getstate() == want_state
+    ms.init(outputDir=None, seed=1337, verbose=False)
