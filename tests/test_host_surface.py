@@ -348,3 +348,141 @@ def test_batched_alpha_ladder_is_the_sequential_search(monkeypatch, batch):
     assert got == want
     assert random.getstate() == want_state
     ms.init(outputDir=None, seed=1337, verbose=False)
+
+
+def _keyed_noise(stream, cell, step, n, sigma):
+    rs = np.random.RandomState(({"step": 1, "probe": 2}[stream] * 2000003 + int(cell) * 7919 + int(step) * 13) % (2 ** 32))
+    return sigma * rs.randn(n)
+
+
+class _StepperDouble:
+    """Stand-in for engine.Engine on the stepping path: the port's own per-cell loops, noise a pure function of
+    (stream, cell, steps the cell has done) like the device generator's key."""
+
+    def __init__(self, device=0, precision="f32"):
+        self.cells = 0
+
+    def set_network(self, gc):
+        self.gc = np.array(gc, dtype=np.float64)
+        self.n = self.gc.shape[0]
+
+    def alloc_cells(self, cells, global_offset=0):
+        self.cells = cells
+
+    def set_states(self, S, cell0=0):
+        self.X = np.array(S, dtype=np.float64)
+
+    def get_states(self, cell0=0, count=None, out=None):
+        if out is None:
+            return self.X.copy()
+        out[...] = self.X
+        return out
+
+    def _draws(self):
+        from oracle import matriseq_port as port
+
+        class Keyed(port.Draws):
+            def uniform_scalar(self):
+                return 0.0
+
+            def normal_vec(self, scale, n, tag=None):          # tag = (stream, cell, step) as the port passes it
+                return _keyed_noise(tag[0], tag[1], tag[2], n, scale)
+        return Keyed()
+
+    def run_phase(self, cell_ids, steps, proj, const, step_base=None, dt=0.01, sigma=0.05, mu=0.0, seed=0, noise=None):
+        from oracle import matriseq_port as port
+        for c, k, b in zip(cell_ids, steps, step_base if step_base is not None else np.zeros(len(cell_ids), dtype=int)):
+            self.X[:, c] = port.cell_next_state(self.gc, self.n, dt, proj, const, self.X[:, c], int(k), sigma, mu,
+                                                self._draws(), cell=int(c), step0=int(b))
+
+    def probe(self, sample_ids, proj, const, dt=0.01, sigma=0.05, mu=0.0, thresh=0.1, max_iter=500, avg_num=20, seed=0,
+              stream=1, **kw):
+        from oracle import matriseq_port as port
+        return np.array([port.probe_one_cell(self.n, self.gc, dt, self.X[:, c].copy(), proj, const, sigma, mu, thresh, max_iter,
+                                             avg_num, self._draws(), cell=int(c))[0] for c in sample_ids], dtype=np.int32)
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize("compat", [False, True])
+def test_lineage_walk_host_side_follows_the_reference(monkeypatch, compat):
+    """findAllNextStates of the module with the library replaced by a double built on the port's per-cell loops: the walk
+    order, the probe samples (``random.sample``), the member step draws (``np.random.randint``), the type record, the
+    iteration bookkeeping and the in-place update of a NON-contiguous state matrix are those of the reference's recursion
+    (MS:540-612) -- with ``reference_compat=True`` including its habit of dropping the keyword arguments below the node
+    the caller passes (MS:611-612), otherwise forwarding them."""
+    import scrutiny_b200.MatriSeq as ms
+    from oracle import matriseq_port as port
+    monkeypatch.setattr(ms, "Engine", _StepperDouble)
+    n, num = 12, [50, 51, 50]
+    cells = sum(num)
+    user = dict(timeStep=0.02, noiseDisp=0.03, convergenceThreshold=0.3, maxNumIterations=120, convDistAvgNum=6,
+                cellsToSample=11)
+
+    def inputs():
+        gc, tf = port.generate_network(n, "Random", networkSparsity=0.75)
+        tree, _, _ = port.form_tree(n, cells, [-1, 0, 0], num, [0.1, 0.2, 0.2], tf, [0, 0, 0])
+        return gc / 1.5, tree, port.initial_states(n, cells, sameInitialCell=False)
+
+    seed_all(321)
+    gc, tree, want = inputs()
+    wt, wi = np.zeros(cells, dtype="int64"), np.zeros(cells, dtype="int64")
+    port.all_next_states(gc, tree[0], tree, want, wt, wi, forward_kwargs=not compat, draws=_StepperDouble()._draws(),
+                         **user)
+    ms.init(outputDir=None, seed=321, verbose=False)
+    gc2, tree2, init = inputs()
+    wide = np.zeros((n, 2 * cells))
+    states = wide[:, ::2]                                                     # strided columns: not the fast download path
+    states[...] = init
+    gt, gi = np.zeros(cells, dtype="int64"), np.zeros(cells, dtype="int64")
+
+    class ModTree:
+        def walk(self, start):
+            yield start
+            for ch in start.children:
+                yield from self.walk(tree2[ch])
+    assert ms.findAllNextStates(gc2, tree2[0], ModTree(), states, gt, gi, reference_compat=compat, **user) is None
+    assert np.array_equal(gt, wt) and np.array_equal(gi, wi)
+    assert np.array_equal(states, want) and np.array_equal(wide[:, 1::2], np.zeros((n, cells)))
+    assert gi.max() > 100 if compat else gi.max() <= 3 * 120                  # children ran with the defaults / the user's limits
+    ms.init(outputDir=None, seed=1337, verbose=False)
+
+
+def test_single_cell_wrappers_host_side(monkeypatch):
+    """developCell / findCellNextState / findOptimalIterations of the module (MS:503-537, 683-736, 616-680) with the library
+    replaced by the stepping double: argument order, the ``random.sample`` of the probe, the returned shapes and that the
+    caller's arrays stay untouched."""
+    import random
+    import scrutiny_b200.MatriSeq as ms
+    from oracle import matriseq_port as port
+    monkeypatch.setattr(ms, "Engine", _StepperDouble)
+    ms.init(outputDir=None, seed=5, verbose=False)
+    n, cells = 14, 20
+    gc, tf = port.generate_network(n, "Random", networkSparsity=0.7)
+    gc = gc / 1.3
+    states = port.initial_states(n, cells, sameInitialCell=False)
+    keep = states.copy()
+    proj = np.ones(n)
+    proj[tf[:2]] = 0
+    const = np.zeros(n)
+    const[tf[:2]] = [1, -1]
+    draws = _StepperDouble()._draws()
+    x0 = states[:, 3]
+    one = ms.developCell(n, gc, 0.02, x0, proj, const, 0.04, 0.001)
+    assert np.array_equal(one, port.develop_cell(n, gc, 0.02, x0, proj, const, 0.04, 0.001, draws, tag=("step", 0, 0)))
+    many = ms.findCellNextState(gc, n, 0.02, 7, proj, const, x0, 25, 0.04, 0, False)
+    assert np.array_equal(many, port.cell_next_state(gc, n, 0.02, proj, const, x0, 25, 0.04, 0, draws, cell=0))
+    assert many.shape == (n,) and np.array_equal(states, keep)
+    members = list(range(2, cells))
+    st = random.getstate()
+    T = ms.findOptimalIterations(n, gc, 0.02, members, proj, const, 0, 0.3, 0.04, states, 150, 6, 5)
+    after = random.getstate()
+    random.setstate(st)
+    cols = random.sample(members, 5)
+    assert random.getstate() == after
+    # the module probes COPIES placed in slots 0..4 of its context: the double keys the noise by slot
+    its = [port.probe_one_cell(n, gc, 0.02, states[:, c].copy(), proj, const, 0.04, 0, 0.3, 150, 6, draws, cell=slot)[0]
+           for slot, c in enumerate(cols)]
+    assert T == int(sum(its) / 5) - 6 and np.array_equal(states, keep)
+    ms.init(outputDir=None, seed=1337, verbose=False)
