@@ -214,3 +214,42 @@ def test_bad_arguments_are_reported():
     assert e.value.code == -1
     with pytest.raises(engine.ScrutinyError):
         eng.set_network(csr=(np.array([0, 1, 2]), np.array([0, 5]), np.array([1.0, 2.0])), n=2)
+
+
+def test_csr_with_unsorted_duplicate_and_zero_entries():
+    """scr_set_network_csr takes what scipy calls a non-canonical CSR: columns in any order, a column listed twice in a row
+    (entries add up, as in ``gc.dot``), explicit zeros, empty rows, self loops."""
+    eng = engine.Engine(device=-1)
+    rowptr = np.array([0, 3, 5, 5, 6], dtype=np.int32)
+    col = np.array([2, 0, 2, 1, 1, 3], dtype=np.int32)
+    val = np.array([1.0, 2.0, 0.5, 3.0, 0.0, -4.0])
+    eng.set_network(csr=(rowptr, col, val), n=4)
+    x = np.array([1.0, 10.0, 100.0, 1000.0])
+    assert np.array_equal(eng.host_matvec(x), [152.0, 30.0, 0.0, -4000.0])
+
+
+def test_packing_fuzz_against_dense_product():
+    """Random operators of every shape the packer distinguishes (sizes off the 128-gene block, empty rows, rows longer than
+    the cap, hubs read by most rows, a few fully dense rows) in both precisions: the packed operator is the matrix."""
+    rng = np.random.RandomState(2024)
+    for case in range(40):
+        n = int(rng.choice([1, 2, 7, 33, 127, 128, 129, 255, 300, 641, 1025]))
+        W = np.zeros((n, n))
+        density = rng.choice([0.0, 0.002, 0.02, 0.2])
+        mask = rng.rand(n, n) < density
+        W[mask] = rng.randn(int(mask.sum()))
+        for _ in range(int(rng.randint(0, 3))):                       # hubs: one regulator read by most rows
+            W[rng.rand(n) < 0.8, rng.randint(n)] = rng.randn()
+        for _ in range(int(rng.randint(0, 3))):                       # long rows
+            W[rng.randint(n), :] = rng.randn(n) * (rng.rand(n) < rng.choice([0.3, 1.0]))
+        W[rng.rand(n) < 0.1, :] = 0.0                                  # empty rows
+        eng = engine.Engine(device=-1, precision=["f32", "f64"][case % 2])
+        eng.set_network(W)
+        lay = eng.layout()
+        assert lay["n_pad"] % 128 == 0 and lay["n_pad"] >= n
+        perm = eng.gene_order()
+        assert sorted(p for p in perm if p >= 0) == list(range(n))
+        x = rng.randn(n)
+        ref = W @ x
+        assert np.allclose(eng.host_matvec(x), ref, rtol=1e-12, atol=1e-12 * max(1.0, np.abs(ref).max())), (case, n)
+        eng.close()
