@@ -135,3 +135,49 @@ def test_example_sequence_runs_end_to_end(tmp_path):
     ms.saveData(counts, types, gc, projM, constM, size, pseudo)
     out = np.load(tmp_path / "MatriSeq" / "synthscRNAseq.npy")
     assert out.shape == (n, cells) and (np.bincount(types) == 100).all() and iters.max() > 50
+
+
+def test_example_artefacts_resemble_the_ones_the_reference_ships(tmp_path):
+    """the reference pins no values, but it SHIPS the output of its example.py (500 genes, 200 cells, two
+    root types); tests/golden/example_fix_summary.json (oracle/make_fix_summary.py) holds shapes, dtypes and summary statistics
+    of those files.  The same call sequence through this module must write artefacts of the same shapes, dtypes and
+    orientation whose statistics sit inside the spread the reference's own algorithm shows from seed to seed (port, 5 seeds:
+    zero fraction 0.50-0.55, library size 890-1062, T 440-480, 1027-1313 links)."""
+    import json
+    import os
+    import scrutiny_b200.MatriSeq as ms
+    from conftest import GOLDEN
+    fix = json.load(open(os.path.join(GOLDEN, "example_fix_summary.json")))
+    st = fix["stats"]
+    out = tmp_path / "MatriSeq"
+    ms.init(outputDir=str(out), seed=1337, verbose=False)
+    n, cells = 500, 200
+    gc, tf = ms.generateGeneCorrelationMatrix(n=n, networkStructure="SimulatedPowerLaw")
+    tree, projM, constM = ms.formCellTypeTree(n, cells, [-1, -1], [100, 100], [0.0, 0.0], tf, [0, 0])
+    states = ms.generateInitialStates(n, cells)
+    alpha = ms.findOptimalAlpha(n, gc, tree, states, numToSample=50)
+    gc /= alpha
+    types = np.zeros(cells, dtype="int64")
+    iters = np.zeros(cells, dtype="int64")
+    ms.findAllNextStates(gc, tree.head(), tree, states, types, iters)
+    counts, size = ms.transformData(n, cells, states)
+    ms.saveData(counts, types, gc, projM, constM, size, 0.01 * iters)
+    for name in ms.ARTEFACTS:
+        a = np.load(out / (name + ".npy"))
+        assert list(a.shape) == fix[name]["shape"] and a.dtype.str == fix[name]["dtype"], name
+        assert (out / (name + ".gzip")).is_file()
+    c = np.load(out / "synthscRNAseq.npy")
+    assert np.array_equal(c, np.round(c)) and c.min() >= 0 and st["counts_integer_valued"]
+    assert abs((c == 0).mean() - st["zero_fraction"]) < 0.1
+    assert 0.6 * st["mean_library_size"] < c.sum(axis=0).mean() < 1.6 * st["mean_library_size"]
+    assert 0.3 * st["max_count"] < c.max() < 5 * st["max_count"]
+    assert 0.4 * st["median_gene_mean"] < np.median(c.mean(axis=1)) < 2.0 * st["median_gene_mean"]
+    pt = np.load(out / "synthPseudotimes.npy")
+    assert pt.min() >= 0 and 3.5 <= pt.max() <= 4.8 and abs(pt.max() - st["pseudotime_max"]) < 1.0
+    g = np.load(out / "gc.npy")
+    assert 45.0 < np.abs(g).max() <= 50.0 and abs(np.abs(g).max() - st["gc_abs_max"]) < 5.0        # alpha = 0.02 on both sides
+    assert abs(np.count_nonzero(g) - st["gc_nnz"]) < 0.35 * st["gc_nnz"]
+    assert np.bincount(np.load(out / "cellTypesRecord.npy")).tolist() == st["cells_per_type"]
+    assert (np.load(out / "projMatrix.npy") == 1).all() and (np.load(out / "constMatrix.npy") == 0).all()
+    sf = np.cbrt(np.load(out / "cellSizeFactors.npy"))
+    assert abs(sf.mean() - 1.0) < 0.04 and abs(sf.std() - 0.14) < 0.03
