@@ -90,25 +90,54 @@ def build_case():
     return n, cells, W, tree, x0
 
 
-def run_rank(rank, world, port_no, out_path):
+def build_case7():
+    """Config c2's tree shape (7 types, 4 leaves, depth 3) over 70 cells in contiguous blocks of 10: with three ranks most
+    nodes have no member -- and so no probe sample -- on some rank."""
+    from scrutiny_b200.lineage import Tree
+    rng = np.random.RandomState(8)
+    n, cells = 20, 70
+    W = (rng.rand(n, n) < 0.2) * rng.randn(n, n) / 0.7
+    parents = [-1, 0, 0, 1, 1, 2, 2]
+    bounds = [0, 10, 20, 30, 40, 50, 60, 70]
+    tree = Tree()
+    tree.add_head(-1, [], np.zeros(n), np.ones(n), 0)
+    for k, par in enumerate(parents):
+        proj = np.ones(n)
+        const = np.zeros(n)
+        proj[k] = 0
+        const[k] = 1.0 if k % 2 else -1.0
+        tree.add_node(k, np.arange(bounds[k], bounds[k + 1]), const, proj, 0, par)
+    below = {3: [], 4: [], 5: [], 6: [], 1: [3, 4], 2: [5, 6], 0: [1, 2, 3, 4, 5, 6]}
+    for k, kids in below.items():
+        tree[k].setChildCellTypeMembers(np.concatenate([np.arange(bounds[c], bounds[c + 1]) for c in kids]) if kids
+                                        else np.zeros(0, dtype=np.int64))
+    tree[-1].setChildCellTypeMembers(np.arange(cells))
+    x0 = rng.uniform(-1, 1, n)
+    return n, cells, W, tree, x0
+
+
+def run_rank(rank, world, port_no, out_path, case="small"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
     from scrutiny_b200.simulate import Comm, LineageSimulation, shard_bounds
     if world > 1:
         dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port_no, rank=rank, world_size=world)
-    n, cells, W, tree, x0 = build_case()
+    n, cells, W, tree, x0 = build_case() if case == "small" else build_case7()
     lo, hi = shard_bounds(cells, rank, world)
     eng = OracleEngine(W, hi - lo, lo)
     eng.set_states_broadcast(x0)
     sim = LineageSimulation(eng, cells, lo, hi, comm=Comm(), seed=99)
     blocks = []   # the two-rank run samples its counts in three row blocks (bench.py's gather overlap), the one-rank run in one
-    res = sim.run_all(tree, seed=99, cellsToSample=6, maxNumIterations=60, convDistAvgNum=5, convergenceThreshold=0.6,
-                      counts_blocks=3 if world > 1 else 1, on_counts_block=lambda r0, r1: blocks.append((r0, r1)))
+    kw = (dict(cellsToSample=6, maxNumIterations=60, convDistAvgNum=5, convergenceThreshold=0.6) if case == "small" else
+          dict(cellsToSample=4, maxNumIterations=40, convDistAvgNum=4, convergenceThreshold=0.7))
+    res = sim.run_all(tree, seed=99, counts_blocks=3 if world > 1 else 1, on_counts_block=lambda r0, r1: blocks.append((r0, r1)),
+                      **kw)
     assert blocks[0][0] == 0 and blocks[-1][1] == hi - lo and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
     assert len(blocks) == (3 if world > 1 else 1)
     np.savez(out_path, lo=lo, hi=hi, X=eng.X, iters=res["iterations"], types=res["types"], size=res["size_factors"],
-             lam=eng.lam, glob=res["global_cell_steps"], T=np.array(sorted(sim.node_iterations.items())))
+             lam=eng.lam, glob=res["global_cell_steps"], T=np.array(sorted(sim.node_iterations.items())),
+             multi_calls=getattr(eng, "multi_calls", 0))
     if world > 1:
         dist.destroy_process_group()
 
@@ -193,6 +222,36 @@ def test_two_ranks_reproduce_one_rank(tmp_path):
     assert one["iters"].max() > 0 and len(np.unique(one["types"])) == 3
 
 
+def test_three_ranks_on_the_seven_type_tree_reproduce_one_rank(tmp_path):
+    """World size 3 on config c2's tree shape, phases in level order with a level's probes batched: ranks that own no sample
+    of a node (or of a whole level) still take part in that round's all-reduce, and the shards put together are the
+    single-rank run -- states, iteration counts, types, the probes' T, the Poisson rates of the read-out."""
+    import torch.multiprocessing as mp
+    single = str(tmp_path / "single.npz")
+    run_rank(0, 1, 0, single, "tree7")
+    port_no = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = []
+    for r in range(3):
+        p = ctx.Process(target=run_rank, args=(r, 3, port_no, str(tmp_path / ("rank%d.npz" % r)), "tree7"))
+        p.start()
+        procs.append(p)
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    one = np.load(single)
+    parts = [np.load(str(tmp_path / ("rank%d.npz" % r))) for r in range(3)]
+    assert [int(q["lo"]) for q in parts] == [0, 24, 48] and int(parts[2]["hi"]) == 70
+    assert len(one["T"]) == 7 and all(np.array_equal(q["T"], one["T"]) for q in parts)
+    for key in ("X", "iters", "types", "size", "lam"):
+        assert np.allclose(np.concatenate([q[key] for q in parts]), one[key], rtol=1e-13, atol=1e-13), key
+    assert all(float(q["glob"]) == float(one["glob"]) for q in parts) and float(one["glob"]) == float(one["iters"].sum())
+    assert int(one["multi_calls"]) == 2                                   # levels {1, 2} and {3, 4, 5, 6}: one batched call each
+    # rank 0 (cells 0..23) holds samples of nodes 1 and 2 but of no leaf; rank 1 (24..47) of node 2 alone on level 1 (a plain
+    # probe) and of leaves 3, 4; rank 2 (48..69) of leaves only: one batched call each, in different rounds
+    assert [int(q["multi_calls"]) for q in parts] == [1, 1, 1]
+
+
 def test_batched_sibling_probes_give_the_sequential_schedule(tmp_path):
     """run_all probes the children of a node together right after the parent's phase (scr_probe_multi).  An engine without
     probe_multi is probed node by node in the same order; an engine with it gets the siblings in one call.  Iteration
@@ -224,27 +283,8 @@ def test_level_order_of_the_phases_gives_the_depth_first_result(monkeypatch):
     walk (MS:607-612): subtrees touch disjoint cells and the noise is keyed by (seed, node, cell, iterations done), so
     states, iteration counts, types and the probes' T are those of the depth-first order (SCR_LEVEL_ORDER=0)."""
     sys.path.insert(0, ROOT)
-    from scrutiny_b200.lineage import Tree
     from scrutiny_b200.simulate import Comm, LineageSimulation
-    rng = np.random.RandomState(8)
-    n, cells = 20, 70
-    W = (rng.rand(n, n) < 0.2) * rng.randn(n, n) / 0.7
-    parents = [-1, 0, 0, 1, 1, 2, 2]
-    bounds = [0, 10, 20, 30, 40, 50, 60, 70]
-    tree = Tree()
-    tree.add_head(-1, [], np.zeros(n), np.ones(n), 0)
-    for k, par in enumerate(parents):
-        proj = np.ones(n)
-        const = np.zeros(n)
-        proj[k] = 0
-        const[k] = 1.0 if k % 2 else -1.0
-        tree.add_node(k, np.arange(bounds[k], bounds[k + 1]), const, proj, 0, par)
-    below = {3: [], 4: [], 5: [], 6: [], 1: [3, 4], 2: [5, 6], 0: [1, 2, 3, 4, 5, 6]}
-    for k, kids in below.items():
-        tree[k].setChildCellTypeMembers(np.concatenate([np.arange(bounds[c], bounds[c + 1]) for c in kids]) if kids
-                                        else np.zeros(0, dtype=np.int64))
-    tree[-1].setChildCellTypeMembers(np.arange(cells))
-    x0 = rng.uniform(-1, 1, n)
+    n, cells, W, tree, x0 = build_case7()
     kw = dict(seed=5, cellsToSample=4, maxNumIterations=40, convDistAvgNum=4, convergenceThreshold=0.7, do_counts=False)
 
     def run(level):
