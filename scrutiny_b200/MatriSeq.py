@@ -304,6 +304,10 @@ def findOptimalAlpha(n, gc, cellTypeTree, currentStates, numToSample, timeStep=0
         if done:
             break
     random.setstate(states_after[rung - 1])
+    if __verbose and (precision or __precision) == "f32" and alpha < 0.2:
+        # gain 1 / alpha >= 5: float32 rounding is amplified over a few hundred steps
+        print("Note: alpha = %.2f; for trajectories that follow the float64 reference step for step over hundreds of steps "
+              "use init(precision=\"f64\")" % alpha)
     return alpha
 
 
