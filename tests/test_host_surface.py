@@ -486,3 +486,31 @@ def test_single_cell_wrappers_host_side(monkeypatch):
            for slot, c in enumerate(cols)]
     assert T == int(sum(its) / 5) - 6 and np.array_equal(states, keep)
     ms.init(outputDir=None, seed=1337, verbose=False)
+
+
+def test_prepared_mode_draws_are_keyed_by_the_global_cell_id():
+    """The scalable scheduler's per-cell draws (member step counts U{0..T} / Poisson(T), size factors N(1, sd)^3: the
+    counterparts of MS:589-591 and MS:875-876) are pure functions of (seed, node, GLOBAL cell id): any sharding reproduces
+    them, and they have the reference's distributions."""
+    from scipy import stats
+    from scrutiny_b200.simulate import LineageSimulation, hashed_uniform, poisson_quantile
+    ids = np.arange(200000, dtype=np.int64)
+    u = hashed_uniform(1337, 11, ids)
+    assert u.min() >= 0.0 and u.max() < 1.0 and stats.kstest(u, "uniform").pvalue > 1e-3
+    assert np.array_equal(u[5000:9000], hashed_uniform(1337, 11, ids[5000:9000]))                  # any slice: same values
+    assert abs(np.corrcoef(u, hashed_uniform(1337, 13, ids))[0, 1]) < 0.01                          # another node
+    assert abs(np.corrcoef(u, hashed_uniform(1338, 11, ids))[0, 1]) < 0.01                          # another seed
+    assert abs(np.corrcoef(u[:-1], u[1:])[0, 1]) < 0.01                                            # neighbouring cells
+    big = hashed_uniform(1337, 11, ids + 2 ** 40)
+    assert stats.kstest(big, "uniform").pvalue > 1e-3 and abs(np.corrcoef(u, big)[0, 1]) < 0.01    # ids beyond 32 bits
+    T = 37
+    k = np.minimum((u * (T + 1)).astype(np.int32), T)                                              # run_all's U{0..T}
+    assert k.min() == 0 and k.max() == T and stats.chisquare(np.bincount(k, minlength=T + 1)).pvalue > 1e-3
+    kp = poisson_quantile(u, T)                                                                    # run_all's Poisson(T)
+    assert abs(kp.mean() - T) < 0.1 and abs(kp.var() - T) < 0.5
+    cells = 100000
+    whole = LineageSimulation(None, cells, 0, cells, seed=5)._size_factors(0.14)
+    parts = [LineageSimulation(None, cells, lo, hi, seed=5)._size_factors(0.14) for lo, hi in ((0, 33336), (33336, 66672), (66672, cells))]
+    assert np.array_equal(np.concatenate(parts), whole)
+    z = (np.cbrt(whole) - 1.0) / 0.14
+    assert stats.kstest(z, "norm").pvalue > 1e-3 and abs(z.std() - 1) < 0.01
