@@ -514,3 +514,32 @@ def test_prepared_mode_draws_are_keyed_by_the_global_cell_id():
     assert np.array_equal(np.concatenate(parts), whole)
     z = (np.cbrt(whole) - 1.0) / 0.14
     assert stats.kstest(z, "norm").pvalue > 1e-3 and abs(z.std() - 1) < 0.01
+
+
+def test_all_seven_r_files_of_the_reference_round_trip_when_present():
+    """Build container only (the reference tree is absent on the GPU box): every ``R_files/<artefact>.gzip`` the reference
+    ships -- a saved 3-type run, written by R's save(compress=TRUE) through MS:1062-1065 -- is read by rdata.read_rdata
+    with the artefact's name, shape, dtype and orientation, and written back byte for byte."""
+    import gzip
+    import os
+    from oracle import reference_harness as rh
+    from scrutiny_b200 import rdata
+    import scrutiny_b200.MatriSeq as ms
+    folder = os.path.join(rh.REFERENCE_ROOT, "R_files")
+    if not os.path.isfile(os.path.join(folder, "gc.gzip")):
+        pytest.skip("reference tree not present")
+    shapes = {"synthscRNAseq": (500, 100), "cellTypesRecord": (100,), "gc": (500, 500), "projMatrix": (3, 500),
+              "constMatrix": (3, 500), "cellSizeFactors": (100,), "synthPseudotimes": (100,)}
+    got = {}
+    for name in ms.ARTEFACTS:
+        path = os.path.join(folder, name + ".gzip")
+        label, value = rdata.read_rdata(path)
+        assert label == name and value.shape == shapes[name], name
+        assert value.dtype == (np.int64 if name == "cellTypesRecord" else np.float64)
+        assert rdata.serialize(name, value) == gzip.open(path).read(), name
+        got[name] = value
+    counts = got["synthscRNAseq"]
+    assert np.array_equal(counts, np.round(counts)) and counts.min() >= 0           # (genes, cells), integer-valued
+    assert set(np.unique(got["constMatrix"])) <= {-1.0, 0.0, 1.0} and set(np.unique(got["projMatrix"])) <= {0.0, 1.0}
+    assert ((got["projMatrix"] == 0) >= (got["constMatrix"] != 0)).all()              # a constant is only set where proj is 0
+    assert np.bincount(got["cellTypesRecord"]).sum() == 100 and got["synthPseudotimes"].min() >= 0
