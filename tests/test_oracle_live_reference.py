@@ -111,3 +111,29 @@ def test_single_cell_functions():
     assert np.array_equal(port.develop_cell(n, gc, 0.02, x0, proj, const, 0.04, mu), want1)
     assert np.array_equal(port.cell_next_state(gc, n, 0.02, proj, const, x0, 33, 0.04, mu), want2)
     assert port.optimal_iterations(n, gc, 0.02, list(range(12)), proj, const, 0, 0.3, 0.04, states, 140, 7, 5) == wantT
+
+
+@pytest.mark.parametrize("seed,structure,kw", [(241, "SimulatedPowerLaw", dict(powerLawExponent=2.4)),
+                                               (242, "Random", dict(networkSparsity=0.8, normalizeWRows=True)),
+                                               (243, "TRRUST", dict(maxAlphaBeta=7))])
+def test_module_input_producers_against_the_live_reference(seed, structure, kw):
+    """The product's own host functions (scrutiny_b200.MatriSeq), not the port: network as CSR -> dense, tree, initial
+    states, from the same seeds as the unmodified reference."""
+    import scrutiny_b200.MatriSeq as mine
+    ms = both(seed)
+    n = 31
+    want_gc, want_tf = ms.generateGeneCorrelationMatrix(n, structure, **kw)
+    n = want_gc.shape[0]
+    parents, num, props = [-1, 0, 0], [6, 9, 8], [0.2, 0.4, 0.1]
+    want_tree, want_p, want_c = ms.formCellTypeTree(n, sum(num), parents, num, props, want_tf, [0, 0, 0])
+    want_s = ms.generateInitialStates(n, sum(num), sameInitialCell=False)
+    mine.init(outputDir=None, seed=seed, verbose=False)
+    gc, tf = mine.generateGeneCorrelationMatrix(n if structure != "TRRUST" else 31, structure, **kw)
+    assert np.array_equal(gc, want_gc) and np.array_equal(tf, want_tf)
+    tree, p, c = mine.formCellTypeTree(n, sum(num), parents, num, props, tf, [0, 0, 0])
+    assert np.array_equal(p, want_p) and np.array_equal(c, want_c)
+    for t in range(3):
+        assert list(tree[t].cellTypeMembers) == list(want_tree[t].cellTypeMembers)
+        assert list(tree[t].childCellTypeMembers) == list(want_tree[t].childCellTypeMembers)
+    assert np.array_equal(mine.generateInitialStates(n, sum(num), sameInitialCell=False), want_s)
+    mine.init(outputDir=None, seed=1337, verbose=False)
