@@ -543,3 +543,44 @@ def test_all_seven_r_files_of_the_reference_round_trip_when_present():
     assert set(np.unique(got["constMatrix"])) <= {-1.0, 0.0, 1.0} and set(np.unique(got["projMatrix"])) <= {0.0, 1.0}
     assert ((got["projMatrix"] == 0) >= (got["constMatrix"] != 0)).all()              # a constant is only set where proj is 0
     assert np.bincount(got["cellTypesRecord"]).sum() == 100 and got["synthPseudotimes"].min() >= 0
+
+
+def test_tree_display_and_traverse_like_the_reference(capsys):
+    """tree.py:56-99: ``display`` prints the identifiers indented by depth, ``traverse`` yields the per-type description
+    lists depth first (the stepping order) or breadth first -- compared with the reference's own class when it is present."""
+    import importlib
+    import os
+    import sys
+    from oracle import reference_harness as rh
+    from scrutiny_b200 import lineage
+    n = 4
+    spec = [(0, -1), (1, 0), (2, 0), (3, 1), (4, 1), (5, 2), (6, -1)]
+
+    def build(mod):
+        tree = mod.Tree()
+        tree.add_head(-1, [], np.zeros(n), np.ones(n), 0)
+        tree[-1].setChildCellTypeMembers(list(range(9)))              # the reference's Node has no default for it
+        for k, parent in spec:
+            tree.add_node(k, list(range(k + 1)), np.full(n, float(k)), np.ones(n), k * 0.5, parent)
+            tree[k].setChildCellTypeMembers(list(range(2 * k)))
+        return tree
+
+    mine = build(lineage)
+    order = lambda tree, mode: [int(lines[0].split(": ")[1]) for lines in tree.traverse(-1, mode)]     # noqa: E731
+    assert order(mine, lineage._DEPTH) == [-1, 0, 1, 3, 4, 2, 5, 6] == [nd.identifier for nd in mine.walk()]
+    assert order(mine, lineage._BREADTH) == [-1, 0, 6, 1, 2, 3, 4, 5]
+    assert order(mine, lineage._DEPTH)[:1] == [-1] and [int(l[0].split(": ")[1]) for l in mine.traverse(1)] == [1, 3, 4]
+    first = next(iter(mine.traverse(3)))
+    assert first[4] == "Num cellType Members: 4" and first[5] == "Num cellType Child Members: 6" and len(first) == 6
+    mine.display(-1)
+    shown = capsys.readouterr().out
+    assert shown.splitlines()[:4] == ["-1", "\t 0", "\t\t 1", "\t\t\t 3"]
+    if rh.available():
+        if rh._PKG_DIR not in sys.path:
+            sys.path.insert(0, rh._PKG_DIR)
+        theirs = build(importlib.import_module("tree"))
+        for mode in (lineage._DEPTH, lineage._BREADTH):
+            assert list(mine.traverse(-1, mode)) == list(theirs.traverse(-1, mode))
+        assert list(mine.traverse(2)) == list(theirs.traverse(2))
+        theirs.display(-1)
+        assert capsys.readouterr().out == shown
