@@ -157,6 +157,25 @@ def formCellTypeTree(n, cells, cellTypeParents, cellTypeNumCells, cellTypeConstP
     return tree, projMatrix, constMatrix
 
 
+def addTreeChildren(n, cellTypeTree, cellTypeParents, cellTypeMembers, cellTypeConstProps, projInit, constInit, projMatrix,
+                    constMatrix, cellTypeMeans, parentCellType, transcriptionFactors):
+    """MS:243-297, the reference's public recursion helper (``formCellTypeTree`` above uses its own closure): hang every
+    type whose parent is ``parentCellType`` under it -- proj / const inherited through ``getNextProjConst``, rows of
+    ``projMatrix`` / ``constMatrix`` filled in place -- recurse, record on the parent the cells of everything below it, and
+    return those cells followed by ``cellTypeMembers[parentCellType]`` (for the head, -1, that is the LAST type's list: the
+    reference's negative index, MS:297, kept)."""
+    below = []
+    for kind in np.flatnonzero(np.asarray(cellTypeParents) == parentCellType):
+        proj, const = getNextProjConst(n, projInit, constInit, cellTypeConstProps[kind], transcriptionFactors)
+        projMatrix[kind, :] = proj
+        constMatrix[kind, :] = const
+        cellTypeTree.add_node(kind, cellTypeMembers[kind], const, proj, cellTypeMeans[kind], parentCellType)
+        below += addTreeChildren(n, cellTypeTree, cellTypeParents, cellTypeMembers, cellTypeConstProps, proj, const, projMatrix,
+                                 constMatrix, cellTypeMeans, kind, transcriptionFactors)
+    cellTypeTree[parentCellType].setChildCellTypeMembers(below)
+    return below + list(cellTypeMembers[parentCellType])
+
+
 def generateInitialStates(n, cells, sameInitialCell=True, geneMeanLevels=0):
     """MS:340-365 -> (n, cells) float64."""
     first = (2.0 * np.random.rand(n) - 1.0) + geneMeanLevels

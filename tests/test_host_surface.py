@@ -145,19 +145,15 @@ def test_module_surface_matches_the_reference():
     """Drop-in boundary: every public function of the reference's MatriSeq module (tests/golden/
     matriseq_signatures.json, written from the unmodified module by oracle/make_signatures.py) exists here; the functions of
     the simulation path take the reference's parameters first, in order, with the reference's defaults, and anything added
-    comes after them with a default.  The plotting functions are accepted with any arguments (documented no-ops);
-    ``addTreeChildren`` is the reference's private recursion helper of ``formCellTypeTree`` (a closure here)."""
+    comes after them with a default.  The plotting functions are accepted with any arguments (documented no-ops)."""
     import inspect
     import json
     import os
     import scrutiny_b200.MatriSeq as ms
     table = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "matriseq_signatures.json")))
     no_ops = {"analyzeDataBeforeTransformation", "analyzeSCRNAseqData", "plotSCRNAseqData"}
-    private = {"addTreeChildren"}
     assert len(table) == 16
     for name, ref in table.items():
-        if name in private:
-            continue
         assert hasattr(ms, name), name
         if name in no_ops:
             assert getattr(ms, name)(*range(len(ref["params"]))) is None
@@ -584,3 +580,44 @@ def test_tree_display_and_traverse_like_the_reference(capsys):
         assert list(mine.traverse(2)) == list(theirs.traverse(2))
         theirs.display(-1)
         assert capsys.readouterr().out == shown
+
+
+def test_add_tree_children_is_the_reference_helper(golden):
+    """MS:243-297 as a public function: driven the way formCellTypeTree drives it (MS:217-232), it builds the tree of the
+    7-type fixture -- and, in the build container, returns and records exactly what the reference's own helper does."""
+    import random
+    import scrutiny_b200.MatriSeq as ms
+    from scrutiny_b200.lineage import Tree
+    from oracle import reference_harness as rh
+    from test_oracle_golden import TREE7
+    g = golden("pipeline7")
+    n, kinds = TREE7["n"], 7
+    members = [list(g["members%d" % t]) for t in range(kinds)]
+
+    def drive(mod, tree_cls, seed):
+        random.seed(seed)
+        tree = tree_cls()
+        head = tree.add_head(-1, [], np.zeros(n), np.ones(n), 0)
+        head.setChildCellTypeMembers(list(range(sum(TREE7["num"]))))
+        pm, cm = np.zeros((kinds, n)), np.zeros((kinds, n))
+        got = mod.addTreeChildren(n, tree, TREE7["parents"], members, TREE7["props"], np.ones(n), np.zeros(n), pm, cm, [0] * kinds,
+                                  -1, g["tf"])
+        return tree, pm, cm, got
+
+    tree, pm, cm, got = drive(ms, Tree, 4)
+    for t in range(kinds):
+        assert list(tree[t].cellTypeMembers) == members[t] and list(tree[t].childCellTypeMembers) == list(g["below%d" % t])
+        assert np.array_equal(tree[t].proj, pm[t]) and np.array_equal(tree[t].const, cm[t])
+    assert list(tree.head().children) == [0] and got == list(tree.head().childCellTypeMembers) + members[-1]
+    for child, parent in ((1, 0), (3, 1), (6, 2)):                     # constants are inherited down the lineage
+        assert ((pm[child] == 0) >= (pm[parent] == 0)).all()
+        assert np.array_equal(cm[child][pm[parent] == 0], cm[parent][pm[parent] == 0])
+    if rh.available():
+        import importlib
+        import sys
+        ref = rh.load_reference()
+        theirs, rpm, rcm, rgot = drive(ref, importlib.import_module("tree").Tree, 4)
+        assert got == rgot and np.array_equal(pm, rpm) and np.array_equal(cm, rcm)
+        for t in [-1] + list(range(kinds)):
+            assert list(tree[t].children) == list(theirs[t].children)
+            assert list(tree[t].childCellTypeMembers) == list(theirs[t].childCellTypeMembers)
